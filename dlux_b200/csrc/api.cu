@@ -1,0 +1,403 @@
+// extern "C" surface of libdlux_b200.so (see include/dlux_b200.h).
+#include <atomic>
+#include <cstdio>
+#include "common.cuh"
+
+namespace dlux {
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local int g_last_cuda_error = 0;
+
+void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    fprintf(stderr, "[dlux_b200] CUDA error in %s: %s\n", what, cudaGetErrorString(e));
+    return DLUX_ERR_CUDA;
+  }
+  return DLUX_OK;
+}
+
+int launch_zero(float* p, size_t n, cudaStream_t st);
+
+// per-item parameter expansion for the fused poly-PSF path: item = s * L + l
+__global__ void expand_items_kernel(int n_items, int L, const float* __restrict__ scale_out,
+                                    const float* __restrict__ norm, const float* __restrict__ wavenumber,
+                                    int* __restrict__ item_l, float* __restrict__ s_item,
+                                    float* __restrict__ norm_item, float* __restrict__ k_item) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int l = i % L;
+    item_l[i] = l;
+    s_item[i] = scale_out[l];
+    norm_item[i] = norm ? norm[l] : 1.0f;
+    k_item[i] = wavenumber[l];
+  }
+}
+
+struct Bump {
+  char* base;
+  size_t off, cap;
+  bool ok;
+  Bump(void* b, size_t c) : base((char*)b), off(0), cap(c), ok(true) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 1023) & ~(size_t)1023;
+    const size_t bytes = count * sizeof(T);
+    if (base && off + bytes > cap) ok = false;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+  size_t used() const { return (off + 1023) & ~(size_t)1023; }
+};
+
+static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
+  if (precision == DLUX_PREC_FP32) return launch_gemm_simt(p, st);
+  if (precision == DLUX_PREC_3XTF32) return launch_gemm_tc(p, st);
+  return DLUX_ERR_ARG;
+}
+
+static const size_t kChunkBudget = (size_t)1 << 30;  // per-chunk intermediates, bytes
+
+static int mft_chunk(const dlux_mft_desc* d) {
+  const size_t n_src = d->adjoint ? d->n_out : d->n_in;
+  const size_t per_item = 16 * n_src * n_src + 16 * (size_t)d->n_in * d->n_out +
+                          8 * (size_t)(d->n_in + d->n_out);
+  size_t c = kChunkBudget / per_item;
+  if (c < 1) c = 1;
+  if (c > (size_t)d->batch) c = d->batch;
+  return (int)c;
+}
+
+struct MftScratch {
+  float *xin, *uout, *in_pl[4], *mid_pl[4];
+};
+
+static size_t carve_mft(const dlux_mft_desc* d, void* scratch, size_t cap, MftScratch* s, bool* ok) {
+  Bump b(scratch, cap);
+  const size_t c = mft_chunk(d);
+  const size_t n_src = d->adjoint ? d->n_out : d->n_in;
+  s->xin = b.take<float>(c * 2 * d->n_in);
+  s->uout = b.take<float>(c * 2 * d->n_out);
+  for (int i = 0; i < 4; ++i) s->in_pl[i] = b.take<float>(c * n_src * n_src);
+  for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * (size_t)d->n_in * d->n_out);
+  b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
+  if (ok) *ok = b.ok;
+  return b.used();
+}
+
+static int check_mft_desc(const dlux_mft_desc* d) {
+  if (!d) return DLUX_ERR_ARG;
+  if (d->n_in < 1 || d->n_out < 1 || d->batch < 0) return DLUX_ERR_SHAPE;
+  if (d->n_in > 32768 || d->n_out > 32768) return DLUX_ERR_SHAPE;
+  if (d->precision != DLUX_PREC_3XTF32 && d->precision != DLUX_PREC_FP32) return DLUX_ERR_ARG;
+  return DLUX_OK;
+}
+
+// The two stages of one (chunk of) MFT(s); fwd: data [c][N][N] -> out [c][M][M];
+// adjoint: data [c][M][M] -> out [c][N][N].
+static void fill_stage(GemmParams& g, bool adjoint, int stage, int N, int M, int c,
+                       const float* xin, const float* uout, float sign2pi) {
+  // axis 0 = x (contracts the column index j / b), axis 1 = y (row index i / a)
+  const int axis = stage == 0 ? 0 : 1;
+  g.n_items = c;
+  g.item_data = nullptr;
+  g.sign2pi = sign2pi;
+  if (!adjoint) {
+    g.K = N;
+    g.n_out = M;
+    g.rows = stage == 0 ? N : M;
+    g.kvec = xin + (size_t)axis * N;
+    g.kvec_stride = 2 * N;
+    g.nvec = uout + (size_t)axis * M;
+    g.nvec_stride = 2 * M;
+  } else {
+    g.K = M;
+    g.n_out = N;
+    g.rows = stage == 0 ? M : N;
+    g.kvec = uout + (size_t)axis * M;
+    g.kvec_stride = 2 * M;
+    g.nvec = xin + (size_t)axis * N;
+    g.nvec_stride = 2 * N;
+  }
+}
+
+}  // namespace dlux
+
+using namespace dlux;
+
+extern "C" {
+
+int dlux_abi_version(void) { return DLUX_B200_ABI_VERSION; }
+
+const char* dlux_error_string(int code) {
+  switch (code) {
+    case DLUX_OK: return "ok";
+    case DLUX_ERR_ARG: return "invalid argument";
+    case DLUX_ERR_SHAPE: return "unsupported shape";
+    case DLUX_ERR_SCRATCH: return "scratch buffer too small";
+    case DLUX_ERR_CUDA: return "CUDA error";
+    case DLUX_ERR_UNSUPPORTED: return "unsupported on this device";
+    case DLUX_ERR_ALIGN: return "pointer not 16-byte aligned";
+    default: return "unknown error";
+  }
+}
+
+int dlux_last_cuda_error(void) { return g_last_cuda_error; }
+uint64_t dlux_launch_count(void) { return g_launches.load(); }
+
+size_t dlux_mft_scratch_bytes(const dlux_mft_desc* desc) {
+  if (check_mft_desc(desc) != DLUX_OK) return 0;
+  MftScratch s;
+  return carve_mft(desc, nullptr, 0, &s, nullptr);
+}
+
+int dlux_mft_coords(int32_t n_in, int32_t n_out, int32_t batch, const float* scale_out,
+                    const float* shift_xy, const float* delta_xy, float* xin, float* uout,
+                    void* cuda_stream) {
+  if (!scale_out || !xin || !uout) return DLUX_ERR_ARG;
+  if (n_in < 1 || n_out < 1 || batch < 0) return DLUX_ERR_SHAPE;
+  return launch_coords(n_in, n_out, batch, scale_out, shift_xy, delta_xy, 1, xin, uout,
+                       (cudaStream_t)cuda_stream);
+}
+
+int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
+                 const float* shift_xy, const float* delta_xy, const float* norm, void* out,
+                 void* scratch, size_t scratch_bytes, void* cuda_stream) {
+  int rc = check_mft_desc(d);
+  if (rc != DLUX_OK) return rc;
+  if (!in || !out || !scale_out || !scratch) return DLUX_ERR_ARG;
+  if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)scratch) & 15) return DLUX_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  MftScratch s;
+  bool ok = true;
+  carve_mft(d, scratch, scratch_bytes, &s, &ok);
+  if (!ok) return DLUX_ERR_SCRATCH;
+  const int N = d->n_in, M = d->n_out;
+  const bool adj = d->adjoint != 0;
+  const size_t n_src = adj ? M : N, n_dst = adj ? N : M;
+  // forward exponent sign is -2 pi (propagation.py:124), flipped by inverse (:125-126);
+  // the adjoint conjugates the phasors.
+  float sign2pi = (float)(-2.0 * 3.14159265358979323846);
+  if (d->inverse) sign2pi = -sign2pi;
+  if (adj) sign2pi = -sign2pi;
+  const int chunk = mft_chunk(d);
+  for (int b0 = 0; b0 < d->batch; b0 += chunk) {
+    const int c = d->batch - b0 < chunk ? d->batch - b0 : chunk;
+    rc = launch_coords(N, M, c, scale_out + b0, shift_xy ? shift_xy + 2 * (size_t)b0 : nullptr,
+                       delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr, 1, s.xin, s.uout, st);
+    if (rc) return rc;
+    rc = launch_split_c64((const float2*)in + (size_t)b0 * n_src * n_src, (size_t)c * n_src * n_src,
+                          s.in_pl[0], s.in_pl[1], s.in_pl[2], s.in_pl[3], st);
+    if (rc) return rc;
+    GemmParams g{};
+    fill_stage(g, adj, 0, N, M, c, s.xin, s.uout, sign2pi);
+    for (int i = 0; i < 4; ++i) { g.a_planes[i] = s.in_pl[i]; g.out_planes[i] = s.mid_pl[i]; }
+    g.mode = EPI_PLANES;
+    g.scale = nullptr;
+    rc = run_gemm(g, d->precision, st);
+    if (rc) return rc;
+    GemmParams h{};
+    fill_stage(h, adj, 1, N, M, c, s.xin, s.uout, sign2pi);
+    for (int i = 0; i < 4; ++i) h.a_planes[i] = s.mid_pl[i];
+    h.mode = EPI_C64;
+    h.scale = norm ? norm + b0 : nullptr;
+    h.out_c64 = (float2*)out + (size_t)b0 * n_dst * n_dst;
+    rc = run_gemm(h, d->precision, st);
+    if (rc) return rc;
+  }
+  return DLUX_OK;
+}
+
+// ------------------------------------------------------------------ fused poly-PSF
+struct PolyScratch {
+  float* amp_scale;  // 16 B + 256 doubles
+  float* p_pl[4];    // [L][N][N]
+  int* item_l;
+  float *s_item, *norm_item, *k_item;
+  float *xin, *uout;  // per chunk
+  float* mid_pl[4];   // per chunk [c][M*N]
+  float* ebar_pl[4];  // per chunk [c][M*M]  (bwd only; sized always for simplicity)
+  int chunk;
+};
+
+static int poly_chunk(const dlux_polypsf_desc* d) {
+  const size_t N = d->n_pupil, M = d->n_psf;
+  const size_t per_item = 16 * M * N + 16 * M * M + 8 * (N + M);
+  size_t c = kChunkBudget / per_item;
+  const size_t items = (size_t)d->n_sources * d->n_wavels;
+  if (c < 1) c = 1;
+  if (c > items) c = items;
+  return (int)c;
+}
+
+static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, PolyScratch* s, bool* ok) {
+  Bump b(scratch, cap);
+  const size_t N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
+  const size_t items = (size_t)d->n_sources * L;
+  const size_t c = poly_chunk(d);
+  s->chunk = (int)c;
+  s->amp_scale = b.take<float>(4 + 512);
+  for (int i = 0; i < 4; ++i) s->p_pl[i] = b.take<float>(L * N * N);
+  s->item_l = b.take<int>(items);
+  s->s_item = b.take<float>(items);
+  s->norm_item = b.take<float>(items);
+  s->k_item = b.take<float>(items);
+  s->xin = b.take<float>(c * 2 * N);
+  s->uout = b.take<float>(c * 2 * M);
+  for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * M * N);
+  for (int i = 0; i < 4; ++i) s->ebar_pl[i] = b.take<float>(c * M * M);
+  b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
+  if (ok) *ok = b.ok;
+  return b.used();
+}
+
+static int check_poly_desc(const dlux_polypsf_desc* d) {
+  if (!d) return DLUX_ERR_ARG;
+  if (d->n_pupil < 1 || d->n_psf < 1 || d->n_wavels < 1 || d->n_sources < 1) return DLUX_ERR_SHAPE;
+  if (d->n_pupil > 32768 || d->n_psf > 32768) return DLUX_ERR_SHAPE;
+  if ((long long)d->n_wavels * d->n_sources > (1LL << 30)) return DLUX_ERR_SHAPE;
+  if (d->precision != DLUX_PREC_3XTF32 && d->precision != DLUX_PREC_FP32) return DLUX_ERR_ARG;
+  return DLUX_OK;
+}
+
+size_t dlux_polypsf_scratch_bytes(const dlux_polypsf_desc* desc) {
+  if (check_poly_desc(desc) != DLUX_OK) return 0;
+  PolyScratch s;
+  return carve_poly(desc, nullptr, 0, &s, nullptr);
+}
+
+static int poly_prologue(const dlux_polypsf_desc* d, const PolyScratch& s, const float* T,
+                         const float* opd, const float* phase, const float* wavenumber,
+                         const float* scale_out, const float* norm, cudaStream_t st) {
+  const int N = d->n_pupil, L = d->n_wavels;
+  const int items = d->n_sources * L;
+  int rc = launch_power(N, T, d->normalise, s.amp_scale, st);
+  if (rc) return rc;
+  rc = launch_pupil(N, L, T, opd, phase, wavenumber, s.amp_scale, s.p_pl[0], s.p_pl[1], s.p_pl[2],
+                    s.p_pl[3], st);
+  if (rc) return rc;
+  expand_items_kernel<<<(items + 255) / 256 > 1024 ? 1024 : (items + 255) / 256, 256, 0, st>>>(
+      items, L, scale_out, norm, wavenumber, s.item_l, s.s_item, s.norm_item, s.k_item);
+  note_launch();
+  return check_launch("expand_items");
+}
+
+int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* opd,
+                     const float* phase, const float* wavenumber, const float* scale_out,
+                     const float* norm, const float* weights, const float* delta_xy, float* psf,
+                     void* field, void* scratch, size_t scratch_bytes, void* cuda_stream) {
+  int rc = check_poly_desc(d);
+  if (rc != DLUX_OK) return rc;
+  if (!wavenumber || !scale_out || !weights || !psf || !scratch) return DLUX_ERR_ARG;
+  if (d->save_field && !field) return DLUX_ERR_ARG;
+  if (((uintptr_t)psf | (uintptr_t)scratch | (uintptr_t)field) & 15) return DLUX_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  PolyScratch s;
+  bool ok = true;
+  carve_poly(d, scratch, scratch_bytes, &s, &ok);
+  if (!ok) return DLUX_ERR_SCRATCH;
+  const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
+  const int items = d->n_sources * L;
+  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, st);
+  if (rc) return rc;
+  rc = launch_zero(psf, (size_t)M * M, st);
+  if (rc) return rc;
+  const float sign2pi = (float)(-2.0 * 3.14159265358979323846);
+  for (int b0 = 0; b0 < items; b0 += s.chunk) {
+    const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
+    rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
+                       1, s.xin, s.uout, st);
+    if (rc) return rc;
+    GemmParams g{};
+    fill_stage(g, false, 0, N, M, c, s.xin, s.uout, sign2pi);
+    g.item_data = s.item_l + b0;
+    for (int i = 0; i < 4; ++i) { g.a_planes[i] = s.p_pl[i]; g.out_planes[i] = s.mid_pl[i]; }
+    g.mode = EPI_PLANES;
+    rc = run_gemm(g, d->precision, st);
+    if (rc) return rc;
+    GemmParams h{};
+    fill_stage(h, false, 1, N, M, c, s.xin, s.uout, sign2pi);
+    for (int i = 0; i < 4; ++i) h.a_planes[i] = s.mid_pl[i];
+    h.mode = EPI_PSF;
+    h.scale = s.norm_item + b0;
+    h.psf = psf;
+    h.w = weights + b0;
+    h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * M * M : nullptr;
+    rc = run_gemm(h, d->precision, st);
+    if (rc) return rc;
+  }
+  return DLUX_OK;
+}
+
+int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* opd,
+                     const float* phase, const float* wavenumber, const float* scale_out,
+                     const float* norm, const float* weights, const float* delta_xy,
+                     const void* field, const float* psf_bar, float* opd_bar, float* phase_bar,
+                     float* weights_bar, void* scratch, size_t scratch_bytes, void* cuda_stream) {
+  int rc = check_poly_desc(d);
+  if (rc != DLUX_OK) return rc;
+  if (!wavenumber || !scale_out || !weights || !field || !psf_bar || !scratch) return DLUX_ERR_ARG;
+  if (((uintptr_t)field | (uintptr_t)scratch) & 15) return DLUX_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  PolyScratch s;
+  bool ok = true;
+  carve_poly(d, scratch, scratch_bytes, &s, &ok);
+  if (!ok) return DLUX_ERR_SCRATCH;
+  const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
+  const int items = d->n_sources * L;
+  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, st);
+  if (rc) return rc;
+  if (opd_bar && (rc = launch_zero(opd_bar, (size_t)N * N, st))) return rc;
+  if (phase_bar && (rc = launch_zero(phase_bar, (size_t)N * N, st))) return rc;
+  if (weights_bar && (rc = launch_zero(weights_bar, (size_t)items, st))) return rc;
+  const bool need_pupil_grad = opd_bar || phase_bar;
+  const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
+  for (int b0 = 0; b0 < items; b0 += s.chunk) {
+    const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
+    rc = launch_cotangent(M, c, (const float2*)field + (size_t)b0 * M * M, psf_bar, weights + b0,
+                          s.ebar_pl[0], s.ebar_pl[1], s.ebar_pl[2], s.ebar_pl[3],
+                          weights_bar ? weights_bar + b0 : nullptr, st);
+    if (rc) return rc;
+    if (!need_pupil_grad) continue;
+    rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
+                       1, s.xin, s.uout, st);
+    if (rc) return rc;
+    GemmParams g{};
+    fill_stage(g, true, 0, N, M, c, s.xin, s.uout, sign2pi);
+    for (int i = 0; i < 4; ++i) { g.a_planes[i] = s.ebar_pl[i]; g.out_planes[i] = s.mid_pl[i]; }
+    g.mode = EPI_PLANES;
+    rc = run_gemm(g, d->precision, st);
+    if (rc) return rc;
+    GemmParams h{};
+    fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
+    for (int i = 0; i < 4; ++i) { h.a_planes[i] = s.mid_pl[i]; h.p_planes[i] = s.p_pl[i]; }
+    h.mode = EPI_GRAD;
+    h.scale = s.norm_item + b0;
+    h.w = s.k_item + b0;
+    h.item_p = s.item_l + b0;
+    h.opd_bar = opd_bar;
+    h.phase_bar = phase_bar;
+    rc = run_gemm(h, d->precision, st);
+    if (rc) return rc;
+  }
+  return DLUX_OK;
+}
+
+int dlux_basis_eval(int32_t nz, int64_t npix, const float* basis, const float* coeffs,
+                    const float* base, float* out, void* cuda_stream) {
+  if (!basis || !coeffs || !out) return DLUX_ERR_ARG;
+  if (nz < 1 || nz > 8192 || npix < 1) return DLUX_ERR_SHAPE;
+  return launch_basis_eval(nz, npix, basis, coeffs, base, out, (cudaStream_t)cuda_stream);
+}
+
+int dlux_basis_reduce(int32_t nz, int64_t npix, const float* basis, const float* out_bar,
+                      float* coeff_bar, void* cuda_stream) {
+  if (!basis || !out_bar || !coeff_bar) return DLUX_ERR_ARG;
+  if (nz < 1 || npix < 1) return DLUX_ERR_SHAPE;
+  return launch_basis_reduce(nz, npix, basis, out_bar, coeff_bar, (cudaStream_t)cuda_stream);
+}
+
+}  // extern "C"

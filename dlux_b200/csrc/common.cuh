@@ -1,0 +1,120 @@
+// Shared declarations of the dlux_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dlux_b200.h"
+
+namespace dlux {
+
+// ---------------------------------------------------------------------------
+// One "phasor GEMM" stage.  Every stage of the forward and adjoint MFT is
+//
+//   Out[item][n][m] = scale[item] * sum_k Data[d(item)][m][k] * exp(i * sign2pi * fl(kvec[k] * nvec[n]))
+//
+// i.e. a complex contraction of a data matrix (planar, hi/lo-split fp32 planes)
+// with a DFT phasor matrix that is generated on the fly from two float32
+// coordinate vectors, written TRANSPOSED (m fastest) so that two stages chain.
+// The phase argument is formed exactly as the reference does
+// (/root/reference/src/dLux/utils/propagation.py:124): fl32(fl32(-2pi) * fl32(x*u)).
+// ---------------------------------------------------------------------------
+enum EpilogueMode : int {
+  EPI_PLANES = 0,  // out_planes[p][item][n][m], p = re_hi, re_lo, im_hi, im_lo  (feeds the next stage)
+  EPI_C64 = 1,     // out_c64[item][n][m]
+  EPI_PSF = 2,     // psf[n][m] += w[item] * |v|^2   (optionally also out_c64)
+  EPI_GRAD = 3     // opd_bar[n][m] += kw[item] * Im(conj(P[d2(item)][n][m]) * v); phase_bar likewise with 1
+};
+
+struct GemmParams {
+  // data operand: 4 planes, each [n_data][rows][K] float32
+  const float* a_planes[4];
+  int rows;    // M dimension of the data matrix (rows m)
+  int K;       // contraction length
+  int n_out;   // number of generated output coordinates (n)
+  int n_items;
+  const int* item_data;  // [n_items] -> data matrix index, or nullptr (identity)
+  const float* kvec;     // [n_items][kvec_stride], coordinate along k
+  const float* nvec;     // [n_items][nvec_stride], coordinate along n
+  int kvec_stride, nvec_stride;
+  float sign2pi;         // float32(-2*pi) forward, float32(+2*pi) inverse / adjoint-of-forward
+  const float* scale;    // [n_items] or nullptr
+  int mode;
+  float* out_planes[4];  // EPI_PLANES
+  float2* out_c64;       // EPI_C64 / optional for EPI_PSF
+  float* psf;            // EPI_PSF: [n_out][rows]
+  const float* w;        // EPI_PSF weights [n_items]; EPI_GRAD: wavenumber per item
+  const float* p_planes[4];  // EPI_GRAD: pupil planes [n_p][n_out][rows]
+  const int* item_p;     // EPI_GRAD: item -> pupil index (nullptr = identity)
+  float* opd_bar;        // EPI_GRAD
+  float* phase_bar;      // EPI_GRAD
+};
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// Reference phase argument: two float32 multiplies, no fused contraction.
+__device__ __forceinline__ float phase_arg(float sign2pi, float x, float u) {
+  return __fmul_rn(sign2pi, __fmul_rn(x, u));
+}
+
+// Shared epilogue for one output element D[m][n] = (re, im) of `item`.
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, int m, int n,
+                                               float re, float im) {
+  const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
+  re *= sc;
+  im *= sc;
+  const size_t idx = ((size_t)item * p.n_out + n) * p.rows + m;
+  if (p.mode == EPI_PLANES) {
+    const float rh = tf32_hi(re), ih = tf32_hi(im);
+    p.out_planes[0][idx] = rh;
+    p.out_planes[1][idx] = re - rh;
+    p.out_planes[2][idx] = ih;
+    p.out_planes[3][idx] = im - ih;
+  } else if (p.mode == EPI_C64) {
+    p.out_c64[idx] = make_float2(re, im);
+  } else if (p.mode == EPI_PSF) {
+    if (p.out_c64) p.out_c64[idx] = make_float2(re, im);
+    const float w = __ldg(p.w + item);
+    atomicAdd(p.psf + (size_t)n * p.rows + m, w * (re * re + im * im));
+  } else {  // EPI_GRAD
+    const int ip = p.item_p ? __ldg(p.item_p + item) : item;
+    const size_t pi = ((size_t)ip * p.n_out + n) * p.rows + m;
+    const float pr = __ldg(p.p_planes[0] + pi) + __ldg(p.p_planes[1] + pi);
+    const float pim = __ldg(p.p_planes[2] + pi) + __ldg(p.p_planes[3] + pi);
+    const float g = pr * im - pim * re;  // Im(conj(P) * v)
+    const size_t oi = (size_t)n * p.rows + m;
+    if (p.opd_bar) atomicAdd(p.opd_bar + oi, __ldg(p.w + item) * g);
+    if (p.phase_bar) atomicAdd(p.phase_bar + oi, g);
+  }
+}
+
+// launch counters / error plumbing (api.cu)
+void note_launch(int n = 1);
+int check_launch(const char* what);
+
+// kernels' host launchers
+int launch_gemm_simt(const GemmParams& p, cudaStream_t st);
+int launch_gemm_tc(const GemmParams& p, cudaStream_t st);
+size_t gemm_tc_workspace_bytes();
+
+int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const float* shift_xy,
+                  const float* delta_xy, int delta_stride_items, float* xin, float* uout,
+                  cudaStream_t st);
+int launch_split_c64(const float2* in, size_t n, float* p0, float* p1, float* p2, float* p3,
+                     cudaStream_t st);
+int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
+                 const float* wavenumber, const float* amp_scale /*device scalar*/,
+                 float* p0, float* p1, float* p2, float* p3, cudaStream_t st);
+int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStream_t st);
+int launch_cotangent(int M, int n_items, const float2* field, const float* psf_bar,
+                     const float* w, float* p0, float* p1, float* p2, float* p3, float* w_bar,
+                     cudaStream_t st);
+int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coeffs,
+                      const float* base, float* out, cudaStream_t st);
+int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,
+                        float* coeff_bar, cudaStream_t st);
+int launch_zero(float* p, size_t n, cudaStream_t st);
+
+}  // namespace dlux

@@ -1,0 +1,313 @@
+// HBM-bound helpers around the two phasor GEMM stages: coordinate vectors, operand
+// splitting, pupil phasor, power normalisation, cotangent, basis eval / reduce.
+#include "common.cuh"
+
+namespace dlux {
+
+static inline int grid_for(size_t n, int block, int max_blocks = 148 * 16) {
+  size_t g = (n + block - 1) / block;
+  if (g > (size_t)max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------
+// jnp.linspace lerp form, element i of n (see oracle/mft_oracle.py:jnp_linspace)
+__device__ __forceinline__ float lerp_linspace(float start, float stop, int i, int n) {
+  if (n == 1) return start;
+  if (i == n - 1) return stop;
+  const float t = __fdiv_rn((float)i, (float)(n - 1));
+  return __fadd_rn(__fmul_rn(start, __fsub_rn(1.0f, t)), __fmul_rn(stop, t));
+}
+
+// transfer_matrix's two coordinate vectors (/root/reference/src/dLux/utils/
+// propagation.py:113-121 via utils/coordinates.py:329-332), float32 bit-exact.
+__global__ void coords_kernel(int n_in, int n_out, int batch, const float* __restrict__ scale_out,
+                              const float* __restrict__ shift_xy, const float* __restrict__ delta_xy,
+                              float* __restrict__ xin, float* __restrict__ uout) {
+  const int item = blockIdx.y, axis = blockIdx.z;
+  const float shift = shift_xy ? shift_xy[item * 2 + axis] : 0.0f;
+  const float delta = delta_xy ? delta_xy[item * 2 + axis] : 0.0f;
+  const float s = scale_out[item];
+  // in_vec: scale_in = 1.0 / n_in is a Python float in the reference -> -(n-1)/2*scale
+  // is evaluated in float64 and rounded once; the offset shift*scale_in is float32.
+  const double scale_in = 1.0 / (double)n_in;
+  const double h_in = (double)(n_in - 1) / 2.0;
+  const float off_in = __fmul_rn(shift, (float)scale_in);
+  const float start_in = __fsub_rn((float)(-h_in * scale_in), off_in);
+  const float stop_in = __fsub_rn((float)(h_in * scale_in), off_in);
+  const float h_out = (float)(n_out - 1) * 0.5f;
+  const float off_out = __fmul_rn(shift, s);
+  const float start_out = __fsub_rn(__fmul_rn(-h_out, s), off_out);
+  const float stop_out = __fsub_rn(__fmul_rn(h_out, s), off_out);
+  float* xi = xin + ((size_t)item * 2 + axis) * n_in;
+  float* uo = uout + ((size_t)item * 2 + axis) * n_out;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x)
+    xi[i] = lerp_linspace(start_in, stop_in, i, n_in);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
+    float u = lerp_linspace(start_out, stop_out, i, n_out);
+    if (delta_xy) u = __fsub_rn(u, delta);
+    uo[i] = u;
+  }
+}
+
+int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const float* shift_xy,
+                  const float* delta_xy, int, float* xin, float* uout, cudaStream_t st) {
+  if (batch <= 0) return DLUX_OK;
+  int mx = n_in > n_out ? n_in : n_out;
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    dim3 grid((mx + 255) / 256 > 8 ? 8 : (mx + 255) / 256, nb, 2);
+    coords_kernel<<<grid, 256, 0, st>>>(n_in, n_out, nb, scale_out + b0,
+                                         shift_xy ? shift_xy + 2 * (size_t)b0 : nullptr,
+                                         delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
+                                         xin + (size_t)b0 * 2 * n_in, uout + (size_t)b0 * 2 * n_out);
+    note_launch();
+  }
+  return check_launch("coords");
+}
+
+// ---------------------------------------------------------------------------
+// complex64 interleaved -> 4 planar planes (re_hi, re_lo, im_hi, im_lo), hi = rna tf32
+__global__ void split_c64_kernel(const float2* __restrict__ in, size_t n, float* __restrict__ p0,
+                                 float* __restrict__ p1, float* __restrict__ p2,
+                                 float* __restrict__ p3) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 v = in[i];
+    const float rh = tf32_hi(v.x), ih = tf32_hi(v.y);
+    p0[i] = rh;
+    p1[i] = v.x - rh;
+    p2[i] = ih;
+    p3[i] = v.y - ih;
+  }
+}
+
+int launch_split_c64(const float2* in, size_t n, float* p0, float* p1, float* p2, float* p3,
+                     cudaStream_t st) {
+  if (n == 0) return DLUX_OK;
+  split_c64_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, n, p0, p1, p2, p3);
+  note_launch();
+  return check_launch("split_c64");
+}
+
+// ---------------------------------------------------------------------------
+// power normalisation (wavefronts.py:418-424): amp_scale = sqrt(1 / sum (T/N^2)^2)
+// (|exp(i phi)| = 1, so the power depends on the transmission only).  Deterministic
+// two-pass sum in float64.  scratch layout: double partial[256] then float amp_scale.
+__global__ void power_partial_kernel(int N, const float* __restrict__ T, double* __restrict__ partial) {
+  __shared__ double sm[256];
+  const size_t n = (size_t)N * N;
+  const float a0 = 1.0f / (float)((long long)N * N);
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float v = T ? a0 * T[i] : a0;
+    acc += (double)(v * v);
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+__global__ void power_final_kernel(const double* __restrict__ partial, int n, int normalise,
+                                   float* __restrict__ amp_scale) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    const float power = (float)s;
+    amp_scale[0] = normalise ? sqrtf(1.0f / power) : 1.0f;
+  }
+}
+
+int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStream_t st) {
+  // amp_scale points at: [float amp_scale][pad to 8][double partial[256]]
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(amp_scale) + 16);
+  power_partial_kernel<<<256, 256, 0, st>>>(N, T, partial);
+  power_final_kernel<<<1, 32, 0, st>>>(partial, 256, normalise, amp_scale);
+  note_launch(2);
+  return check_launch("power");
+}
+
+// ---------------------------------------------------------------------------
+// pupil phasor P_l = (1/N^2) T exp(i k_l opd) exp(i phase) * amp_scale, split to planes
+// (wavefronts.py:111-113, 349, 368; layers/optics.py:91-96)
+__global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const float* __restrict__ opd,
+                             const float* __restrict__ phase, const float* __restrict__ wavenumber,
+                             const float* __restrict__ amp_scale, float* __restrict__ p0,
+                             float* __restrict__ p1, float* __restrict__ p2, float* __restrict__ p3) {
+  const size_t n = (size_t)N * N;
+  const float a0 = 1.0f / (float)((long long)N * N);
+  const float sc = amp_scale[0];
+  const int l = blockIdx.y;
+  const float k = wavenumber[l];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float a = T ? a0 * T[i] : a0;
+    float re = a, im = 0.0f;
+    if (opd) {
+      float s, c;
+      sincosf(__fmul_rn(k, opd[i]), &s, &c);
+      re = a * c;
+      im = a * s;
+    }
+    if (phase) {
+      float s, c;
+      sincosf(phase[i], &s, &c);
+      const float r2 = __fsub_rn(__fmul_rn(re, c), __fmul_rn(im, s));
+      const float i2 = __fadd_rn(__fmul_rn(re, s), __fmul_rn(im, c));
+      re = r2;
+      im = i2;
+    }
+    re *= sc;
+    im *= sc;
+    const size_t o = (size_t)l * n + i;
+    const float rh = tf32_hi(re), ih = tf32_hi(im);
+    p0[o] = rh;
+    p1[o] = re - rh;
+    p2[o] = ih;
+    p3[o] = im - ih;
+  }
+}
+
+int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
+                 const float* wavenumber, const float* amp_scale, float* p0, float* p1, float* p2,
+                 float* p3, cudaStream_t st) {
+  dim3 grid(grid_for((size_t)N * N, 256, 148 * 4), L);
+  pupil_kernel<<<grid, 256, 0, st>>>(N, L, T, opd, phase, wavenumber, amp_scale, p0, p1, p2, p3);
+  note_launch();
+  return check_launch("pupil");
+}
+
+// ---------------------------------------------------------------------------
+// cotangent of the field: Ebar = 2 w psf_bar .* E (planes), w_bar[item] = sum psf_bar |E|^2
+__global__ void cotangent_kernel(int M, const float2* __restrict__ field,
+                                 const float* __restrict__ psf_bar, const float* __restrict__ w,
+                                 float* __restrict__ p0, float* __restrict__ p1,
+                                 float* __restrict__ p2, float* __restrict__ p3,
+                                 float* __restrict__ w_bar) {
+  __shared__ float sm[256];
+  const size_t n = (size_t)M * M;
+  const int item = blockIdx.y;
+  const float w2 = 2.0f * w[item];
+  float acc = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 e = field[(size_t)item * n + i];
+    const float g = psf_bar[i];
+    acc += g * (e.x * e.x + e.y * e.y);
+    const float re = w2 * g * e.x, im = w2 * g * e.y;
+    const size_t o = (size_t)item * n + i;
+    const float rh = tf32_hi(re), ih = tf32_hi(im);
+    p0[o] = rh;
+    p1[o] = re - rh;
+    p2[o] = ih;
+    p3[o] = im - ih;
+  }
+  if (w_bar) {
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(w_bar + item, sm[0]);
+  }
+}
+
+int launch_cotangent(int M, int n_items, const float2* field, const float* psf_bar, const float* w,
+                     float* p0, float* p1, float* p2, float* p3, float* w_bar, cudaStream_t st) {
+  for (int b0 = 0; b0 < n_items; b0 += 65535) {
+    int nb = n_items - b0 < 65535 ? n_items - b0 : 65535;
+    const size_t off = (size_t)b0 * M * M;
+    dim3 grid(grid_for((size_t)M * M, 256, 64), nb);
+    cotangent_kernel<<<grid, 256, 0, st>>>(M, field + off, psf_bar, w + b0, p0 + off, p1 + off,
+                                            p2 + off, p3 + off, w_bar ? w_bar + b0 : nullptr);
+    note_launch();
+  }
+  return check_launch("cotangent");
+}
+
+// ---------------------------------------------------------------------------
+// eval_basis (utils/math.py:177-196) and its transpose
+__global__ void basis_eval_kernel(int nz, size_t npix, const float* __restrict__ basis,
+                                  const float* __restrict__ coeffs, const float* __restrict__ base,
+                                  float* __restrict__ out) {
+  extern __shared__ float c_sm[];
+  for (int z = threadIdx.x; z < nz; z += blockDim.x) c_sm[z] = coeffs[z];
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.0f;
+    for (int z = 0; z < nz; ++z) acc = fmaf(c_sm[z], __ldg(basis + (size_t)z * npix + i), acc);
+    out[i] = base ? base[i] + acc : acc;
+  }
+}
+
+int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coeffs,
+                      const float* base, float* out, cudaStream_t st) {
+  basis_eval_kernel<<<grid_for((size_t)npix, 256), 256, nz * sizeof(float), st>>>(
+      nz, (size_t)npix, basis, coeffs, base, out);
+  note_launch();
+  return check_launch("basis_eval");
+}
+
+__global__ void zero_kernel(float* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    p[i] = 0.0f;
+}
+
+__global__ void basis_reduce_kernel(int nz, size_t npix, const float* __restrict__ basis,
+                                    const float* __restrict__ out_bar, float* __restrict__ coeff_bar) {
+  __shared__ float sm[8];
+  constexpr int PER = 8;
+  float g[PER];
+  const size_t base_i = ((size_t)blockIdx.x * blockDim.x) * PER + threadIdx.x;
+  // each block owns a contiguous chunk of PER*blockDim pixels (grid sized to cover npix)
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const size_t i = base_i + (size_t)j * blockDim.x;
+    g[j] = i < npix ? out_bar[i] : 0.0f;
+  }
+  for (int z = 0; z < nz; ++z) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const size_t i = base_i + (size_t)j * blockDim.x;
+      if (i < npix) acc = fmaf(g[j], __ldg(basis + (size_t)z * npix + i), acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.0f;
+      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += sm[wv];
+      atomicAdd(coeff_bar + z, s);
+    }
+    __syncthreads();
+  }
+}
+
+int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,
+                        float* coeff_bar, cudaStream_t st) {
+  zero_kernel<<<1, 256, 0, st>>>(coeff_bar, (size_t)nz);
+  const size_t per_block = 256 * 8;
+  const int grid = (int)(((size_t)npix + per_block - 1) / per_block);
+  basis_reduce_kernel<<<grid, 256, 0, st>>>(nz, (size_t)npix, basis, out_bar, coeff_bar);
+  note_launch(2);
+  return check_launch("basis_reduce");
+}
+
+int launch_zero(float* p, size_t n, cudaStream_t st) {
+  if (n == 0) return DLUX_OK;
+  zero_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n);
+  note_launch();
+  return check_launch("zero");
+}
+
+}  // namespace dlux

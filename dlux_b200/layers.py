@@ -1,0 +1,142 @@
+"""Mirror of the pupil-plane and propagator layers that feed the MFT
+(/root/reference/src/dLux/layers/optical_layers.py:80-371, layers/optics.py:77-175,
+layers/propagators.py:145-217).  Same class names, constructor arguments and
+``layer(wavefront) -> wavefront`` contract; arrays are torch CUDA tensors."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .utils import propagation as _prop
+from .wavefronts import Wavefront
+
+__all__ = ["OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer", "Tilt", "Normalise",
+           "Optic", "BasisOptic", "MFT"]
+
+
+def _arr(x, device=None):
+    if x is None:
+        return None
+    if torch.is_tensor(x):
+        return x.to(dtype=torch.float32, device=device or x.device)
+    return torch.as_tensor(np.asarray(x, dtype=np.float32), device=device or "cuda")
+
+
+class OpticalLayer:
+    """optical_layers.py:80-105: the reference's user-extension API."""
+
+    def apply(self, wavefront: Wavefront) -> Wavefront:
+        return self(wavefront)
+
+    def __call__(self, wavefront: Wavefront) -> Wavefront:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+
+class TransmissiveLayer(OpticalLayer):
+    def __init__(self, transmission=None, normalise: bool = False, device=None):
+        self.transmission = _arr(transmission, device)
+        self.normalise = bool(normalise)
+
+    def __call__(self, wavefront):                     # optical_layers.py:181-186
+        if self.transmission is not None:
+            wavefront = wavefront * self.transmission
+        if self.normalise:
+            wavefront = wavefront.normalise()
+        return wavefront
+
+
+class AberratedLayer(OpticalLayer):
+    def __init__(self, opd=None, phase=None, device=None):
+        self.opd = _arr(opd, device)
+        self.phase = _arr(phase, device)
+        if self.opd is not None and self.phase is not None and self.opd.shape != self.phase.shape:
+            raise ValueError("opd and phase must have the same shape. Got "
+                             f"shapes {tuple(self.opd.shape)} and {tuple(self.phase.shape)}.")
+
+    def __call__(self, wavefront):                     # optical_layers.py:233-236
+        return wavefront.add_opd(self.opd).add_phase(self.phase)
+
+
+class BasisLayer(OpticalLayer):
+    def __init__(self, basis=None, coefficients=None, effect: str = "opd", device=None):
+        self.basis = _arr(basis, device)
+        if coefficients is None and self.basis is not None:
+            coefficients = torch.zeros(self.basis.shape[:-2], dtype=torch.float32,
+                                       device=self.basis.device)
+        self.coefficients = _arr(coefficients, device)
+        if effect not in ("opd", "phase", "amplitude"):
+            raise ValueError("effect must be 'opd', 'phase', or 'amplitude'.")
+        self.effect = effect
+
+    def eval_basis(self):                              # optical_layers.py:304-313
+        return _prop.eval_basis(self.basis, self.coefficients)
+
+    def __call__(self, wavefront):                     # optical_layers.py:319-327
+        output = self.eval_basis()
+        if self.effect == "phase":
+            return wavefront.add_phase(output)
+        if self.effect == "opd":
+            return wavefront.add_opd(output)
+        return wavefront * (1 + output)
+
+
+class Tilt(OpticalLayer):
+    def __init__(self, angles, device=None):
+        self.angles = _arr(angles, device)
+        if tuple(self.angles.shape) != (2,):
+            raise ValueError("angles must have shape (2,).")
+
+    def __call__(self, wavefront):                     # optical_layers.py:358-359
+        return wavefront.tilt(self.angles)
+
+
+class Normalise(OpticalLayer):
+    def __call__(self, wavefront):                     # optical_layers.py:370-371
+        return wavefront.normalise()
+
+
+class Optic(TransmissiveLayer, AberratedLayer):
+    def __init__(self, transmission=None, opd=None, phase=None, normalise: bool = False, device=None):
+        TransmissiveLayer.__init__(self, transmission, normalise, device)
+        AberratedLayer.__init__(self, opd, phase, device)
+        for name in ("opd", "phase"):
+            v = getattr(self, name)
+            if self.transmission is not None and v is not None and v.shape != self.transmission.shape:
+                raise ValueError(f"transmission and {name} must have the same shape. Got shapes "
+                                 f"{tuple(self.transmission.shape)} and {tuple(v.shape)}.")
+
+    def __call__(self, wavefront):                     # layers/optics.py:91-96
+        if self.transmission is not None:
+            wavefront = wavefront * self.transmission
+        wavefront = wavefront.add_opd(self.opd).add_phase(self.phase)
+        if self.normalise:
+            wavefront = wavefront.normalise()
+        return wavefront
+
+
+class BasisOptic(TransmissiveLayer, BasisLayer):
+    def __init__(self, basis, transmission=None, coefficients=None, effect: str = "opd",
+                 normalise: bool = False, device=None):
+        TransmissiveLayer.__init__(self, transmission, normalise, device)
+        BasisLayer.__init__(self, basis, coefficients, effect, device)
+
+    def __call__(self, wavefront):                     # layers/optics.py:168-175
+        if self.transmission is not None:
+            wavefront = wavefront * self.transmission
+        wavefront = BasisLayer.__call__(self, wavefront)
+        if self.normalise:
+            wavefront = wavefront.normalise()
+        return wavefront
+
+
+class MFT(OpticalLayer):
+    """layers/propagators.py:145-217."""
+
+    def __init__(self, npixels: int, pixel_scale, focal_length=None, inverse: bool = False):
+        self.npixels = int(npixels)
+        self.pixel_scale = np.float32(pixel_scale)
+        self.focal_length = None if focal_length is None else np.float32(focal_length)
+        self.inverse = bool(inverse)
+
+    def __call__(self, wavefront):                     # layers/propagators.py:198-217
+        return wavefront.propagate(self.npixels, self.pixel_scale, self.focal_length, self.inverse)

@@ -1,0 +1,279 @@
+"""Thin Python ops over the C ABI: torch tensors supply device memory and the CUDA
+stream (plumbing only); all arithmetic on the hot path happens in libdlux_b200.so.
+
+These are the calls the XLA-FFI handlers would make under JAX; here
+they are wired into ``torch.autograd.Function`` so that ``loss.backward()`` plays the
+role of ``jax.grad`` through ``custom_vjp``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MftDesc, PolyPsfDesc, PREC_3XTF32, PREC_FP32, check
+
+__all__ = ["default_precision", "set_default_precision", "mft_c64", "mft_coords", "MFTFunction",
+           "polypsf_fwd", "polypsf_bwd", "PolyPSFFunction", "basis_eval", "basis_reduce",
+           "BasisEvalFunction"]
+
+_default_precision = {"3xtf32": PREC_3XTF32, "fp32": PREC_FP32}[
+    os.environ.get("DLUX_B200_PRECISION", "3xtf32").lower()]
+
+
+def default_precision() -> int:
+    return _default_precision
+
+
+def set_default_precision(p) -> None:
+    global _default_precision
+    _default_precision = {"3xtf32": PREC_3XTF32, "fp32": PREC_FP32}.get(p, p)
+
+
+def _prec(p) -> int:
+    if p is None:
+        return _default_precision
+    if isinstance(p, str):
+        return {"3xtf32": PREC_3XTF32, "fp32": PREC_FP32}[p.lower()]
+    return int(p)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"dlux_b200: `{name}` must be a CUDA tensor (no CPU fallback exists)")
+
+
+def _f32(t, device, shape=None) -> torch.Tensor:
+    t = torch.as_tensor(t, dtype=torch.float32, device=device).contiguous()
+    if shape is not None:
+        t = t.reshape(shape)
+    return t
+
+
+_scratch: dict = {}
+
+
+def _get_scratch(device, nbytes: int) -> torch.Tensor:
+    """Per-device grow-only workspace (stream-ordered reuse on the current stream)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _scratch.pop(key, None)
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------- MFT
+def mft_coords(n_in: int, n_out: int, scale_out, shift_xy=None, delta_xy=None):
+    lib = _lib.load()
+    scale_out = scale_out.contiguous()
+    _need_cuda(scale_out, "scale_out")
+    dev = scale_out.device
+    batch = scale_out.numel()
+    xin = torch.empty((batch, 2, n_in), dtype=torch.float32, device=dev)
+    uout = torch.empty((batch, 2, n_out), dtype=torch.float32, device=dev)
+    shift_xy = None if shift_xy is None else _f32(shift_xy, dev, (batch, 2))
+    delta_xy = None if delta_xy is None else _f32(delta_xy, dev, (batch, 2))
+    check(lib.dlux_mft_coords(n_in, n_out, batch, _ptr(scale_out), _ptr(shift_xy), _ptr(delta_xy),
+                              _ptr(xin), _ptr(uout), _stream(dev)), "dlux_mft_coords")
+    return xin, uout
+
+
+def mft_c64(phasor: torch.Tensor, scale_out, n_out_or_in: int, shift_xy=None, delta_xy=None,
+            norm=None, inverse: bool = False, adjoint: bool = False, precision=None) -> torch.Tensor:
+    """Batched MFT through ``dlux_mft_c64``.  ``phasor``: complex64 [..., n, n].
+    forward: n = n_in, ``n_out_or_in`` = n_out; adjoint: n = n_out, ``n_out_or_in`` = n_in."""
+    lib = _lib.load()
+    _need_cuda(phasor, "phasor")
+    if phasor.dtype != torch.complex64:
+        raise TypeError("dlux_b200: phasor must be complex64 (x64 inputs are outside the contract)")
+    if phasor.shape[-1] != phasor.shape[-2]:
+        raise ValueError("phasor must be square")
+    dev = phasor.device
+    lead = phasor.shape[:-2]
+    n_src = phasor.shape[-1]
+    x = phasor.reshape(-1, n_src, n_src).contiguous()
+    batch = x.shape[0]
+    n_in, n_out = (n_out_or_in, n_src) if adjoint else (n_src, n_out_or_in)
+    n_dst = n_in if adjoint else n_out
+    scale_out = _f32(scale_out, dev).expand(batch).contiguous() if torch.as_tensor(scale_out).numel() == 1 \
+        else _f32(scale_out, dev, (batch,))
+
+    def per_item(v, width):
+        if v is None:
+            return None
+        v = _f32(v, dev)
+        if v.numel() == width:
+            v = v.reshape(1, width).expand(batch, width)
+        return v.reshape(batch, width).contiguous()
+
+    shift_xy = per_item(shift_xy, 2)
+    delta_xy = per_item(delta_xy, 2)
+    norm = None if norm is None else per_item(norm, 1)
+    desc = MftDesc(n_in, n_out, batch, int(bool(inverse)), int(bool(adjoint)), _prec(precision))
+    nbytes = lib.dlux_mft_scratch_bytes(C.byref(desc))
+    scratch = _get_scratch(dev, nbytes)
+    out = torch.empty((batch, n_dst, n_dst), dtype=torch.complex64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dlux_mft_c64(C.byref(desc), _ptr(x), _ptr(scale_out), _ptr(shift_xy), _ptr(delta_xy),
+                               _ptr(norm), _ptr(out), _ptr(scratch), scratch.numel(), _stream(dev)),
+              "dlux_mft_c64")
+    return out.reshape(*lead, n_dst, n_dst)
+
+
+class MFTFunction(torch.autograd.Function):
+    """Linear in the phasor; the VJP is the adjoint kernel (what ``jax.custom_vjp`` /
+    the primitive's transpose rule would call)."""
+
+    @staticmethod
+    def forward(ctx, phasor, scale_out, n_out, shift_xy, delta_xy, norm, inverse, precision):
+        ctx.n_in = phasor.shape[-1]
+        ctx.args = (scale_out, shift_xy, delta_xy, norm, inverse, precision)
+        return mft_c64(phasor, scale_out, n_out, shift_xy, delta_xy, norm, inverse, False, precision)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        scale_out, shift_xy, delta_xy, norm, inverse, precision = ctx.args
+        g = mft_c64(grad_out.contiguous(), scale_out, ctx.n_in, shift_xy, delta_xy, norm, inverse, True,
+                    precision)
+        return g, None, None, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------- poly-PSF
+def _poly_desc(N, M, L, S, normalise, precision, save_field):
+    return PolyPsfDesc(N, M, L, S, int(bool(normalise)), _prec(precision), int(bool(save_field)), 0)
+
+
+def polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, n_pupil,
+                n_psf, normalise=True, precision=None, save_field=False):
+    lib = _lib.load()
+    dev = wavenumber.device
+    _need_cuda(wavenumber, "wavenumber")
+    L = wavenumber.numel()
+    weights = weights.reshape(-1, L).contiguous()
+    S = weights.shape[0]
+    desc = _poly_desc(n_pupil, n_psf, L, S, normalise, precision, save_field)
+    nbytes = lib.dlux_polypsf_scratch_bytes(C.byref(desc))
+    scratch = _get_scratch(dev, nbytes)
+    psf = torch.empty((n_psf, n_psf), dtype=torch.float32, device=dev)
+    field = torch.empty((S * L, n_psf, n_psf), dtype=torch.complex64, device=dev) if save_field else None
+    with torch.cuda.device(dev):
+        check(lib.dlux_polypsf_fwd(C.byref(desc), _ptr(transmission), _ptr(opd), _ptr(phase),
+                                   _ptr(wavenumber), _ptr(scale_out), _ptr(norm), _ptr(weights),
+                                   _ptr(delta_xy), _ptr(psf), _ptr(field), _ptr(scratch),
+                                   scratch.numel(), _stream(dev)), "dlux_polypsf_fwd")
+    return psf, field
+
+
+def polypsf_bwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,
+                psf_bar, n_pupil, n_psf, normalise=True, precision=None, want_opd=True,
+                want_phase=False, want_weights=False):
+    lib = _lib.load()
+    dev = wavenumber.device
+    L = wavenumber.numel()
+    weights = weights.reshape(-1, L).contiguous()
+    S = weights.shape[0]
+    desc = _poly_desc(n_pupil, n_psf, L, S, normalise, precision, True)
+    nbytes = lib.dlux_polypsf_scratch_bytes(C.byref(desc))
+    scratch = _get_scratch(dev, nbytes)
+    mk = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    opd_bar = mk(n_pupil, n_pupil) if want_opd else None
+    phase_bar = mk(n_pupil, n_pupil) if want_phase else None
+    w_bar = mk(S, L) if want_weights else None
+    psf_bar = psf_bar.to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        check(lib.dlux_polypsf_bwd(C.byref(desc), _ptr(transmission), _ptr(opd), _ptr(phase),
+                                   _ptr(wavenumber), _ptr(scale_out), _ptr(norm), _ptr(weights),
+                                   _ptr(delta_xy), _ptr(field), _ptr(psf_bar), _ptr(opd_bar),
+                                   _ptr(phase_bar), _ptr(w_bar), _ptr(scratch), scratch.numel(),
+                                   _stream(dev)), "dlux_polypsf_bwd")
+    return opd_bar, phase_bar, w_bar
+
+
+class PolyPSFFunction(torch.autograd.Function):
+    """psf = sum_{s,l} w_sl |MFT_l(amp T exp(i(k_l opd + phase)))|^2 with gradients w.r.t.
+    opd, phase and weights (the fused primitive behind OpticalSystem.propagate)."""
+
+    @staticmethod
+    def forward(ctx, opd, phase, weights, transmission, wavenumber, scale_out, norm, delta_xy,
+                n_pupil, n_psf, normalise, precision):
+        need = any(t is not None and t.requires_grad for t in (opd, phase, weights))
+        psf, field = polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights,
+                                 delta_xy, n_pupil, n_psf, normalise, precision, save_field=need)
+        ctx.save_for_backward(*(t for t in (opd, phase, weights, transmission, wavenumber, scale_out,
+                                            norm, delta_xy, field) if t is not None))
+        ctx.present = [t is not None for t in (opd, phase, weights, transmission, wavenumber,
+                                               scale_out, norm, delta_xy, field)]
+        ctx.cfg = (n_pupil, n_psf, normalise, precision, weights.shape)
+        return psf
+
+    @staticmethod
+    def backward(ctx, psf_bar):
+        it = iter(ctx.saved_tensors)
+        opd, phase, weights, transmission, wavenumber, scale_out, norm, delta_xy, field = [
+            next(it) if p else None for p in ctx.present]
+        n_pupil, n_psf, normalise, precision, wshape = ctx.cfg
+        want = ctx.needs_input_grad
+        opd_bar, phase_bar, w_bar = polypsf_bwd(
+            transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,
+            psf_bar, n_pupil, n_psf, normalise, precision, want_opd=bool(want[0]),
+            want_phase=bool(want[1]), want_weights=bool(want[2]))
+        if w_bar is not None:
+            w_bar = w_bar.reshape(wshape)
+        return (opd_bar, phase_bar, w_bar) + (None,) * 9
+
+
+# --------------------------------------------------------------------------- basis
+def basis_eval(basis: torch.Tensor, coeffs: torch.Tensor, base: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    _need_cuda(basis, "basis")
+    nz = coeffs.numel()
+    b = basis.reshape(nz, -1).contiguous()
+    npix = b.shape[1]
+    out = torch.empty(basis.shape[coeffs.dim():], dtype=torch.float32, device=basis.device)
+    base_c = None if base is None else base.contiguous()
+    check(lib.dlux_basis_eval(nz, npix, _ptr(b), _ptr(coeffs.contiguous().reshape(-1)), _ptr(base_c),
+                              _ptr(out), _stream(basis.device)), "dlux_basis_eval")
+    return out
+
+
+def basis_reduce(basis: torch.Tensor, out_bar: torch.Tensor, coeff_shape) -> torch.Tensor:
+    lib = _lib.load()
+    nz = 1
+    for s in coeff_shape:
+        nz *= int(s)
+    b = basis.reshape(nz, -1).contiguous()
+    cb = torch.empty(nz, dtype=torch.float32, device=basis.device)
+    check(lib.dlux_basis_reduce(nz, b.shape[1], _ptr(b), _ptr(out_bar.contiguous()), _ptr(cb),
+                                _stream(basis.device)), "dlux_basis_reduce")
+    return cb.reshape(tuple(coeff_shape))
+
+
+class BasisEvalFunction(torch.autograd.Function):
+    """dlu.eval_basis (utils/math.py:177-196) with its transpose as the VJP."""
+
+    @staticmethod
+    def forward(ctx, coeffs, basis, base):
+        ctx.save_for_backward(basis)
+        ctx.cshape = coeffs.shape
+        ctx.has_base = base is not None
+        return basis_eval(basis, coeffs, base)
+
+    @staticmethod
+    def backward(ctx, out_bar):
+        (basis,) = ctx.saved_tensors
+        cb = basis_reduce(basis, out_bar, ctx.cshape) if ctx.needs_input_grad[0] else None
+        return cb, None, (out_bar if ctx.has_base and ctx.needs_input_grad[2] else None)

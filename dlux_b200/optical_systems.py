@@ -1,0 +1,236 @@
+"""Mirror of the optical-system classes around the MFT
+(/root/reference/src/dLux/optical_systems.py:30-775): ``propagate_mono``,
+``propagate``, ``model`` with the reference's argument checks and messages.
+
+Two routes produce the same numbers:
+ * layer-by-layer (``fused=False``): Wavefront -> layers -> ``Wavefront.propagate`` ->
+   ``dlux_mft_c64`` per wavelength batch; works for any layer stack;
+ * fused (default when the stack is pupil-only): one ``dlux_polypsf_fwd`` call does
+   the pupil phasor, both contractions, |E|^2, spectral weights and the source sum on
+   the GPU, and ``dlux_polypsf_bwd`` is its VJP.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .layers import (AberratedLayer, BasisLayer, BasisOptic, Normalise, Optic, OpticalLayer,
+                     TransmissiveLayer)
+from .utils import propagation as _prop
+from .wavefronts import Wavefront
+
+__all__ = ["BaseOpticalSystem", "LayeredOpticalSystem", "AngularOpticalSystem",
+           "CartesianOpticalSystem"]
+
+
+def _np32(x):
+    if torch.is_tensor(x):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=np.float32)
+
+
+class BaseOpticalSystem:
+    def propagate_mono(self, wavelength, offset=None, return_wf=False):  # pragma: no cover
+        raise NotImplementedError
+
+    def propagate(self, wavelengths, offset=None, weights=None, return_wf=False, return_psf=False):
+        """optical_systems.py:147-223 (layer-by-layer route)."""
+        if return_wf and return_psf:
+            raise ValueError(
+                "Cannot return both Wavefront and PSF objects. Choose one: "
+                "return_wf=True for Wavefront, or return_psf=True for PSF.")
+        wavelengths = np.atleast_1d(_np32(wavelengths))
+        if weights is None:
+            weights = np.ones_like(wavelengths) / np.float32(len(wavelengths))
+        else:
+            weights = np.atleast_1d(_np32(weights)) if not (torch.is_tensor(weights) and weights.is_cuda) \
+                else torch.atleast_1d(weights)
+        if tuple(weights.shape) != tuple(wavelengths.shape):
+            raise ValueError(
+                f"Wavelength and weight shape mismatch: "
+                f"wavelengths {tuple(wavelengths.shape)} vs weights {tuple(weights.shape)}. "
+                f"Must have same length and dimensions.")
+        offset = np.zeros(2, np.float32) if offset is None else (
+            offset if torch.is_tensor(offset) else _np32(offset))
+        if tuple(offset.shape) != (2,):
+            raise ValueError(
+                f"offset must be [x, y] array of shape (2,), "
+                f"got shape {tuple(offset.shape)}. "
+                "Pass offset as [on_axis_x, on_axis_y] angles in radians.")
+        return self._propagate(wavelengths, offset, weights, return_wf)
+
+    def _propagate(self, wavelengths, offset, weights, return_wf):
+        fields = []
+        for wl, w in zip(wavelengths, weights):
+            wf = self.propagate_mono(wl, offset, return_wf=True)
+            fields.append(wf.phasor * (w ** 0.5))
+        fields = torch.stack(fields)
+        if return_wf:
+            return fields
+        return (fields.real ** 2 + fields.imag ** 2).sum(0)
+
+    def model(self, source, return_wf=False, return_psf=False):   # optical_systems.py:225-260
+        return source.model(self, return_wf, return_psf)
+
+
+class LayeredOpticalSystem(BaseOpticalSystem):
+    def __init__(self, wf_npixels: int, diameter, layers, device=None, fused=True, precision=None):
+        self.wf_npixels = int(wf_npixels)
+        self.diameter = np.float32(diameter)
+        if isinstance(layers, (list, tuple)):
+            od = OrderedDict()
+            for i, l in enumerate(layers):
+                if isinstance(l, tuple):
+                    od[l[0]] = l[1]
+                else:
+                    od[f"{type(l).__name__}_{i}" if type(l).__name__ in od else type(l).__name__] = l
+            layers = od
+        self.layers = OrderedDict(layers)
+        self.device = torch.device("cuda" if device is None else device)
+        self.fused = bool(fused)
+        self.precision = precision
+
+    def __getattr__(self, key):                        # zodiax-style access to layers by name
+        layers = self.__dict__.get("layers", {})
+        if key in layers:
+            return layers[key]
+        raise AttributeError(key)
+
+    def initialise_wavefront(self, wavelength, offset=None):      # optical_systems.py:363-389
+        wf = Wavefront(wavelength, self.wf_npixels, self.diameter, device=self.device)
+        return wf.tilt(np.zeros(2, np.float32) if offset is None else offset)
+
+    def propagate_mono(self, wavelength, offset=None, return_wf=False):   # :391-425
+        wf = self.initialise_wavefront(wavelength, offset)
+        for layer in self.layers.values():
+            wf = layer(wf)
+        return wf if return_wf else wf.psf
+
+
+class _FocalSystem(LayeredOpticalSystem):
+    """Pupil-plane layers followed by one MFT to the focal plane."""
+
+    def __init__(self, wf_npixels, diameter, layers, psf_npixels, psf_pixel_scale, oversample=1,
+                 **kw):
+        super().__init__(wf_npixels, diameter, layers, **kw)
+        self.psf_npixels = int(psf_npixels)
+        self.oversample = int(oversample)
+        self.psf_pixel_scale = np.float32(psf_pixel_scale)
+
+    # -- units --------------------------------------------------------------------
+    def _focal_args(self):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def to_focus(self, wavefront):
+        npix, ps, fl = self._focal_args()
+        return wavefront.propagate(npix, ps, fl, precision=self.precision)
+
+    def propagate_mono(self, wavelength, offset=None, return_wf=False):   # :560-594
+        wf = super().propagate_mono(wavelength, offset, return_wf=True)
+        wf = self.to_focus(wf)
+        return wf if return_wf else wf.psf
+
+    # -- fused route ----------------------------------------------------------------
+    def _fusable(self):
+        """Collapse a pupil-only stack into (T, opd, phase, normalise) or None."""
+        T = opd = phase = None
+        normalise = False
+        t_after_norm = False
+
+        def mul(a, b):
+            return b if a is None else (a if b is None else a * b)
+
+        def add(a, b):
+            return b if a is None else (a if b is None else a + b)
+
+        for layer in self.layers.values():
+            if type(layer) not in (TransmissiveLayer, AberratedLayer, BasisLayer, Optic, BasisOptic,
+                                   Normalise):
+                return None
+            t = getattr(layer, "transmission", None)
+            if t is not None:
+                if normalise:
+                    t_after_norm = True
+                T = mul(T, t)
+            if isinstance(layer, BasisLayer):
+                out = layer.eval_basis()
+                if layer.effect == "opd":
+                    opd = add(opd, out)
+                elif layer.effect == "phase":
+                    phase = add(phase, out)
+                else:
+                    if normalise:
+                        t_after_norm = True
+                    T = mul(T, 1 + out)
+            if isinstance(layer, AberratedLayer):
+                opd = add(opd, layer.opd)
+                phase = add(phase, layer.phase)
+            if isinstance(layer, Normalise) or getattr(layer, "normalise", False):
+                normalise = True
+        if t_after_norm:
+            return None
+        return T, opd, phase, normalise
+
+    def _geometry(self, wavelengths):
+        npix, ps, fl = self._focal_args()
+        ps_in = np.float32(self.diameter / np.float32(self.wf_npixels))
+        scale_out, norm = _prop.mft_geometry(wavelengths, self.wf_npixels, ps_in, npix, ps, fl)
+        k = (np.float32(2 * math.pi) / wavelengths).astype(np.float32)
+        return npix, scale_out.astype(np.float32), norm.astype(np.float32), k
+
+    def fused_propagate(self, wavelengths, offsets, weights):
+        """psf = sum_{s,l} weights[s,l] |E_sl|^2 in one fused call.
+        wavelengths [L] (host), offsets [S,2] rad (host or device), weights [S,L]."""
+        parts = self._fusable()
+        if parts is None:
+            raise ValueError("layer stack is not pupil-only; use fused=False")
+        T, opd, phase, normalise = parts
+        dev = self.device
+        wavelengths = np.atleast_1d(_np32(wavelengths))
+        npix, scale_out, norm, k = self._geometry(wavelengths)
+        up = lambda a: torch.as_tensor(a, device=dev)
+        offsets_t = offsets.to(dev, torch.float32) if torch.is_tensor(offsets) else up(_np32(offsets))
+        offsets_t = offsets_t.reshape(-1, 2)
+        # tilt (wavefronts.py:370-395) folded into the output coordinates:
+        # delta = theta * D / lambda, in fringes
+        delta = (offsets_t[:, None, :] * self.diameter) / up(wavelengths)[None, :, None]
+        weights_t = weights.to(dev, torch.float32) if torch.is_tensor(weights) else up(_np32(weights))
+        weights_t = weights_t.reshape(offsets_t.shape[0], len(wavelengths))
+        cont = lambda t: None if t is None else t.contiguous()
+        return ops.PolyPSFFunction.apply(cont(opd), cont(phase), weights_t.contiguous(), cont(T), up(k),
+                                         up(scale_out), up(norm), delta.contiguous(), self.wf_npixels,
+                                         npix, normalise, self.precision)
+
+    def _propagate(self, wavelengths, offset, weights, return_wf):
+        if self.fused and not return_wf and self._fusable() is not None:
+            off = offset if torch.is_tensor(offset) else _np32(offset)
+            return self.fused_propagate(wavelengths, off.reshape(1, 2), weights.reshape(1, -1))
+        return super()._propagate(wavelengths, offset, weights, return_wf)
+
+
+class AngularOpticalSystem(_FocalSystem):
+    """optical_systems.py:597-680: psf_pixel_scale in arcseconds."""
+
+    def _focal_args(self):                              # :676-680
+        true_pixel_scale = np.float32(self.psf_pixel_scale / np.float32(self.oversample))
+        return (self.psf_npixels * self.oversample, np.float32(_prop.arcsec2rad(true_pixel_scale)),
+                None)
+
+
+class CartesianOpticalSystem(_FocalSystem):
+    """optical_systems.py:683-775: psf_pixel_scale in microns.  NOTE: the
+    reference's ``to_focus`` (:771-775) does not forward ``focal_length`` to
+    ``wavefront.propagate``; that behaviour is preserved, not fixed."""
+
+    def __init__(self, wf_npixels, diameter, layers, focal_length, psf_npixels, psf_pixel_scale,
+                 oversample=1, **kw):
+        super().__init__(wf_npixels, diameter, layers, psf_npixels, psf_pixel_scale, oversample, **kw)
+        self.focal_length = np.float32(focal_length)
+
+    def _focal_args(self):                              # :771-775
+        true_pixel_scale = np.float32(self.psf_pixel_scale / np.float32(self.oversample))
+        return (self.psf_npixels * self.oversample, np.float32(1e-6 * true_pixel_scale), None)

@@ -1,0 +1,146 @@
+"""Mirror of ``dLux.wavefronts.Wavefront`` (/root/reference/src/dLux/wavefronts.py:17)
+restricted to what the MFT hot path touches.  State lives in torch CUDA tensors; the
+pupil-plane methods are plain elementwise plumbing for the layer-by-layer (unfused)
+route -- the fused route is ``OpticalSystem.propagate`` (optical_systems.py here)."""
+from __future__ import annotations
+
+import copy
+import math
+
+import numpy as np
+import torch
+
+from .utils import propagation as _prop
+
+__all__ = ["Wavefront"]
+
+
+class Wavefront:
+    def __init__(self, wavelength, npixels: int, diameter=None, pixel_scale=None, center=None,
+                 device=None):
+        # wavefronts.py:96-122
+        if diameter is None and pixel_scale is None:
+            raise ValueError("Provide one: diameter or pixel_scale.")
+        if diameter is not None and pixel_scale is not None:
+            raise ValueError(
+                "Cannot specify both 'diameter' and 'pixel_scale' - they are "
+                "interdependent (diameter = pixel_scale × npixels). Choose one: "
+                "use 'diameter' for wavefront diameter, or 'pixel_scale' for "
+                "wavefront sampling.")
+        device = torch.device("cuda" if device is None else device)
+        f = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float32), device=device)
+        self.wavelength = f(wavelength)
+        self.pixel_scale = f(np.float32(diameter) / np.float32(npixels)) if diameter is not None \
+            else f(pixel_scale)
+        amp = torch.full((npixels, npixels), 1.0 / npixels ** 2, dtype=torch.float32, device=device)
+        self.phasor = torch.complex(amp, torch.zeros_like(amp))
+        if center is not None:
+            self.center = f(center)
+            if tuple(self.center.shape) != (1,):
+                raise ValueError("center must have shape (1,).")
+        else:
+            self.center = torch.zeros(1, dtype=torch.float32, device=device)
+
+    # ------------------------------------------------------------------ zodiax-like
+    def set(self, **kw):
+        new = copy.copy(self)
+        for k, v in kw.items():
+            setattr(new, k, v)
+        return new
+
+    def multiply(self, name, value):
+        return self.set(**{name: getattr(self, name) * value})
+
+    def __mul__(self, other):
+        return self.multiply("phasor", other)
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def npixels(self):
+        return self.phasor.shape[-1]
+
+    @property
+    def diameter(self):
+        return self.npixels * self.pixel_scale
+
+    @property
+    def amplitude(self):
+        return self.phasor.abs()
+
+    @property
+    def phase(self):
+        return self.phasor.angle()
+
+    @property
+    def psf(self):                                     # wavefronts.py:279
+        return self.phasor.real ** 2 + self.phasor.imag ** 2
+
+    @property
+    def wavenumber(self):                              # wavefronts.py:303
+        return np.float32(2 * math.pi) / self.wavelength
+
+    @property
+    def power(self):                                   # wavefronts.py:330
+        return self.psf.sum()
+
+    @property
+    def xs(self):                                      # coordinates.py:129
+        n = self.npixels
+        idx = torch.arange(n, dtype=torch.float32, device=self.phasor.device)
+        return self.center + (idx - np.float32((n - 1) / 2)) * self.pixel_scale
+
+    def coordinates(self, scale=1.0):                  # wavefronts.py:584-609
+        xs = self.xs * np.float32(scale)
+        X, Y = torch.meshgrid(xs, xs, indexing="xy")
+        return torch.stack([X, Y])
+
+    # ------------------------------------------------------------------ pupil ops
+    def add_phase(self, phase):                        # wavefronts.py:332-349
+        if phase is None:
+            return self
+        phase = torch.as_tensor(phase, dtype=torch.float32, device=self.phasor.device)
+        return self.multiply("phasor", torch.polar(torch.ones_like(phase), phase))
+
+    def add_opd(self, opd):                            # wavefronts.py:351-368
+        if opd is None:
+            return self
+        opd = torch.as_tensor(opd, dtype=torch.float32, device=self.phasor.device)
+        return self.add_phase(self.wavenumber * opd)
+
+    def tilt(self, angles, unit: str = "rad"):         # wavefronts.py:370-395
+        angles = torch.as_tensor(np.asarray(angles, dtype=np.float32) if not torch.is_tensor(angles)
+                                 else angles, dtype=torch.float32, device=self.phasor.device)
+        if tuple(angles.shape) != (2,):
+            raise ValueError("angles must be a 1d array of shape (2,).")
+        if unit != "rad":
+            raise ValueError("only unit='rad' is supported")
+        coords = self.coordinates()
+        return self.add_opd((angles[:, None, None] * coords).sum(0))
+
+    def normalise(self, mode: str = "power", value: float = 1.0):   # wavefronts.py:397-424
+        if mode == "power":
+            scale = torch.sqrt(np.float32(value) / self.power)
+        elif mode == "peak":
+            scale = torch.sqrt(np.float32(value) / self.psf.max())
+        else:
+            raise ValueError("mode must be 'power' or 'peak'")
+        return self.multiply("phasor", scale)
+
+    # ------------------------------------------------------------------ propagation
+    def propagate(self, npixels: int, pixel_scale, focal_length=None, inverse: bool = False,
+                  precision=None):
+        """wavefronts.py:729-772 -> dlu.MFT."""
+        phasor = _prop.MFT(self.phasor, self.wavelength, self.pixel_scale, npixels, pixel_scale,
+                           focal_length=focal_length, inverse=bool(inverse), precision=precision)
+        ps = torch.as_tensor(np.asarray(pixel_scale.detach().cpu() if torch.is_tensor(pixel_scale)
+                                        else pixel_scale, dtype=np.float32), device=phasor.device)
+        return self.set(phasor=phasor, pixel_scale=ps)
+
+    def propagate_MFT(self, spec_out, focal_length=None, inverse=None, precision=None):
+        """wavefronts.py:774-805; ``spec_out`` needs attributes ``n`` and ``d``."""
+        return self.propagate(spec_out.n, spec_out.d, focal_length, bool(inverse), precision)
+
+    def propagate_FFT(self, *a, **k):
+        raise NotImplementedError(
+            "FFT propagation is the NEXT-2 row of the scope table (SURVEY.md 8f); "
+            "only the MFT path is implemented")

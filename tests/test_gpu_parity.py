@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via dlux_b200.ops) against the
+oracle, the committed golden vectors and size-independent properties.
+
+Tolerance (BASELINE.json north_star): relative L2 <= 1e-5 on fields, PSFs and
+gradients, against the reference's complex64 arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import mft_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+PRECS = ["fp32", "3xtf32"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dlux_b200 import _lib
+    _lib.load()          # raises loudly if the native library is missing
+    return torch.device("cuda:0")
+
+
+def _geom(g):
+    n_in, n_out, wl, psi, pso, fl, sx, sy, pixel, inverse = g
+    return dict(n_in=int(n_in), n_out=int(n_out), wl=wl, psi=psi, pso=pso,
+                fl=None if fl < 0 else fl, shift=(sx, sy), pixel=bool(pixel), inverse=bool(inverse))
+
+
+def _rand_c64(rng, *shape):
+    return ((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / shape[-1]).astype(np.complex64)
+
+
+# ------------------------------------------------------------------ bit-exact pieces
+def test_coords_bit_exact(dev):
+    from dlux_b200 import ops
+    cases = [(32, 16, 0.25, 1.0), (96, 40, 0.0817, -2.0), (256, 128, 0.24240684, 0.0),
+             (1024, 512, 0.12207031, 0.5), (100, 37, 1.7, 3.25)]
+    for n_in, n_out, s, shift in cases:
+        sc = torch.tensor([s, s * 1.1], dtype=torch.float32, device=dev)
+        sh = torch.tensor([[shift, -shift], [0.0, 2 * shift]], dtype=torch.float32, device=dev)
+        xin, uout = ops.mft_coords(n_in, n_out, sc, sh)
+        xin, uout = xin.cpu().numpy(), uout.cpu().numpy()
+        for b in range(2):
+            for ax in range(2):
+                sft = np.float32(sh[b, ax].item())
+                sv = np.float32(sc[b].item())
+                ref_in = O.nd_coords_1d(n_in, 1.0 / n_in, sft * np.float32(1.0 / n_in))
+                ref_out = O.nd_coords_1d(n_out, sv, sft * sv)
+                assert np.array_equal(xin[b, ax], ref_in), (n_in, b, ax)
+                assert np.array_equal(uout[b, ax], ref_out), (n_out, b, ax)
+
+
+# ------------------------------------------------------------------ MFT vs reference source
+@pytest.mark.parametrize("prec", PRECS)
+def test_mft_golden_reference_vectors(dev, golden, prec):
+    import dlux_b200 as dl
+    for g in range(int(golden["n_geoms"])):
+        p = _geom(golden[f"mft_{g}_geom"])
+        ph = torch.as_tensor(golden[f"mft_{g}_in"], device=dev)
+        out = dl.utils.MFT(ph, np.float32(p["wl"]), np.float32(p["psi"]), p["n_out"], np.float32(p["pso"]),
+                           None if p["fl"] is None else np.float32(p["fl"]),
+                           np.asarray(p["shift"], np.float32), p["pixel"], p["inverse"], precision=prec)
+        err = rel_l2(out.cpu().numpy(), golden[f"mft_{g}_out"])
+        assert err < TOL, (g, prec, err)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_mft_reference_test_fixture(dev, golden, prec):
+    # /root/reference/tests/utils/test_propagation.py:98-139 (+ values)
+    import dlux_b200 as dl
+    ones32 = torch.ones((32, 32), dtype=torch.complex64, device=dev)
+    k = 0
+    for fl in (None, np.float32(2.0)):
+        for inverse in (False, True):
+            for pixel in (True, False):
+                out = dl.utils.MFT(ones32, np.float32(1.0), np.float32(0.1), 16, np.float32(0.05), fl,
+                                   np.asarray([1.0, -2.0], np.float32), pixel, inverse, precision=prec)
+                assert out.shape == (16, 16)
+                assert not torch.isnan(out.real).any()
+                assert rel_l2(out.cpu().numpy(), golden[f"reftest_{k}"]) < TOL, k
+                k += 1
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_mft_shift_units_identity(dev, prec):
+    # /root/reference/tests/utils/test_propagation.py:141-176
+    import dlux_b200 as dl
+    ph = torch.ones((32, 32), dtype=torch.complex64, device=dev)
+    a = dl.utils.MFT(ph, 1.0, 0.1, 16, 0.05, 2.0, np.asarray([1.0, -2.0], np.float32), True, precision=prec)
+    b = dl.utils.MFT(ph, 1.0, 0.1, 16, 0.05, 2.0, np.asarray([0.05, -0.1], np.float32), False, precision=prec)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n_in,n_out,nl", [(256, 128, 1), (512, 256, 3), (200, 72, 2), (130, 131, 1)])
+def test_mft_vs_oracle_batched(dev, prec, n_in, n_out, nl):
+    import dlux_b200 as dl
+    rng = np.random.default_rng(n_in + n_out)
+    ph = _rand_c64(rng, nl, n_in, n_in)
+    wls = np.linspace(0.9e-6, 1.1e-6, nl).astype(np.float32)
+    ps_in = np.float32(1.0 / n_in)
+    pso = O.arcsec2rad(0.05)
+    out = dl.utils.MFT(torch.as_tensor(ph, device=dev), wls, ps_in, n_out, pso, precision=prec)
+    assert out.shape == (nl, n_out, n_out)
+    for l in range(nl):
+        ref = O.MFT(ph[l], wls[l], ps_in, n_out, pso)
+        err = rel_l2(out[l].cpu().numpy(), ref)
+        assert err < TOL, (l, err)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_adjoint_is_conjugate_transpose(dev, prec):
+    from dlux_b200 import ops
+    rng = np.random.default_rng(7)
+    n_in, n_out = 96, 40
+    x = torch.as_tensor(_rand_c64(rng, 2, n_in, n_in), device=dev)
+    y = torch.as_tensor(_rand_c64(rng, 2, n_out, n_out), device=dev)
+    s = torch.tensor([0.21, 0.33], device=dev)
+    sh = torch.tensor([[0.5, -1.0], [0.0, 2.0]], device=dev)
+    nrm = torch.tensor([0.7, 1.3], device=dev)
+    Ax = ops.mft_c64(x, s, n_out, sh, None, nrm, False, False, prec)
+    Aty = ops.mft_c64(y, s, n_in, sh, None, nrm, False, True, prec)
+    lhs = torch.sum(torch.conj(y) * Ax, dim=(1, 2)).cpu().numpy()
+    rhs = torch.sum(torch.conj(Aty) * x, dim=(1, 2)).cpu().numpy()
+    assert np.allclose(lhs, rhs, rtol=2e-5, atol=1e-8), (lhs, rhs)
+    # against the oracle's matrices
+    xin, uout = ops.mft_coords(n_in, n_out, s, sh)
+    xin, uout = xin.cpu().numpy().astype(np.float64), uout.cpu().numpy().astype(np.float64)
+    for b in range(2):
+        Ay = np.exp(-2j * np.pi * np.outer(xin[b, 1], uout[b, 1]))
+        Axm = np.exp(-2j * np.pi * np.outer(xin[b, 0], uout[b, 0]))
+        ref = float(nrm[b]) * (np.conj(Ay) @ y[b].cpu().numpy().astype(np.complex128) @ np.conj(Axm).T)
+        assert rel_l2(Aty[b].cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_mft_autograd_matches_adjoint(dev, prec):
+    import dlux_b200 as dl
+    rng = np.random.default_rng(8)
+    ph = torch.as_tensor(_rand_c64(rng, 64, 64), device=dev).requires_grad_(True)
+    out = dl.utils.MFT(ph, 1e-6, 1.0 / 64, 32, 1.5e-7, precision=prec)
+    g = torch.as_tensor(_rand_c64(rng, 32, 32), device=dev)
+    loss = (out.real * g.real + out.imag * g.imag).sum()
+    loss.backward()
+    tm = O.transfer_matrix(1e-6, 64, 1.0 / 64, 32, 1.5e-7, dtype=np.float64)
+    nrm = O.mft_norm(O.calc_nfringes(1e-6, 64, 1.0 / 64, 32, 1.5e-7, dtype=np.float64), 64, 32, np.float64)
+    ref = nrm * (np.conj(tm) @ g.cpu().numpy().astype(np.complex128) @ np.conj(tm).T)
+    assert rel_l2(ph.grad.cpu().numpy(), ref) < TOL
+
+
+# ------------------------------------------------------------------ fused poly-PSF
+def _optics_dict(N, M, nz, seed, oversample=1, pscale=0.05):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[:N, :N]
+    r = np.hypot(xx - (N - 1) / 2, yy - (N - 1) / 2) / (N / 2)
+    T = (r <= 1).astype(np.float32)
+    basis = (rng.standard_normal((nz, N, N)).astype(np.float32) * T) * np.float32(2e-8)
+    coeffs = rng.standard_normal(nz).astype(np.float32)
+    return dict(wf_npixels=N, diameter=1.0, psf_npixels=M, psf_pixel_scale=pscale,
+                oversample=oversample, transmission=T, basis=basis, coefficients=coeffs,
+                normalise=True)
+
+
+def _system(od, dev, fused=True, prec=None):
+    import dlux_b200 as dl
+    layer = dl.BasisOptic(od["basis"], od["transmission"], od["coefficients"], "opd", normalise=True,
+                          device=dev)
+    return dl.AngularOpticalSystem(od["wf_npixels"], od["diameter"], [("aperture", layer)],
+                                   od["psf_npixels"], od["psf_pixel_scale"], od["oversample"],
+                                   device=dev, fused=fused, precision=prec)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_config1_angular_system_psf(dev, prec):
+    # BASELINE config 1: 256 px circular aperture + 10-term basis OPD, 1 source, 1 wavelength,
+    # MFT to 128x128
+    od = _optics_dict(256, 128, 10, 0)
+    sys_ = _system(od, dev, True, prec)
+    psf = sys_.propagate(np.array([1.0e-6], np.float32))
+    ref = O.propagate(od, [1.0e-6])
+    assert psf.shape == (128, 128)
+    assert rel_l2(psf.cpu().numpy(), ref) < TOL
+    # the layer-by-layer route gives the same numbers
+    psf2 = _system(od, dev, False, prec).propagate(np.array([1.0e-6], np.float32))
+    assert rel_l2(psf2.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_polychromatic_offset_weights(dev, prec):
+    od = _optics_dict(128, 64, 5, 1, oversample=2, pscale=0.08)
+    sys_ = _system(od, dev, True, prec)
+    wls = np.linspace(0.9e-6, 1.1e-6, 5).astype(np.float32)
+    w = np.array([0.1, 0.3, 0.2, 0.25, 0.15], np.float32)
+    off = np.array([3.0e-7, -2.0e-7], np.float32)
+    psf = sys_.propagate(wls, off, w)
+    ref = O.propagate(od, wls, off, w)
+    assert psf.shape == (128, 128)
+    assert rel_l2(psf.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_point_sources_model(dev, prec):
+    import dlux_b200 as dl
+    od = _optics_dict(96, 48, 4, 2)
+    sys_ = _system(od, dev, True, prec)
+    wls = np.linspace(0.95e-6, 1.05e-6, 3).astype(np.float32)
+    pos = np.array([[1e-7, -2e-7], [-3e-7, 0.5e-7], [0.0, 0.0]], np.float32)
+    flux = np.array([3.0, 0.25, 1.0], np.float32)
+    src = dl.PointSources(wls, pos, flux)
+    psf = sys_.model(src)
+    ref = O.point_sources_model(od, wls, pos, flux)
+    assert rel_l2(psf.cpu().numpy(), ref) < TOL
+    one = dl.PointSource(wls, pos[0], 3.0)
+    assert rel_l2(sys_.model(one).cpu().numpy(), O.point_source_model(od, wls, pos[0], 3.0)) < TOL
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_phase_retrieval_gradient(dev, prec):
+    # BASELINE config 2 (scaled down): grad of a PSF loss w.r.t. the basis coefficients
+    import dlux_b200 as dl
+    from oracle import torch_twin
+    N, M, nz = 128, 64, 6
+    od = _optics_dict(N, M, nz, 3)
+    wls = np.linspace(0.9e-6, 1.1e-6, 4).astype(np.float32)
+    w = np.full(4, 0.25, np.float32)
+    off = np.array([2.0e-7, 1.0e-7], np.float32)
+    rng = np.random.default_rng(30)
+    G = rng.standard_normal((M, M)).astype(np.float32)
+
+    coeffs = torch.as_tensor(od["coefficients"], device=dev).requires_grad_(True)
+    wt = torch.as_tensor(w, device=dev).requires_grad_(True)
+    layer = dl.BasisOptic(od["basis"], od["transmission"], coeffs, "opd", normalise=True, device=dev)
+    sys_ = dl.AngularOpticalSystem(N, 1.0, [("aperture", layer)], M, 0.05, device=dev, precision=prec)
+    psf = sys_.propagate(wls, off, wt)
+    loss = (psf * torch.as_tensor(G, device=dev)).sum()
+    loss.backward()
+
+    c_ref = torch.tensor(od["coefficients"], dtype=torch.float64, requires_grad=True)
+    w_ref = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    psf_ref = torch_twin.poly_psf(od["transmission"], None, wls, w_ref, diameter=1.0, psf_npixels=M,
+                                  pixel_scale_rad=O.arcsec2rad(0.05), offset=off, basis=od["basis"],
+                                  coefficients=c_ref, dtype=np.float64)
+    (psf_ref * torch.tensor(G, dtype=torch.float64)).sum().backward()
+    assert rel_l2(psf.detach().cpu().numpy(), psf_ref.detach().numpy()) < TOL
+    assert rel_l2(coeffs.grad.cpu().numpy(), c_ref.grad.numpy()) < TOL
+    assert rel_l2(wt.grad.cpu().numpy(), w_ref.grad.numpy()) < TOL
+
+
+# ------------------------------------------------------------------ full-size properties (C3)
+@pytest.mark.parametrize("prec", ["3xtf32"])
+def test_c3_size_properties(dev, prec):
+    """1024 -> 512 (BASELINE config 3 shape): linearity, inverse symmetry and agreement
+    with the fp32 CUDA-core path -- properties that do not need the oracle at full size."""
+    from dlux_b200 import ops
+    rng = np.random.default_rng(11)
+    N, M = 1024, 512
+    x = torch.as_tensor(_rand_c64(rng, 2, N, N), device=dev)
+    s = torch.tensor([0.1221, 0.1180], device=dev)
+    nrm = s / N
+    a = ops.mft_c64(x, s, M, None, None, nrm, False, False, prec)
+    lin = ops.mft_c64((2.0 * x[0] - 0.5j * x[1])[None], s[:1], M, None, None, nrm[:1], False, False, prec)
+    a1 = ops.mft_c64(x[1:2], s[:1], M, None, None, nrm[:1], False, False, prec)
+    assert rel_l2(lin[0].cpu().numpy(), (2.0 * a[0] - 0.5j * a1[0]).cpu().numpy()) < TOL
+    inv = ops.mft_c64(torch.conj(x), s, M, None, None, nrm, True, False, prec)
+    assert rel_l2(torch.conj(inv).cpu().numpy(), a.cpu().numpy()) < TOL
+    ref = ops.mft_c64(x, s, M, None, None, nrm, False, False, "fp32")
+    assert rel_l2(a.cpu().numpy(), ref.cpu().numpy()) < TOL
+    # one wavelength against the oracle at full size (a few seconds of CPU)
+    ps_in = np.float32(6.6 / N)
+    pso = O.arcsec2rad(0.0656 / 4)
+    import dlux_b200 as dl
+    out = dl.utils.MFT(x[0], np.float32(4.3e-6), ps_in, M, pso, precision=prec)
+    assert rel_l2(out.cpu().numpy(), O.MFT(x[0].cpu().numpy(), 4.3e-6, ps_in, M, pso)) < TOL
+
+
+# ------------------------------------------------------------------ API behaviour
+def test_api_errors_and_shapes(dev):
+    import dlux_b200 as dl
+    wf = dl.Wavefront(1e-6, 16, diameter=1.0, device=dev)
+    out = wf.propagate(8, 1e-7)
+    assert isinstance(out, dl.Wavefront) and out.phasor.shape == (8, 8)
+    assert isinstance(dl.MFT(8, 1e-7)(wf), dl.Wavefront)
+    with pytest.raises(ValueError):
+        dl.Wavefront(1e-6, 16)
+    with pytest.raises(ValueError):
+        dl.Wavefront(1e-6, 16, diameter=1.0, pixel_scale=0.1)
+    sys_ = _system(_optics_dict(16, 8, 2, 5), dev)
+    with pytest.raises(ValueError, match="shape mismatch"):
+        sys_.propagate(np.array([1e-6, 2e-6]), None, np.ones(3))
+    with pytest.raises(ValueError, match="offset must be"):
+        sys_.propagate(np.array([1e-6]), np.zeros(3))
+    with pytest.raises(ValueError, match="Cannot return both"):
+        sys_.propagate(np.array([1e-6]), return_wf=True, return_psf=True)
+    with pytest.raises(TypeError):
+        dl.utils.MFT(torch.ones((8, 8), dtype=torch.complex128, device=dev), 1e-6, 0.1, 4, 1e-7)
+    with pytest.raises(ValueError):
+        dl.utils.MFT(torch.ones((8, 8), dtype=torch.complex64), 1e-6, 0.1, 4, 1e-7)  # CPU tensor

@@ -1,0 +1,120 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares,
+host-side geometry matches the oracle bit for bit, and the mirrored API validates its
+arguments like the reference.  No compute calls (there is no GPU here)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mft_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, ROOT)
+    from dlux_b200 import build, _lib
+    build.build()                       # no-op when up to date; nvcc cross-compiles on CPU
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from dlux_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dlux_b200.h")).read()
+    declared = set(re.findall(r"DLUX_API\s+[\w\s\*]+?\b(dlux_\w+)\s*\(", hdr))
+    assert len(declared) >= 12
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (dlux_\w+)", nm))
+    assert declared <= exported, declared - exported
+    assert lib.dlux_abi_version() == 1
+    assert lib.dlux_error_string(-3) == b"scratch buffer too small"
+
+
+def test_scratch_sizes_and_arg_checks(lib):
+    import ctypes as C
+    from dlux_b200._lib import MftDesc, PolyPsfDesc
+    d = MftDesc(1024, 512, 64, 0, 0, 0)
+    n = lib.dlux_mft_scratch_bytes(C.byref(d))
+    assert 64 * 1024 * 1024 < n < 4 * 1024 ** 3
+    assert lib.dlux_mft_scratch_bytes(C.byref(MftDesc(0, 8, 1, 0, 0, 0))) == 0
+    p = PolyPsfDesc(1024, 512, 64, 1, 1, 0, 1, 0)
+    assert lib.dlux_polypsf_scratch_bytes(C.byref(p)) > 64 * 1024 * 1024
+    # null pointers are rejected before any CUDA call
+    assert lib.dlux_mft_c64(C.byref(d), None, None, None, None, None, None, None, 0, None) == -1
+    assert lib.dlux_mft_c64(C.byref(MftDesc(8, 8, 1, 0, 0, 7)), None, None, None, None, None, None,
+                            None, 0, None) == -1
+    assert lib.dlux_basis_eval(0, 10, None, None, None, None, None) == -1
+
+
+def test_missing_library_is_loud(monkeypatch):
+    from dlux_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdlux_b200.so")
+    with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_cpu_tensors_rejected():
+    import dlux_b200 as dl
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        dl.utils.MFT(torch.ones((8, 8), dtype=torch.complex64), 1e-6, 0.1, 4, 1e-7)
+
+
+def test_geometry_scalars_match_oracle_bits():
+    from dlux_b200.utils import propagation as P
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        wl = np.float32(rng.uniform(4e-7, 5e-6))
+        n_in, n_out = int(rng.integers(16, 2049)), int(rng.integers(8, 1025))
+        psi = np.float32(rng.uniform(0.1, 8.0) / n_in)
+        pso = np.float32(rng.uniform(1e-8, 1e-6))
+        fl = None if rng.random() < 0.5 else np.float32(rng.uniform(0.5, 20.0))
+        s, nrm = P.mft_geometry(wl, n_in, psi, n_out, pso, fl)
+        assert np.float32(s) == O.mft_scalars(wl, n_in, psi, pso, fl)
+        nf = O.calc_nfringes(wl, n_in, psi, n_out, pso, fl)
+        assert np.float32(P.calc_nfringes(wl, n_in, psi, n_out, pso, fl)) == nf
+        assert np.float32(nrm) == O.mft_norm(nf, n_in, n_out)
+    # vectorised over wavelengths
+    wls = np.linspace(0.9e-6, 1.1e-6, 7).astype(np.float32)
+    s, nrm = P.mft_geometry(wls, 512, np.float32(1 / 512), 256, np.float32(1.2e-7))
+    for i, wl in enumerate(wls):
+        assert s[i] == O.mft_scalars(wl, 512, np.float32(1 / 512), np.float32(1.2e-7))
+    assert P.arcsec2rad(np.float32(0.05)) == O.arcsec2rad(0.05)
+
+
+def test_fusable_logic_and_validation():
+    import dlux_b200 as dl
+    T = np.ones((8, 8), np.float32)
+    basis = np.zeros((2, 8, 8), np.float32)
+    mk = lambda layers: dl.AngularOpticalSystem(8, 1.0, layers, 4, 0.1, device="cpu")
+    s1 = mk([dl.Optic(T, np.zeros((8, 8), np.float32), normalise=True, device="cpu")])
+    T_, opd, phase, norm = s1._fusable()
+    assert norm and phase is None and opd.shape == (8, 8) and T_.shape == (8, 8)
+    # a transmission after the normalisation changes the power: not fusable
+    s2 = mk([dl.Optic(T, normalise=True, device="cpu"), dl.TransmissiveLayer(T * 0.5, device="cpu")])
+    assert s2._fusable() is None
+    # an MFT layer in the stack is not pupil-only
+    s3 = mk([dl.Optic(T, device="cpu"), dl.MFT(4, 1e-7)])
+    assert s3._fusable() is None
+    # evaluating a basis needs the CUDA kernel: loud error on a CPU tensor
+    s4 = mk([dl.BasisOptic(basis, T, np.zeros(2, np.float32), normalise=True, device="cpu")])
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        s4._fusable()
+    with pytest.raises(ValueError, match="effect must be"):
+        dl.BasisLayer(basis, effect="bogus", device="cpu")
+    with pytest.raises(ValueError, match="same shape"):
+        dl.AberratedLayer(np.zeros((4, 4)), np.zeros((5, 5)), device="cpu")
+    with pytest.raises(ValueError, match="2d array"):
+        dl.PointSources(np.array([1e-6]), np.zeros(2))
+    with pytest.raises(ValueError, match="Length of flux"):
+        dl.PointSources(np.array([1e-6]), np.zeros((3, 2)), np.ones(2))
+    src = dl.PointSource(np.array([1e-6, 2e-6]), weights=np.array([2.0, 6.0]))
+    assert np.allclose(src.normalised_weights(), [0.25, 0.75])
+    npix, ps, fl = s1._focal_args()
+    assert npix == 4 and fl is None and ps == O.arcsec2rad(np.float32(0.1))
