@@ -61,9 +61,15 @@ static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
 
 static const size_t kChunkBudget = (size_t)1 << 30;  // per-chunk intermediates, bytes
 
+// intermediate planes hold [M][pitch(N)] (forward) or [N][pitch(M)] (adjoint)
+static size_t mid_elems(int N, int M) {
+  const size_t a = (size_t)M * pitch4(N), b = (size_t)N * pitch4(M);
+  return a > b ? a : b;
+}
+
 static int mft_chunk(const dlux_mft_desc* d) {
   const size_t n_src = d->adjoint ? d->n_out : d->n_in;
-  const size_t per_item = 16 * n_src * n_src + 16 * (size_t)d->n_in * d->n_out +
+  const size_t per_item = 16 * n_src * pitch4((int)n_src) + 16 * mid_elems(d->n_in, d->n_out) +
                           8 * (size_t)(d->n_in + d->n_out);
   size_t c = kChunkBudget / per_item;
   if (c < 1) c = 1;
@@ -81,8 +87,8 @@ static size_t carve_mft(const dlux_mft_desc* d, void* scratch, size_t cap, MftSc
   const size_t n_src = d->adjoint ? d->n_out : d->n_in;
   s->xin = b.take<float>(c * 2 * d->n_in);
   s->uout = b.take<float>(c * 2 * d->n_out);
-  for (int i = 0; i < 4; ++i) s->in_pl[i] = b.take<float>(c * n_src * n_src);
-  for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * (size_t)d->n_in * d->n_out);
+  for (int i = 0; i < 4; ++i) s->in_pl[i] = b.take<float>(c * n_src * pitch4((int)n_src));
+  for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * mid_elems(d->n_in, d->n_out));
   b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
   if (ok) *ok = b.ok;
   return b.used();
@@ -103,6 +109,7 @@ static void fill_stage(GemmParams& g, bool adjoint, int stage, int N, int M, int
   // axis 0 = x (contracts the column index j / b), axis 1 = y (row index i / a)
   const int axis = stage == 0 ? 0 : 1;
   g.n_items = c;
+  g.n_data = c;
   g.item_data = nullptr;
   g.sign2pi = sign2pi;
   if (!adjoint) {
@@ -122,6 +129,8 @@ static void fill_stage(GemmParams& g, bool adjoint, int stage, int N, int M, int
     g.nvec = xin + (size_t)axis * N;
     g.nvec_stride = 2 * N;
   }
+  g.a_pitch = pitch4(g.K);
+  g.out_pitch = pitch4(g.rows);  // EPI_PLANES output is the next stage's data: its K is this stage's rows
 }
 
 }  // namespace dlux
@@ -189,7 +198,7 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
     rc = launch_coords(N, M, c, scale_out + b0, shift_xy ? shift_xy + 2 * (size_t)b0 : nullptr,
                        delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr, 1, s.xin, s.uout, st);
     if (rc) return rc;
-    rc = launch_split_c64((const float2*)in + (size_t)b0 * n_src * n_src, (size_t)c * n_src * n_src,
+    rc = launch_split_c64((const float2*)in + (size_t)b0 * n_src * n_src, (size_t)c * n_src, (int)n_src,
                           s.in_pl[0], s.in_pl[1], s.in_pl[2], s.in_pl[3], st);
     if (rc) return rc;
     GemmParams g{};
@@ -225,7 +234,7 @@ struct PolyScratch {
 
 static int poly_chunk(const dlux_polypsf_desc* d) {
   const size_t N = d->n_pupil, M = d->n_psf;
-  const size_t per_item = 16 * M * N + 16 * M * M + 8 * (N + M);
+  const size_t per_item = 16 * mid_elems((int)N, (int)M) + 16 * M * pitch4((int)M) + 8 * (N + M);
   size_t c = kChunkBudget / per_item;
   const size_t items = (size_t)d->n_sources * d->n_wavels;
   if (c < 1) c = 1;
@@ -240,15 +249,15 @@ static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, 
   const size_t c = poly_chunk(d);
   s->chunk = (int)c;
   s->amp_scale = b.take<float>(4 + 512);
-  for (int i = 0; i < 4; ++i) s->p_pl[i] = b.take<float>(L * N * N);
+  for (int i = 0; i < 4; ++i) s->p_pl[i] = b.take<float>(L * N * pitch4((int)N));
   s->item_l = b.take<int>(items);
   s->s_item = b.take<float>(items);
   s->norm_item = b.take<float>(items);
   s->k_item = b.take<float>(items);
   s->xin = b.take<float>(c * 2 * N);
   s->uout = b.take<float>(c * 2 * M);
-  for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * M * N);
-  for (int i = 0; i < 4; ++i) s->ebar_pl[i] = b.take<float>(c * M * M);
+  for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * mid_elems((int)N, (int)M));
+  for (int i = 0; i < 4; ++i) s->ebar_pl[i] = b.take<float>(c * M * pitch4((int)M));
   b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
   if (ok) *ok = b.ok;
   return b.used();
@@ -314,6 +323,7 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
     GemmParams g{};
     fill_stage(g, false, 0, N, M, c, s.xin, s.uout, sign2pi);
     g.item_data = s.item_l + b0;
+    g.n_data = L;
     for (int i = 0; i < 4; ++i) { g.a_planes[i] = s.p_pl[i]; g.out_planes[i] = s.mid_pl[i]; }
     g.mode = EPI_PLANES;
     rc = run_gemm(g, d->precision, st);
@@ -378,6 +388,7 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     h.scale = s.norm_item + b0;
     h.w = s.k_item + b0;
     h.item_p = s.item_l + b0;
+    h.p_pitch = pitch4(N);
     h.opd_bar = opd_bar;
     h.phase_bar = phase_bar;
     rc = run_gemm(h, d->precision, st);

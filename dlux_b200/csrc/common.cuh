@@ -27,6 +27,8 @@ enum EpilogueMode : int {
 struct GemmParams {
   // data operand: 4 planes, each [n_data][rows][K] float32
   const float* a_planes[4];
+  int a_pitch;  // floats per data row (>= K, multiple of 4 so TMA can stride it)
+  int n_data;   // number of data matrices in a_planes
   int rows;    // M dimension of the data matrix (rows m)
   int K;       // contraction length
   int n_out;   // number of generated output coordinates (n)
@@ -38,11 +40,13 @@ struct GemmParams {
   float sign2pi;         // float32(-2*pi) forward, float32(+2*pi) inverse / adjoint-of-forward
   const float* scale;    // [n_items] or nullptr
   int mode;
-  float* out_planes[4];  // EPI_PLANES
+  float* out_planes[4];  // EPI_PLANES: [n_items][n_out][out_pitch]
+  int out_pitch;
   float2* out_c64;       // EPI_C64 / optional for EPI_PSF
   float* psf;            // EPI_PSF: [n_out][rows]
   const float* w;        // EPI_PSF weights [n_items]; EPI_GRAD: wavenumber per item
-  const float* p_planes[4];  // EPI_GRAD: pupil planes [n_p][n_out][rows]
+  const float* p_planes[4];  // EPI_GRAD: pupil planes [n_p][n_out][p_pitch]
+  int p_pitch;
   const int* item_p;     // EPI_GRAD: item -> pupil index (nullptr = identity)
   float* opd_bar;        // EPI_GRAD
   float* phase_bar;      // EPI_GRAD
@@ -67,11 +71,12 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
   im *= sc;
   const size_t idx = ((size_t)item * p.n_out + n) * p.rows + m;
   if (p.mode == EPI_PLANES) {
+    const size_t po = ((size_t)item * p.n_out + n) * p.out_pitch + m;
     const float rh = tf32_hi(re), ih = tf32_hi(im);
-    p.out_planes[0][idx] = rh;
-    p.out_planes[1][idx] = re - rh;
-    p.out_planes[2][idx] = ih;
-    p.out_planes[3][idx] = im - ih;
+    p.out_planes[0][po] = rh;
+    p.out_planes[1][po] = re - rh;
+    p.out_planes[2][po] = ih;
+    p.out_planes[3][po] = im - ih;
   } else if (p.mode == EPI_C64) {
     p.out_c64[idx] = make_float2(re, im);
   } else if (p.mode == EPI_PSF) {
@@ -80,7 +85,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
     atomicAdd(p.psf + (size_t)n * p.rows + m, w * (re * re + im * im));
   } else {  // EPI_GRAD
     const int ip = p.item_p ? __ldg(p.item_p + item) : item;
-    const size_t pi = ((size_t)ip * p.n_out + n) * p.rows + m;
+    const size_t pi = ((size_t)ip * p.n_out + n) * p.p_pitch + m;
     const float pr = __ldg(p.p_planes[0] + pi) + __ldg(p.p_planes[1] + pi);
     const float pim = __ldg(p.p_planes[2] + pi) + __ldg(p.p_planes[3] + pi);
     const float g = pr * im - pim * re;  // Im(conj(P) * v)
@@ -102,8 +107,10 @@ size_t gemm_tc_workspace_bytes();
 int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const float* shift_xy,
                   const float* delta_xy, int delta_stride_items, float* xin, float* uout,
                   cudaStream_t st);
-int launch_split_c64(const float2* in, size_t n, float* p0, float* p1, float* p2, float* p3,
-                     cudaStream_t st);
+__host__ __device__ inline int pitch4(int k) { return (k + 3) & ~3; }
+// in: [n_mat][rows][cols] c64 -> planes [n_mat][rows][pitch4(cols)]
+int launch_split_c64(const float2* in, size_t n_mat_rows, int cols, float* p0, float* p1, float* p2,
+                     float* p3, cudaStream_t st);
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
                  const float* wavenumber, const float* amp_scale /*device scalar*/,
                  float* p0, float* p1, float* p2, float* p3, cudaStream_t st);

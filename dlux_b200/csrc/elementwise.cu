@@ -69,24 +69,28 @@ int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const 
 
 // ---------------------------------------------------------------------------
 // complex64 interleaved -> 4 planar planes (re_hi, re_lo, im_hi, im_lo), hi = rna tf32
-__global__ void split_c64_kernel(const float2* __restrict__ in, size_t n, float* __restrict__ p0,
-                                 float* __restrict__ p1, float* __restrict__ p2,
-                                 float* __restrict__ p3) {
+__global__ void split_c64_kernel(const float2* __restrict__ in, size_t n_rows, int cols, int pitch,
+                                 float* __restrict__ p0, float* __restrict__ p1,
+                                 float* __restrict__ p2, float* __restrict__ p3) {
+  const size_t n = n_rows * (size_t)cols;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols;
+    const size_t o = r * pitch + (i - r * cols);
     const float2 v = in[i];
     const float rh = tf32_hi(v.x), ih = tf32_hi(v.y);
-    p0[i] = rh;
-    p1[i] = v.x - rh;
-    p2[i] = ih;
-    p3[i] = v.y - ih;
+    p0[o] = rh;
+    p1[o] = v.x - rh;
+    p2[o] = ih;
+    p3[o] = v.y - ih;
   }
 }
 
-int launch_split_c64(const float2* in, size_t n, float* p0, float* p1, float* p2, float* p3,
-                     cudaStream_t st) {
-  if (n == 0) return DLUX_OK;
-  split_c64_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, n, p0, p1, p2, p3);
+int launch_split_c64(const float2* in, size_t n_rows, int cols, float* p0, float* p1, float* p2,
+                     float* p3, cudaStream_t st) {
+  if (n_rows == 0) return DLUX_OK;
+  split_c64_kernel<<<grid_for(n_rows * cols, 256), 256, 0, st>>>(in, n_rows, cols, pitch4(cols), p0, p1,
+                                                                  p2, p3);
   note_launch();
   return check_launch("split_c64");
 }
@@ -141,6 +145,7 @@ __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const fl
                              const float* __restrict__ amp_scale, float* __restrict__ p0,
                              float* __restrict__ p1, float* __restrict__ p2, float* __restrict__ p3) {
   const size_t n = (size_t)N * N;
+  const int pitch = pitch4(N);
   const float a0 = 1.0f / (float)((long long)N * N);
   const float sc = amp_scale[0];
   const int l = blockIdx.y;
@@ -165,7 +170,8 @@ __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const fl
     }
     re *= sc;
     im *= sc;
-    const size_t o = (size_t)l * n + i;
+    const size_t r = i / N;
+    const size_t o = ((size_t)l * N + r) * pitch + (i - r * N);
     const float rh = tf32_hi(re), ih = tf32_hi(im);
     p0[o] = rh;
     p1[o] = re - rh;
@@ -201,7 +207,8 @@ __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
     const float g = psf_bar[i];
     acc += g * (e.x * e.x + e.y * e.y);
     const float re = w2 * g * e.x, im = w2 * g * e.y;
-    const size_t o = (size_t)item * n + i;
+    const size_t r = i / M;
+    const size_t o = ((size_t)item * M + r) * pitch4(M) + (i - r * M);
     const float rh = tf32_hi(re), ih = tf32_hi(im);
     p0[o] = rh;
     p1[o] = re - rh;
@@ -224,9 +231,10 @@ int launch_cotangent(int M, int n_items, const float2* field, const float* psf_b
   for (int b0 = 0; b0 < n_items; b0 += 65535) {
     int nb = n_items - b0 < 65535 ? n_items - b0 : 65535;
     const size_t off = (size_t)b0 * M * M;
+    const size_t poff = (size_t)b0 * M * pitch4(M);
     dim3 grid(grid_for((size_t)M * M, 256, 64), nb);
-    cotangent_kernel<<<grid, 256, 0, st>>>(M, field + off, psf_bar, w + b0, p0 + off, p1 + off,
-                                            p2 + off, p3 + off, w_bar ? w_bar + b0 : nullptr);
+    cotangent_kernel<<<grid, 256, 0, st>>>(M, field + off, psf_bar, w + b0, p0 + poff, p1 + poff,
+                                            p2 + poff, p3 + poff, w_bar ? w_bar + b0 : nullptr);
     note_launch();
   }
   return check_launch("cotangent");

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p, int t
   const int t = blockIdx.x % tiles;
   const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
   const int d = p.item_data ? __ldg(p.item_data + item) : item;
-  const size_t a_off = (size_t)d * p.rows * p.K;
+  const size_t a_off = (size_t)d * p.rows * p.a_pitch;
   const float* kv = p.kvec + (size_t)item * p.kvec_stride;
   const float* nv = p.nvec + (size_t)item * p.nvec_stride;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p, int t
       const int m = m0 + ml, k = k0 + kl;
       float re = 0.0f, im = 0.0f;
       if (m < p.rows && k < p.K) {
-        const size_t o = a_off + (size_t)m * p.K + k;
+        const size_t o = a_off + (size_t)m * p.a_pitch + k;
         re = __ldg(p.a_planes[0] + o) + __ldg(p.a_planes[1] + o);
         im = __ldg(p.a_planes[2] + o) + __ldg(p.a_planes[3] + o);
       }

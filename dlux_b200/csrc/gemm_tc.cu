@@ -1,5 +1,442 @@
+// DLUX_PREC_3XTF32: the phasor GEMM stage on Blackwell tensor cores (sm_100a).
+//
+//   D[m][n] = sum_k Data[m][k] * G[k][n],   G[k][n] = exp(i * fl(sign2pi * fl(kvec[k]*nvec[n])))
+//
+// * A operand (data): four planar fp32 planes (re_hi, re_lo, im_hi, im_lo; hi = rna-tf32,
+//   lo = exact residual) streamed by TMA (cp.async.bulk.tensor, SWIZZLE_64B, K-major).
+// * B operand (DFT phasors): never materialised in HBM.  Generator warps evaluate the
+//   reference's float32 phase argument, sincosf, split into tf32 hi/lo and write K-major
+//   SWIZZLE_64B tiles straight into shared memory (generic proxy -> fence.proxy.async ->
+//   mbarrier).  Two stacked arrangements of the same 64 phasor columns are written,
+//   B1 = [cos; sin] and B2 = [-sin; cos] (128 rows each), so that ONE N=128 MMA produces
+//   the real and the imaginary halves of the complex product:
+//       [Re | Im] += A_re * B1 + A_im * B2.
+// * 3xTF32: 6 tcgen05.mma kind::tf32 (M128 x N128 x K8) per k-step -- lo*hi, hi*lo and
+//   hi*hi for each of the two products; lo*lo is dropped (2^-22 relative).
+// * Tensor-core fp32 accumulation truncates (measured: ~2e-8 relative per accumulate,
+//   systematic), so long K chains are NOT kept in TMEM: every FLUSH_CHUNKS k-chunks the
+//   partial accumulator (one of four 128-column TMEM buffers) is drained by the epilogue
+//   warps with tcgen05.ld and added, round-to-nearest, into fp32 registers (the scheme of
+//   Ootomo & Yokota for error-corrected TF32 GEMM).  Draining overlaps the MMAs of the
+//   next partial.
+// * Persistent CTAs, one per SM; warp roles: 0 TMA producer, 1 MMA issuer, 2..5 drain +
+//   fused epilogue (coalesced transposed stores), 6.. phasor generators.
+#include <cuda.h>
+#include <cstdio>
+#include <mutex>
 #include "common.cuh"
+
 namespace dlux {
-size_t gemm_tc_workspace_bytes() { return 0; }
-int launch_gemm_tc(const GemmParams& p, cudaStream_t st) { return DLUX_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BM = 128;            // data rows per tile (UMMA M)
+constexpr int NB = 64;             // generated output coordinates per tile
+constexpr int BN = 2 * NB;         // UMMA N: [Re | Im] halves
+constexpr int BK = 16;             // k per pipeline stage = one 64-byte swizzle row of fp32
+constexpr int UMMA_K = 8;          // kind::tf32
+constexpr int STAGES = 3;
+constexpr int PLANE_BYTES = BM * BK * 4;            // 8 KiB
+constexpr int A_BYTES = 4 * PLANE_BYTES;            // 32 KiB: re_hi, re_lo, im_hi, im_lo
+constexpr int B_BYTES = 4 * BN * BK * 4;            // 32 KiB: B1_hi, B1_lo, B2_hi, B2_lo
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 64 KiB
+constexpr int FLUSH_CHUNKS = 4;    // k-chunks accumulated in TMEM before draining to registers
+constexpr int NUM_ACC = 4;         // TMEM partial-accumulator ring
+constexpr int NUM_GEN_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_GEN_THREADS = 32 * NUM_GEN_WARPS;
+constexpr int PH_PER_THREAD = NB * BK / NUM_GEN_THREADS;  // phasors per generator thread per chunk
+constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS + NUM_GEN_WARPS);
+constexpr int TMEM_COLS = NUM_ACC * BN;  // 512
+static_assert(TMEM_COLS == 512, "TMEM ring must be a power of two <= 512 columns");
+static_assert(PH_PER_THREAD % 4 == 0, "each generator thread writes whole 16-byte chunks");
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused) | SBO>>4 [32,46) (8 rows * 64 B = 512)
+// | version=1 [46,48) | layout_type=4 (SWIZZLE_64B) [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32, K-major both, N=128, M=128.
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+
+struct TcParams {
+  GemmParams g;
+  int tiles_m, tiles_n, n_tiles, k_chunks;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+               const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
+               const TcParams tp) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmParams& p = tp.g;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of the aligned base
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
+  uint32_t* tmem_slot =
+      reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map0));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map1));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map2));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map3));
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1 + NUM_GEN_WARPS);  // TMA producer (expect_tx) + one arrive per generator warp
+      mbar_init(empty_bar(s), 1);                 // tcgen05.commit
+    }
+    for (int a = 0; a < NUM_ACC; ++a) {
+      mbar_init(tfull_bar(a), 1);                    // tcgen05.commit closing a partial
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS * 32);  // every drain thread
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_item = tp.tiles_m * tp.tiles_n;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
+        const int item = tile / tiles_per_item;
+        const int t = tile % tiles_per_item;
+        const int m0 = (t % tp.tiles_m) * BM;
+        const int d = p.item_data ? __ldg(p.item_data + item) : item;
+        for (int kc = 0; kc < tp.k_chunks; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
+          tma_load_3d(a_dst + 0 * PLANE_BYTES, &map0, full_bar(stage), kc * BK, m0, d);
+          tma_load_3d(a_dst + 1 * PLANE_BYTES, &map1, full_bar(stage), kc * BK, m0, d);
+          tma_load_3d(a_dst + 2 * PLANE_BYTES, &map2, full_bar(stage), kc * BK, m0, d);
+          tma_load_3d(a_dst + 3 * PLANE_BYTES, &map3, full_bar(stage), kc * BK, m0, d);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < tp.k_chunks; ++kc) {
+          const int in_partial = kc % FLUSH_CHUNKS;
+          if (in_partial == 0) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // drain warps are done with this buffer
+            tc_fence_after();
+          }
+          const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_base + stage * STAGE_BYTES;
+          const uint32_t b0 = a0 + A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint32_t koff = ks * UMMA_K * 4;  // bytes inside the 64-byte swizzle row
+            const uint64_t a_rh = make_desc_sw64(a0 + 0 * PLANE_BYTES + koff);
+            const uint64_t a_rl = make_desc_sw64(a0 + 1 * PLANE_BYTES + koff);
+            const uint64_t a_ih = make_desc_sw64(a0 + 2 * PLANE_BYTES + koff);
+            const uint64_t a_il = make_desc_sw64(a0 + 3 * PLANE_BYTES + koff);
+            const uint64_t b1h = make_desc_sw64(b0 + 0 * PLANE_BYTES + koff);
+            const uint64_t b1l = make_desc_sw64(b0 + 1 * PLANE_BYTES + koff);
+            const uint64_t b2h = make_desc_sw64(b0 + 2 * PLANE_BYTES + koff);
+            const uint64_t b2l = make_desc_sw64(b0 + 3 * PLANE_BYTES + koff);
+            const uint32_t accum = (in_partial | ks) ? 1u : 0u;
+            // [Re | Im] += A_re * [cos; sin] + A_im * [-sin; cos]; small terms first
+            umma_tf32(d, a_rl, b1h, IDESC, accum);
+            umma_tf32(d, a_rh, b1l, IDESC, 1u);
+            umma_tf32(d, a_il, b2h, IDESC, 1u);
+            umma_tf32(d, a_ih, b2l, IDESC, 1u);
+            umma_tf32(d, a_rh, b1h, IDESC, 1u);
+            umma_tf32(d, a_ih, b2h, IDESC, 1u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (in_partial == FLUSH_CHUNKS - 1 || kc == tp.k_chunks - 1) {
+            umma_commit(tfull_bar(acc));  // partial complete -> drain warps
+            if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 2 + NUM_EPI_WARPS) {
+    // ===================== drain + epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int n_partials = (tp.k_chunks + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS;
+    for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
+      const int item = tile / tiles_per_item;
+      const int t = tile % tiles_per_item;
+      const int m = (t % tp.tiles_m) * BM + q * 32 + lane;
+      const int n0 = (t / tp.tiles_m) * NB;
+      float tot[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) tot[j] = 0.0f;
+      for (int part = 0; part < n_partials; ++part) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v0[16], v1[16];
+          tmem_ld16(t0 + c, v0);
+          tmem_ld16(t0 + c + 16, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            tot[c + j] += __uint_as_float(v0[j]);
+            tot[c + 16 + j] += __uint_as_float(v1[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+      if (m < p.rows) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int n = n0 + j;
+          if (n < p.n_out) epilogue_store(p, item, m, n, tot[j], tot[NB + j]);
+        }
+      }
+    }
+  } else {
+    // ===================== phasor generators =====================
+    const int gt = threadIdx.x - 32 * (2 + NUM_EPI_WARPS);
+    const int nl = gt & (NB - 1);   // output coordinate within the tile
+    const int kg = gt / NB;         // which PH_PER_THREAD-wide k group of the chunk
+    int stage = 0;
+    uint32_t phase = 0;
+    // SWIZZLE_64B: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3).  Rows nl
+    // and nl + 64 share the same swizzle term (64 is a multiple of 8).
+    const uint32_t row_lo = (uint32_t)nl * 64u;          // rows [0, 64): cos (B1) / -sin (B2)
+    const uint32_t row_hi = (uint32_t)(nl + NB) * 64u;   // rows [64, 128): sin (B1) / cos (B2)
+    const uint32_t sw = ((uint32_t)nl >> 1) & 3u;
+    for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
+      const int item = tile / tiles_per_item;
+      const int t = tile % tiles_per_item;
+      const int n = (t / tp.tiles_m) * NB + nl;
+      const float* kv = p.kvec + (size_t)item * p.kvec_stride;
+      const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
+      for (int kc = 0; kc < tp.k_chunks; ++kc) {
+        const int k0 = kc * BK + kg * PH_PER_THREAD;
+        float c_hi[PH_PER_THREAD], c_lo[PH_PER_THREAD], s_hi[PH_PER_THREAD], s_lo[PH_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < PH_PER_THREAD; ++j) {
+          const int k = k0 + j;
+          const float x = (k < p.K) ? __ldg(kv + k) : 0.0f;
+          float sn, cs;
+          sincosf(phase_arg(p.sign2pi, x, u), &sn, &cs);
+          c_hi[j] = tf32_hi(cs);
+          c_lo[j] = cs - c_hi[j];
+          s_hi[j] = tf32_hi(sn);
+          s_lo[j] = sn - s_hi[j];
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        uint8_t* bb = smem_gen + stage * STAGE_BYTES + A_BYTES;
+#pragma unroll
+        for (int h = 0; h < PH_PER_THREAD / 4; ++h) {
+          const uint32_t chunk = ((uint32_t)(kg * (PH_PER_THREAD / 4) + h) ^ sw) * 16u;
+          const float4 ch = make_float4(c_hi[4 * h], c_hi[4 * h + 1], c_hi[4 * h + 2], c_hi[4 * h + 3]);
+          const float4 cl = make_float4(c_lo[4 * h], c_lo[4 * h + 1], c_lo[4 * h + 2], c_lo[4 * h + 3]);
+          const float4 sh = make_float4(s_hi[4 * h], s_hi[4 * h + 1], s_hi[4 * h + 2], s_hi[4 * h + 3]);
+          const float4 sl = make_float4(s_lo[4 * h], s_lo[4 * h + 1], s_lo[4 * h + 2], s_lo[4 * h + 3]);
+          const float4 nsh = make_float4(-sh.x, -sh.y, -sh.z, -sh.w);
+          const float4 nsl = make_float4(-sl.x, -sl.y, -sl.z, -sl.w);
+          *reinterpret_cast<float4*>(bb + 0 * PLANE_BYTES + row_lo + chunk) = ch;   // B1_hi: cos
+          *reinterpret_cast<float4*>(bb + 0 * PLANE_BYTES + row_hi + chunk) = sh;   //        sin
+          *reinterpret_cast<float4*>(bb + 1 * PLANE_BYTES + row_lo + chunk) = cl;   // B1_lo
+          *reinterpret_cast<float4*>(bb + 1 * PLANE_BYTES + row_hi + chunk) = sl;
+          *reinterpret_cast<float4*>(bb + 2 * PLANE_BYTES + row_lo + chunk) = nsh;  // B2_hi: -sin
+          *reinterpret_cast<float4*>(bb + 2 * PLANE_BYTES + row_hi + chunk) = ch;   //        cos
+          *reinterpret_cast<float4*>(bb + 3 * PLANE_BYTES + row_lo + chunk) = nsl;  // B2_lo
+          *reinterpret_cast<float4*>(bb + 3 * PLANE_BYTES + row_hi + chunk) = cl;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+struct TcState {
+  EncodeTiledFn encode = nullptr;
+  int num_sms = 0;
+  int cc_major = 0;
+  int rc = DLUX_OK;
+};
+
+TcState& tc_state() {
+  static TcState st;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { st.rc = DLUX_ERR_CUDA; return; }
+    cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&st.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (st.cc_major != 10) { st.rc = DLUX_ERR_UNSUPPORTED; return; }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn) {
+      st.rc = DLUX_ERR_CUDA;
+      return;
+    }
+    st.encode = (EncodeTiledFn)fn;
+    if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+        cudaSuccess) {
+      st.rc = DLUX_ERR_CUDA;
+      return;
+    }
+  });
+  return st;
+}
+
+}  // namespace
+
+size_t gemm_tc_workspace_bytes() { return 0; }
+
+int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
+  if (p.n_items <= 0) return DLUX_OK;
+  TcState& s = tc_state();
+  if (s.rc != DLUX_OK) return s.rc;
+  if (p.a_pitch % 4 != 0) return DLUX_ERR_SHAPE;  // TMA global strides are multiples of 16 bytes
+
+  const cuuint64_t n_data = (cuuint64_t)(p.n_data > 0 ? p.n_data : p.n_items);
+  CUtensorMap maps[4];
+  for (int i = 0; i < 4; ++i) {
+    cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.rows, n_data};
+    cuuint64_t strides[2] = {(cuuint64_t)p.a_pitch * 4, (cuuint64_t)p.a_pitch * 4 * (cuuint64_t)p.rows};
+    cuuint32_t box[3] = {BK, BM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = s.encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.a_planes[i], dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[dlux_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
+      return DLUX_ERR_CUDA;
+    }
+  }
+  TcParams tp;
+  tp.g = p;
+  tp.tiles_m = (p.rows + BM - 1) / BM;
+  tp.tiles_n = (p.n_out + NB - 1) / NB;
+  const long long total = (long long)tp.tiles_m * tp.tiles_n * p.n_items;
+  if (total > 2147483647LL) return DLUX_ERR_SHAPE;
+  tp.n_tiles = (int)total;
+  tp.k_chunks = (p.K + BK - 1) / BK;
+  const int grid = tp.n_tiles < s.num_sms ? tp.n_tiles : s.num_sms;
+  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], tp);
+  note_launch();
+  return check_launch("gemm_tc");
+}
+
+}  // namespace dlux

@@ -105,7 +105,7 @@ def mft_c64(phasor: torch.Tensor, scale_out, n_out_or_in: int, shift_xy=None, de
     dev = phasor.device
     lead = phasor.shape[:-2]
     n_src = phasor.shape[-1]
-    x = phasor.reshape(-1, n_src, n_src).contiguous()
+    x = phasor.resolve_conj().reshape(-1, n_src, n_src).contiguous()   # conj views are lazy in torch
     batch = x.shape[0]
     n_in, n_out = (n_out_or_in, n_src) if adjoint else (n_src, n_out_or_in)
     n_dst = n_in if adjoint else n_out
