@@ -36,6 +36,8 @@ SIGNATURES = {
     "dlux_error_string": (C.c_char_p, [C.c_int]),
     "dlux_last_cuda_error": (C.c_int, []),
     "dlux_launch_count": (C.c_uint64, []),
+    "dlux_profile_enable": (C.c_int, [C.c_int]),
+    "dlux_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "dlux_mft_scratch_bytes": (C.c_size_t, [C.POINTER(MftDesc)]),
     "dlux_mft_c64": (C.c_int, [C.POINTER(MftDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "dlux_mft_coords": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
@@ -78,3 +80,14 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().dlux_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    load().dlux_profile_enable(int(on))
+
+
+def profile_read():
+    """(gemm_ms, gemm_launches, gemm_algorithmic_flops) since the last read."""
+    ms, n, fl = C.c_double(), C.c_uint64(), C.c_double()
+    load().dlux_profile_read(C.byref(ms), C.byref(n), C.byref(fl))
+    return ms.value, int(n.value), fl.value

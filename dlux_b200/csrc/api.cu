@@ -1,6 +1,8 @@
 // extern "C" surface of libdlux_b200.so (see include/dlux_b200.h).
 #include <atomic>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace dlux {
@@ -53,10 +55,30 @@ struct Bump {
   size_t used() const { return (off + 1023) & ~(size_t)1023; }
 };
 
+struct ProfRec { cudaEvent_t a, b; double flops; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+
 static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
-  if (precision == DLUX_PREC_FP32) return launch_gemm_simt(p, st);
-  if (precision == DLUX_PREC_3XTF32) return launch_gemm_tc(p, st);
-  return DLUX_ERR_ARG;
+  ProfRec r{};
+  const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
+  if (prof) {
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    r.flops = 8.0 * (double)p.rows * p.K * (double)p.n_out * p.n_items;
+    cudaEventRecord(r.a, st);
+  }
+  int rc;
+  if (precision == DLUX_PREC_FP32) rc = launch_gemm_simt(p, st);
+  else if (precision == DLUX_PREC_3XTF32) rc = launch_gemm_tc(p, st);
+  else rc = DLUX_ERR_ARG;
+  if (prof) {
+    cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+  }
+  return rc;
 }
 
 static const size_t kChunkBudget = (size_t)1 << 30;  // per-chunk intermediates, bytes
@@ -156,6 +178,30 @@ const char* dlux_error_string(int code) {
 
 int dlux_last_cuda_error(void) { return g_last_cuda_error; }
 uint64_t dlux_launch_count(void) { return g_launches.load(); }
+
+int dlux_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return DLUX_OK;
+}
+
+int dlux_profile_read(double* gemm_ms, uint64_t* gemm_launches, double* gemm_flops) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    cudaEventSynchronize(r.b);
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms += t;
+    fl += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_launches) *gemm_launches = g_prof.size();
+  if (gemm_flops) *gemm_flops = fl;
+  g_prof.clear();
+  return DLUX_OK;
+}
 
 size_t dlux_mft_scratch_bytes(const dlux_mft_desc* desc) {
   if (check_mft_desc(desc) != DLUX_OK) return 0;

@@ -59,6 +59,14 @@ DLUX_API int dlux_last_cuda_error(void);
 /* Number of kernels this library has launched since load (process-wide counter). */
 DLUX_API uint64_t dlux_launch_count(void);
 
+/* Optional per-kernel timing of the phasor-GEMM launches (the dominant kernel) with CUDA
+ * events recorded on the launching stream; used by bench.py for the roofline line.
+ * dlux_profile_read synchronises on the recorded events, returns the summed kernel
+ * time [ms], the number of GEMM launches and their algorithmic FLOPs (8 per complex
+ * MAC), and clears the record. */
+DLUX_API int dlux_profile_enable(int on);
+DLUX_API int dlux_profile_read(double* gemm_ms, uint64_t* gemm_launches, double* gemm_flops);
+
 /* ------------------------------------------------------------------------------
  * dlux_mft_c64: batched matrix Fourier transform.
  * Replaces dLux.utils.propagation.MFT (src/dLux/utils/propagation.py:178-256)
