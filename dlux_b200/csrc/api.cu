@@ -326,14 +326,17 @@ size_t dlux_polypsf_scratch_bytes(const dlux_polypsf_desc* desc) {
 
 static int poly_prologue(const dlux_polypsf_desc* d, const PolyScratch& s, const float* T,
                          const float* opd, const float* phase, const float* wavenumber,
-                         const float* scale_out, const float* norm, cudaStream_t st) {
+                         const float* scale_out, const float* norm, bool need_planes,
+                         cudaStream_t st) {
   const int N = d->n_pupil, L = d->n_wavels;
   const int items = d->n_sources * L;
   int rc = launch_power(N, T, d->normalise, s.amp_scale, st);
   if (rc) return rc;
-  rc = launch_pupil(N, L, T, opd, phase, wavenumber, s.amp_scale, s.p_pl[0], s.p_pl[1], s.p_pl[2],
-                    s.p_pl[3], st);
-  if (rc) return rc;
+  if (need_planes) {
+    rc = launch_pupil(N, L, T, opd, phase, wavenumber, s.amp_scale, s.p_pl[0], s.p_pl[1], s.p_pl[2],
+                      s.p_pl[3], st);
+    if (rc) return rc;
+  }
   expand_items_kernel<<<(items + 255) / 256 > 1024 ? 1024 : (items + 255) / 256, 256, 0, st>>>(
       items, L, scale_out, norm, wavenumber, s.item_l, s.s_item, s.norm_item, s.k_item);
   note_launch();
@@ -356,7 +359,7 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
   if (!ok) return DLUX_ERR_SCRATCH;
   const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
   const int items = d->n_sources * L;
-  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, st);
+  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, true, st);
   if (rc) return rc;
   rc = launch_zero(psf, (size_t)M * M, st);
   if (rc) return rc;
@@ -404,7 +407,8 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   if (!ok) return DLUX_ERR_SCRATCH;
   const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
   const int items = d->n_sources * L;
-  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, st);
+  // the gradient epilogue re-evaluates the pupil phasor itself: no operand planes needed
+  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, false, st);
   if (rc) return rc;
   if (opd_bar && (rc = launch_zero(opd_bar, (size_t)N * N, st))) return rc;
   if (phase_bar && (rc = launch_zero(phase_bar, (size_t)N * N, st))) return rc;
@@ -429,12 +433,15 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     if (rc) return rc;
     GemmParams h{};
     fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
-    for (int i = 0; i < 4; ++i) { h.a_planes[i] = s.mid_pl[i]; h.p_planes[i] = s.p_pl[i]; }
+    for (int i = 0; i < 4; ++i) h.a_planes[i] = s.mid_pl[i];
     h.mode = EPI_GRAD;
     h.scale = s.norm_item + b0;
     h.w = s.k_item + b0;
-    h.item_p = s.item_l + b0;
-    h.p_pitch = pitch4(N);
+    h.pup_T = T;
+    h.pup_opd = opd;
+    h.pup_phase = phase;
+    h.amp_scale = s.amp_scale;
+    h.a0 = 1.0f / (float)((long long)N * N);
     h.opd_bar = opd_bar;
     h.phase_bar = phase_bar;
     rc = run_gemm(h, d->precision, st);

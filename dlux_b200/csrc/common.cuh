@@ -45,9 +45,13 @@ struct GemmParams {
   float2* out_c64;       // EPI_C64 / optional for EPI_PSF
   float* psf;            // EPI_PSF: [n_out][rows]
   const float* w;        // EPI_PSF weights [n_items]; EPI_GRAD: wavenumber per item
-  const float* p_planes[4];  // EPI_GRAD: pupil planes [n_p][n_out][p_pitch]
-  int p_pitch;
-  const int* item_p;     // EPI_GRAD: item -> pupil index (nullptr = identity)
+  // EPI_GRAD: the pupil phasor P = amp * T * exp(i (k * opd + phase)) is re-evaluated in the
+  // epilogue from the (L2-resident) pupil arrays instead of being re-read per wavelength
+  const float* pup_T;      // [n_out][rows] or nullptr (= 1)
+  const float* pup_opd;    // [n_out][rows] or nullptr
+  const float* pup_phase;  // [n_out][rows] or nullptr
+  const float* amp_scale;  // device scalar (power normalisation)
+  float a0;                // 1 / N^2
   float* opd_bar;        // EPI_GRAD
   float* phase_bar;      // EPI_GRAD
 };
@@ -61,6 +65,39 @@ __device__ __forceinline__ float tf32_hi(float x) {
 // Reference phase argument: two float32 multiplies, no fused contraction.
 __device__ __forceinline__ float phase_arg(float sign2pi, float x, float u) {
   return __fmul_rn(sign2pi, __fmul_rn(x, u));
+}
+
+// sin/cos of a float32 argument, ~1.5 ulp: Cody-Waite reduction by pi/2 in three parts
+// followed by minimax polynomials on [-pi/4, pi/4] (the classic single-precision
+// sincosf fast path).  Valid for |a| < 1e5; larger arguments (never reached by optical
+// MFT geometries, where |a| ~ pi * nfringes / 2) take the libdevice slow path.
+__device__ __forceinline__ void fast_sincos(float a, float* sn, float* cs) {
+  if (fabsf(a) > 1.0e5f) {
+    sincosf(a, sn, cs);
+    return;
+  }
+  float j = fmaf(a, 0.636619747f, 12582912.0f);
+  const int q = __float_as_int(j);
+  j -= 12582912.0f;
+  float r = fmaf(j, -1.57079601e+00f, a);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const float s2 = r * r;
+  float c = 2.44677067e-5f;
+  c = fmaf(c, s2, -1.38877297e-3f);
+  c = fmaf(c, s2, 4.16666567e-2f);
+  c = fmaf(c, s2, -5.00000000e-1f);
+  c = fmaf(c, s2, 1.0f);
+  float s = 2.86567956e-6f;
+  s = fmaf(s, s2, -1.98559923e-4f);
+  s = fmaf(s, s2, 8.33338592e-3f);
+  s = fmaf(s, s2, -1.66666672e-1f);
+  const float t = r * s2;
+  s = fmaf(s, t, r);
+  const float so = (q & 1) ? c : s;
+  const float co = (q & 1) ? s : c;
+  *sn = (q & 2) ? -so : so;
+  *cs = ((q + 1) & 2) ? -co : co;
 }
 
 // Shared epilogue for one output element D[m][n] = (re, im) of `item`.
@@ -84,13 +121,16 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
     const float w = __ldg(p.w + item);
     atomicAdd(p.psf + (size_t)n * p.rows + m, w * (re * re + im * im));
   } else {  // EPI_GRAD
-    const int ip = p.item_p ? __ldg(p.item_p + item) : item;
-    const size_t pi = ((size_t)ip * p.n_out + n) * p.p_pitch + m;
-    const float pr = __ldg(p.p_planes[0] + pi) + __ldg(p.p_planes[1] + pi);
-    const float pim = __ldg(p.p_planes[2] + pi) + __ldg(p.p_planes[3] + pi);
-    const float g = pr * im - pim * re;  // Im(conj(P) * v)
     const size_t oi = (size_t)n * p.rows + m;
-    if (p.opd_bar) atomicAdd(p.opd_bar + oi, __ldg(p.w + item) * g);
+    const float kw = __ldg(p.w + item);
+    float a = p.a0 * __ldg(p.amp_scale);
+    if (p.pup_T) a *= __ldg(p.pup_T + oi);
+    float th = p.pup_opd ? __fmul_rn(kw, __ldg(p.pup_opd + oi)) : 0.0f;
+    if (p.pup_phase) th += __ldg(p.pup_phase + oi);
+    float sn, cs;
+    fast_sincos(th, &sn, &cs);
+    const float g = a * (cs * im - sn * re);  // Im(conj(P) * v)
+    if (p.opd_bar) atomicAdd(p.opd_bar + oi, kw * g);
     if (p.phase_bar) atomicAdd(p.phase_bar + oi, g);
   }
 }

@@ -130,6 +130,71 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
 
+// Fused epilogue of one tile row: thread = data row m, tot[0..NB) = Re, tot[NB..2NB) = Im
+// of the NB output coordinates n0.. .  Stores are transposed (m fastest), so a warp writes
+// 128 (fp32) or 256 (c64) contiguous bytes per output coordinate.  Global loads of the
+// gradient epilogue are issued in batches of 8 so that their latency overlaps.
+__device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int m, int n0,
+                                              float (&tot)[BN]) {
+  const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
+  const int nmax = p.n_out - n0;  // columns j < nmax are valid
+  if (p.mode == EPI_PLANES) {
+    const size_t base = ((size_t)item * p.n_out + n0) * p.out_pitch + m;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (j < nmax) {
+        const float re = tot[j] * sc, im = tot[NB + j] * sc;
+        const float rh = tf32_hi(re), ih = tf32_hi(im);
+        const size_t o = base + (size_t)j * p.out_pitch;
+        p.out_planes[0][o] = rh;
+        p.out_planes[1][o] = re - rh;
+        p.out_planes[2][o] = ih;
+        p.out_planes[3][o] = im - ih;
+      }
+    }
+  } else if (p.mode == EPI_C64 || p.mode == EPI_PSF) {
+    const size_t base = ((size_t)item * p.n_out + n0) * p.rows + m;
+    const float w = p.mode == EPI_PSF ? __ldg(p.w + item) : 0.0f;
+    float* psf = p.psf + (size_t)n0 * p.rows + m;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (j < nmax) {
+        const float re = tot[j] * sc, im = tot[NB + j] * sc;
+        if (p.out_c64) p.out_c64[base + (size_t)j * p.rows] = make_float2(re, im);
+        if (p.mode == EPI_PSF) atomicAdd(psf + (size_t)j * p.rows, w * (re * re + im * im));
+      }
+    }
+  } else {  // EPI_GRAD
+    const float kw = __ldg(p.w + item);
+    const float amp = p.a0 * __ldg(p.amp_scale);
+    const size_t base = (size_t)n0 * p.rows + m;
+#pragma unroll
+    for (int j0 = 0; j0 < NB; j0 += 8) {
+      float tv[8], ov[8], pv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = (j0 + j) < nmax;
+        const size_t o = base + (size_t)(j0 + j) * p.rows;
+        tv[j] = (ok && p.pup_T) ? __ldg(p.pup_T + o) : 1.0f;
+        ov[j] = (ok && p.pup_opd) ? __ldg(p.pup_opd + o) : 0.0f;
+        pv[j] = (ok && p.pup_phase) ? __ldg(p.pup_phase + o) : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if ((j0 + j) < nmax) {
+          const float re = tot[j0 + j] * sc, im = tot[NB + j0 + j] * sc;
+          float sn, cs;
+          fast_sincos(__fmul_rn(kw, ov[j]) + pv[j], &sn, &cs);
+          const float g = amp * tv[j] * (cs * im - sn * re);  // Im(conj(P) * v)
+          const size_t o = base + (size_t)(j0 + j) * p.rows;
+          if (p.opd_bar) atomicAdd(p.opd_bar + o, kw * g);
+          if (p.phase_bar) atomicAdd(p.phase_bar + o, g);
+        }
+      }
+    }
+  }
+}
+
 struct TcParams {
   GemmParams g;
   int tiles_m, tiles_n, n_tiles, k_chunks;
@@ -286,13 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         mbar_arrive(tempty_bar(acc));
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
-      if (m < p.rows) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const int n = n0 + j;
-          if (n < p.n_out) epilogue_store(p, item, m, n, tot[j], tot[NB + j]);
-        }
-      }
+      if (m < p.rows) tile_epilogue(p, item, m, n0, tot);
     }
   } else {
     // ===================== phasor generators =====================
@@ -320,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           const int k = k0 + j;
           const float x = (k < p.K) ? __ldg(kv + k) : 0.0f;
           float sn, cs;
-          sincosf(phase_arg(p.sign2pi, x, u), &sn, &cs);
+          fast_sincos(phase_arg(p.sign2pi, x, u), &sn, &cs);
           c_hi[j] = tf32_hi(cs);
           c_lo[j] = cs - c_hi[j];
           s_hi[j] = tf32_hi(sn);
