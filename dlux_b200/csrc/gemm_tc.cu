@@ -19,8 +19,11 @@
 //   warps with tcgen05.ld and added, round-to-nearest, into fp32 registers (the scheme of
 //   Ootomo & Yokota for error-corrected TF32 GEMM).  Draining overlaps the MMAs of the
 //   next partial.
-// * Persistent CTAs, one per SM; warp roles: 0 TMA producer, 1 MMA issuer, 2..5 drain +
-//   fused epilogue (coalesced transposed stores), 6.. phasor generators.
+// * Persistent CTAs, one per SM, 16 warps in 4 warpgroups: WG0 = drain + fused epilogue
+//   (one warp per TMEM lane quarter; setmaxnreg.inc, they hold the 128 running totals),
+//   WG1 = TMA producer + MMA issuer (setmaxnreg.dec), WG2/WG3 = phasor generators.
+//   The data (TMA) and phasor (generated) operands have separate shared-memory rings
+//   (4 x 32 KiB and 3 x 32 KiB) so that HBM/L2 latency gets the deeper prefetch.
 #include <cuda.h>
 #include <cstdio>
 #include <mutex>
@@ -35,22 +38,30 @@ constexpr int NB = 64;             // generated output coordinates per tile
 constexpr int BN = 2 * NB;         // UMMA N: [Re | Im] halves
 constexpr int BK = 16;             // k per pipeline stage = one 64-byte swizzle row of fp32
 constexpr int UMMA_K = 8;          // kind::tf32
-constexpr int STAGES = 3;
+constexpr int A_STAGES = 4;        // data ring (TMA)
+constexpr int B_STAGES = 3;        // phasor ring (generated)
 constexpr int PLANE_BYTES = BM * BK * 4;            // 8 KiB
 constexpr int A_BYTES = 4 * PLANE_BYTES;            // 32 KiB: re_hi, re_lo, im_hi, im_lo
 constexpr int B_BYTES = 4 * BN * BK * 4;            // 32 KiB: B1_hi, B1_lo, B2_hi, B2_lo
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 64 KiB
+constexpr int B_BASE = A_STAGES * A_BYTES;
+constexpr int RING_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES;  // 224 KiB
 constexpr int FLUSH_CHUNKS = 4;    // k-chunks accumulated in TMEM before draining to registers
 constexpr int NUM_ACC = 4;         // TMEM partial-accumulator ring
-constexpr int NUM_GEN_WARPS = 4;
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 4;   // warps 0..3   (WG0)
+constexpr int WARP_TMA = 4;        // WG1
+constexpr int WARP_MMA = 5;
+constexpr int FIRST_GEN_WARP = 8;  // WG2, WG3
+constexpr int NUM_GEN_WARPS = 8;
 constexpr int NUM_GEN_THREADS = 32 * NUM_GEN_WARPS;
-constexpr int PH_PER_THREAD = NB * BK / NUM_GEN_THREADS;  // phasors per generator thread per chunk
-constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS + NUM_GEN_WARPS);
+constexpr int PH_PER_THREAD = NB * BK / NUM_GEN_THREADS;  // phasors per generator thread per chunk (4)
+constexpr int NUM_THREADS = 32 * (FIRST_GEN_WARP + NUM_GEN_WARPS);  // 512
+constexpr int REGS_EPI = 232, REGS_CTRL = 40, REGS_GEN = 112;  // setmaxnreg budgets (launch: 128)
 constexpr int TMEM_COLS = NUM_ACC * BN;  // 512
 static_assert(TMEM_COLS == 512, "TMEM ring must be a power of two <= 512 columns");
 static_assert(PH_PER_THREAD % 4 == 0, "each generator thread writes whole 16-byte chunks");
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(128 * (REGS_EPI - 128) <= 128 * (128 - REGS_CTRL) + 256 * (128 - REGS_GEN), "register budget");
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -208,26 +219,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   const GemmParams& p = tp.g;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of the aligned base
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
-  uint32_t* tmem_slot =
-      reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
+  const uint32_t bar_base = smem_base + RING_BYTES;
+  auto fullA_bar = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA_bar = [&](int s) { return bar_base + 8u * (A_STAGES + s); };
+  auto fullB_bar = [&](int s) { return bar_base + 8u * (2 * A_STAGES + s); };
+  auto emptyB_bar = [&](int s) { return bar_base + 8u * (2 * A_STAGES + B_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * A_STAGES + 2 * B_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * A_STAGES + 2 * B_STAGES + NUM_ACC + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(
+      smem_gen + RING_BYTES + 8 * (2 * A_STAGES + 2 * B_STAGES + 2 * NUM_ACC));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == WARP_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map0));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map1));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map2));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map3));
   }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + NUM_GEN_WARPS);  // TMA producer (expect_tx) + one arrive per generator warp
-      mbar_init(empty_bar(s), 1);                 // tcgen05.commit
+  if (warp == WARP_MMA && lane == 0) {
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(fullA_bar(s), 1);   // TMA producer's arrive.expect_tx
+      mbar_init(emptyA_bar(s), 1);  // tcgen05.commit
+    }
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(fullB_bar(s), NUM_GEN_WARPS);  // one arrive per generator warp
+      mbar_init(emptyB_bar(s), 1);             // tcgen05.commit
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);                    // tcgen05.commit closing a partial
@@ -235,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -245,9 +262,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register re-balancing between warpgroups: setmaxnreg is the first instruction of each
+  // warpgroup's branch (all four warps of a warpgroup execute it).
   const int tiles_per_item = tp.tiles_m * tp.tiles_n;
 
-  if (warp == 0) {
+  if (warp >= NUM_EPI_WARPS && warp < FIRST_GEN_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+    if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -258,22 +279,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         const int m0 = (t % tp.tiles_m) * BM;
         const int d = p.item_data ? __ldg(p.item_data + item) : item;
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
-          tma_load_3d(a_dst + 0 * PLANE_BYTES, &map0, full_bar(stage), kc * BK, m0, d);
-          tma_load_3d(a_dst + 1 * PLANE_BYTES, &map1, full_bar(stage), kc * BK, m0, d);
-          tma_load_3d(a_dst + 2 * PLANE_BYTES, &map2, full_bar(stage), kc * BK, m0, d);
-          tma_load_3d(a_dst + 3 * PLANE_BYTES, &map3, full_bar(stage), kc * BK, m0, d);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          mbar_wait(emptyA_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * A_BYTES;
+          mbar_arrive_expect_tx(fullA_bar(stage), A_BYTES);
+          tma_load_3d(a_dst + 0 * PLANE_BYTES, &map0, fullA_bar(stage), kc * BK, m0, d);
+          tma_load_3d(a_dst + 1 * PLANE_BYTES, &map1, fullA_bar(stage), kc * BK, m0, d);
+          tma_load_3d(a_dst + 2 * PLANE_BYTES, &map2, fullA_bar(stage), kc * BK, m0, d);
+          tma_load_3d(a_dst + 3 * PLANE_BYTES, &map3, fullA_bar(stage), kc * BK, m0, d);
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+    } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
@@ -284,10 +305,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             tc_fence_after();
           }
           const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(fullB_bar(sb), pb);
+          mbar_wait(fullA_bar(sa), pa);
           tc_fence_after();
-          const uint32_t a0 = smem_base + stage * STAGE_BYTES;
-          const uint32_t b0 = a0 + A_BYTES;
+          const uint32_t a0 = smem_base + sa * A_BYTES;
+          const uint32_t b0 = smem_base + B_BASE + sb * B_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BK / UMMA_K; ++ks) {
             const uint32_t koff = ks * UMMA_K * 4;  // bytes inside the 64-byte swizzle row
@@ -308,17 +330,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             umma_tf32(d, a_rh, b1h, IDESC, 1u);
             umma_tf32(d, a_ih, b2h, IDESC, 1u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          umma_commit(emptyA_bar(sa));  // free both smem slots when these MMAs retire
+          umma_commit(emptyB_bar(sb));
           if (in_partial == FLUSH_CHUNKS - 1 || kc == tp.k_chunks - 1) {
             umma_commit(tfull_bar(acc));  // partial complete -> drain warps
             if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
         }
       }
     }
-  } else if (warp < 2 + NUM_EPI_WARPS) {
+    }
+  } else if (warp < NUM_EPI_WARPS) {
     // ===================== drain + epilogue =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -355,7 +381,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     }
   } else {
     // ===================== phasor generators =====================
-    const int gt = threadIdx.x - 32 * (2 + NUM_EPI_WARPS);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GEN));
+    const int gt = threadIdx.x - 32 * FIRST_GEN_WARP;
     const int nl = gt & (NB - 1);   // output coordinate within the tile
     const int kg = gt / NB;         // which PH_PER_THREAD-wide k group of the chunk
     int stage = 0;
@@ -385,8 +412,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           s_hi[j] = tf32_hi(sn);
           s_lo[j] = sn - s_hi[j];
         }
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        uint8_t* bb = smem_gen + stage * STAGE_BYTES + A_BYTES;
+        mbar_wait(emptyB_bar(stage), phase ^ 1);
+        uint8_t* bb = smem_gen + B_BASE + stage * B_BYTES;
 #pragma unroll
         for (int h = 0; h < PH_PER_THREAD / 4; ++h) {
           const uint32_t chunk = ((uint32_t)(kg * (PH_PER_THREAD / 4) + h) ^ sw) * 16u;
@@ -407,15 +434,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(fullB_bar(stage));
+        if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
