@@ -166,8 +166,10 @@ def run_ours(args):
     N, M = cfg["wf_npixels"], cfg["psf_npixels"] * cfg["oversample"]
     L, nz = len(cfg["wavelengths"]), len(cfg["coefficients"])
     # one source per rank (PointSources with `world` stars); rank r owns star r
-    rng = np.random.default_rng(100 + rank)
-    position = (rng.uniform(-1, 1, 2) * 2e-7).astype(np.float32) if world > 1 else cfg["positions"][0]
+    all_positions = np.stack([(np.random.default_rng(100 + r).uniform(-1, 1, 2) * 2e-7).astype(np.float32)
+                              for r in range(world)]) if world > 1 else cfg["positions"][:1]
+    all_fluxes = np.ones(world, np.float32)
+    position = all_positions[rank]
     flux = np.float32(1.0)
 
     up = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
@@ -200,7 +202,7 @@ def run_ours(args):
     G_h = torch.as_tensor(cfg["G"]).pin_memory()
     psf_h = torch.empty((M, M), dtype=torch.float32).pin_memory()
     grad_h = torch.empty(nz, dtype=torch.float32).pin_memory()
-    src = dl.PointSources(cfg["wavelengths"], position[None, :], np.array([flux], np.float32))
+    from dlux_b200 import distributed as D
 
     def step_e2e():
         c = coeffs_h.to(dev, non_blocking=True).requires_grad_(True)
@@ -208,29 +210,16 @@ def run_ours(args):
         layer = dl.BasisOptic(basis_d, T_d, c, "opd", normalise=True, device=dev)
         optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("pupil", layer)], cfg["psf_npixels"],
                                          cfg["psf_pixel_scale"], cfg["oversample"], device=dev)
-        psf = optics.model(src)
-        if world > 1:
-            psf = AllReduceSum.apply(psf)
+        # PointSources(world stars).model(optics), sources sharded one per rank + NCCL all-reduce
+        psf = D.sharded_point_sources_model(optics, cfg["wavelengths"], all_positions, all_fluxes,
+                                            cfg["weights"])
         loss = (psf * G).sum()
         loss.backward()
-        g = c.grad
-        if world > 1:
-            dist.all_reduce(g)
+        D.all_reduce_grads([c])
         psf_h.copy_(psf.detach(), non_blocking=True)
-        grad_h.copy_(g, non_blocking=True)
+        grad_h.copy_(c.grad, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(psf_h[0, 0])
-
-    class AllReduceSum(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, x):
-            y = x.clone()
-            dist.all_reduce(y)
-            return y
-
-        @staticmethod
-        def backward(ctx, g):
-            return g          # every rank holds the same dL/dpsf
 
     def barrier():
         if world > 1:
