@@ -81,7 +81,15 @@ static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
   return rc;
 }
 
-static const size_t kChunkBudget = (size_t)1 << 30;  // per-chunk intermediates, bytes
+static const size_t kChunkBudget = (size_t)2 << 30;  // per-chunk intermediates, bytes
+
+// largest chunk <= cmax that splits `n` items into equal-sized chunks (no small tail launch)
+static size_t balanced_chunk(size_t n, size_t cmax) {
+  if (cmax < 1) cmax = 1;
+  if (n <= cmax) return n < 1 ? 1 : n;
+  const size_t parts = (n + cmax - 1) / cmax;
+  return (n + parts - 1) / parts;
+}
 
 // intermediate planes hold [M][pitch(N)] (forward) or [N][pitch(M)] (adjoint)
 static size_t mid_elems(int N, int M) {
@@ -93,10 +101,7 @@ static int mft_chunk(const dlux_mft_desc* d) {
   const size_t n_src = d->adjoint ? d->n_out : d->n_in;
   const size_t per_item = 16 * n_src * pitch4((int)n_src) + 16 * mid_elems(d->n_in, d->n_out) +
                           8 * (size_t)(d->n_in + d->n_out);
-  size_t c = kChunkBudget / per_item;
-  if (c < 1) c = 1;
-  if (c > (size_t)d->batch) c = d->batch;
-  return (int)c;
+  return (int)balanced_chunk((size_t)d->batch, kChunkBudget / per_item);
 }
 
 struct MftScratch {
@@ -275,17 +280,17 @@ struct PolyScratch {
   float *xin, *uout;  // per chunk
   float* mid_pl[4];   // per chunk [c][M*N]
   float* ebar_pl[4];  // per chunk [c][M*M]  (bwd only; sized always for simplicity)
+  float* gbuf;        // per chunk [c][N*N]: per-item gradient contributions (bwd)
+  float2* fbuf;       // per chunk [c][M*M]: field, when the caller does not keep it (fwd)
   int chunk;
 };
 
 static int poly_chunk(const dlux_polypsf_desc* d) {
   const size_t N = d->n_pupil, M = d->n_psf;
-  const size_t per_item = 16 * mid_elems((int)N, (int)M) + 16 * M * pitch4((int)M) + 8 * (N + M);
-  size_t c = kChunkBudget / per_item;
+  const size_t per_item = 16 * mid_elems((int)N, (int)M) + 16 * M * pitch4((int)M) + 8 * (N + M) +
+                          4 * N * N + 8 * M * M;
   const size_t items = (size_t)d->n_sources * d->n_wavels;
-  if (c < 1) c = 1;
-  if (c > items) c = items;
-  return (int)c;
+  return (int)balanced_chunk(items, kChunkBudget / per_item);
 }
 
 static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, PolyScratch* s, bool* ok) {
@@ -304,6 +309,8 @@ static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, 
   s->uout = b.take<float>(c * 2 * M);
   for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * mid_elems((int)N, (int)M));
   for (int i = 0; i < 4; ++i) s->ebar_pl[i] = b.take<float>(c * M * pitch4((int)M));
+  s->gbuf = b.take<float>(c * N * N);
+  s->fbuf = b.take<float2>(c * M * M);
   b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
   if (ok) *ok = b.ok;
   return b.used();
@@ -361,8 +368,6 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
   const int items = d->n_sources * L;
   rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, true, st);
   if (rc) return rc;
-  rc = launch_zero(psf, (size_t)M * M, st);
-  if (rc) return rc;
   const float sign2pi = (float)(-2.0 * 3.14159265358979323846);
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
@@ -380,12 +385,13 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
     GemmParams h{};
     fill_stage(h, false, 1, N, M, c, s.xin, s.uout, sign2pi);
     for (int i = 0; i < 4; ++i) h.a_planes[i] = s.mid_pl[i];
-    h.mode = EPI_PSF;
+    h.mode = EPI_C64;
     h.scale = s.norm_item + b0;
-    h.psf = psf;
-    h.w = weights + b0;
-    h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * M * M : nullptr;
+    h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * M * M : s.fbuf;
     rc = run_gemm(h, d->precision, st);
+    if (rc) return rc;
+    // psf (+)= sum over this chunk's (source, wavelength) items of w |E|^2
+    rc = launch_psf_reduce((size_t)M * M, c, h.out_c64, weights + b0, psf, b0 > 0, st);
     if (rc) return rc;
   }
   return DLUX_OK;
@@ -410,8 +416,6 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   // the gradient epilogue re-evaluates the pupil phasor itself: no operand planes needed
   rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, false, st);
   if (rc) return rc;
-  if (opd_bar && (rc = launch_zero(opd_bar, (size_t)N * N, st))) return rc;
-  if (phase_bar && (rc = launch_zero(phase_bar, (size_t)N * N, st))) return rc;
   if (weights_bar && (rc = launch_zero(weights_bar, (size_t)items, st))) return rc;
   const bool need_pupil_grad = opd_bar || phase_bar;
   const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
@@ -442,9 +446,10 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     h.pup_phase = phase;
     h.amp_scale = s.amp_scale;
     h.a0 = 1.0f / (float)((long long)N * N);
-    h.opd_bar = opd_bar;
-    h.phase_bar = phase_bar;
+    h.out_g = s.gbuf;
     rc = run_gemm(h, d->precision, st);
+    if (rc) return rc;
+    rc = launch_grad_reduce((size_t)N * N, c, s.gbuf, s.k_item + b0, opd_bar, phase_bar, b0 > 0, st);
     if (rc) return rc;
   }
   return DLUX_OK;

@@ -20,8 +20,7 @@ namespace dlux {
 enum EpilogueMode : int {
   EPI_PLANES = 0,  // out_planes[p][item][n][m], p = re_hi, re_lo, im_hi, im_lo  (feeds the next stage)
   EPI_C64 = 1,     // out_c64[item][n][m]
-  EPI_PSF = 2,     // psf[n][m] += w[item] * |v|^2   (optionally also out_c64)
-  EPI_GRAD = 3     // opd_bar[n][m] += kw[item] * Im(conj(P[d2(item)][n][m]) * v); phase_bar likewise with 1
+  EPI_GRAD = 3     // out_g[item][n][m] = Im(conj(P[n][m]) * v)  (summed over items by grad_reduce)
 };
 
 struct GemmParams {
@@ -42,9 +41,8 @@ struct GemmParams {
   int mode;
   float* out_planes[4];  // EPI_PLANES: [n_items][n_out][out_pitch]
   int out_pitch;
-  float2* out_c64;       // EPI_C64 / optional for EPI_PSF
-  float* psf;            // EPI_PSF: [n_out][rows]
-  const float* w;        // EPI_PSF weights [n_items]; EPI_GRAD: wavenumber per item
+  float2* out_c64;       // EPI_C64: [n_items][n_out][rows]
+  const float* w;        // EPI_GRAD: wavenumber per item
   // EPI_GRAD: the pupil phasor P = amp * T * exp(i (k * opd + phase)) is re-evaluated in the
   // epilogue from the (L2-resident) pupil arrays instead of being re-read per wavelength
   const float* pup_T;      // [n_out][rows] or nullptr (= 1)
@@ -52,8 +50,7 @@ struct GemmParams {
   const float* pup_phase;  // [n_out][rows] or nullptr
   const float* amp_scale;  // device scalar (power normalisation)
   float a0;                // 1 / N^2
-  float* opd_bar;        // EPI_GRAD
-  float* phase_bar;      // EPI_GRAD
+  float* out_g;            // EPI_GRAD: [n_items][n_out][rows]
 };
 
 __device__ __forceinline__ float tf32_hi(float x) {
@@ -116,10 +113,6 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
     p.out_planes[3][po] = im - ih;
   } else if (p.mode == EPI_C64) {
     p.out_c64[idx] = make_float2(re, im);
-  } else if (p.mode == EPI_PSF) {
-    if (p.out_c64) p.out_c64[idx] = make_float2(re, im);
-    const float w = __ldg(p.w + item);
-    atomicAdd(p.psf + (size_t)n * p.rows + m, w * (re * re + im * im));
   } else {  // EPI_GRAD
     const size_t oi = (size_t)n * p.rows + m;
     const float kw = __ldg(p.w + item);
@@ -129,9 +122,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
     if (p.pup_phase) th += __ldg(p.pup_phase + oi);
     float sn, cs;
     fast_sincos(th, &sn, &cs);
-    const float g = a * (cs * im - sn * re);  // Im(conj(P) * v)
-    if (p.opd_bar) atomicAdd(p.opd_bar + oi, kw * g);
-    if (p.phase_bar) atomicAdd(p.phase_bar + oi, g);
+    p.out_g[idx] = a * (cs * im - sn * re);  // Im(conj(P) * v)
   }
 }
 
@@ -163,5 +154,11 @@ int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coe
 int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,
                         float* coeff_bar, cudaStream_t st);
 int launch_zero(float* p, size_t n, cudaStream_t st);
+// psf[i] (+)= sum_item w[item] |field[item][i]|^2
+int launch_psf_reduce(size_t npix, int n_items, const float2* field, const float* w, float* psf,
+                      int accumulate, cudaStream_t st);
+// opd_bar[i] (+)= sum_item k[item] g[item][i];  phase_bar[i] (+)= sum_item g[item][i]
+int launch_grad_reduce(size_t npix, int n_items, const float* g, const float* k, float* opd_bar,
+                       float* phase_bar, int accumulate, cudaStream_t st);
 
 }  // namespace dlux

@@ -311,6 +311,56 @@ int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* o
   return check_launch("basis_reduce");
 }
 
+// Sums over items replace per-element atomics in the GEMM epilogues: each (source,
+// wavelength) writes its contribution with plain coalesced stores and these HBM-bound
+// kernels reduce them (optical_systems.py:222-223 `psf.sum(0)`, sources.py:409-411).
+__global__ void psf_reduce_kernel(size_t npix, int n_items, const float2* __restrict__ field,
+                                  const float* __restrict__ w, float* __restrict__ psf, int accumulate) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float acc = accumulate ? psf[i] : 0.0f;
+#pragma unroll 8
+    for (int it = 0; it < n_items; ++it) {
+      const float2 e = field[(size_t)it * npix + i];
+      acc = fmaf(__ldg(w + it), e.x * e.x + e.y * e.y, acc);
+    }
+    psf[i] = acc;
+  }
+}
+
+int launch_psf_reduce(size_t npix, int n_items, const float2* field, const float* w, float* psf,
+                      int accumulate, cudaStream_t st) {
+  psf_reduce_kernel<<<grid_for(npix, 128, 148 * 8), 128, 0, st>>>(npix, n_items, field, w, psf, accumulate);
+  note_launch();
+  return check_launch("psf_reduce");
+}
+
+__global__ void grad_reduce_kernel(size_t npix, int n_items, const float* __restrict__ g,
+                                   const float* __restrict__ k, float* __restrict__ opd_bar,
+                                   float* __restrict__ phase_bar, int accumulate) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float ao = (accumulate && opd_bar) ? opd_bar[i] : 0.0f;
+    float ap = (accumulate && phase_bar) ? phase_bar[i] : 0.0f;
+#pragma unroll 8
+    for (int it = 0; it < n_items; ++it) {
+      const float v = g[(size_t)it * npix + i];
+      ao = fmaf(__ldg(k + it), v, ao);
+      ap += v;
+    }
+    if (opd_bar) opd_bar[i] = ao;
+    if (phase_bar) phase_bar[i] = ap;
+  }
+}
+
+int launch_grad_reduce(size_t npix, int n_items, const float* g, const float* k, float* opd_bar,
+                       float* phase_bar, int accumulate, cudaStream_t st) {
+  grad_reduce_kernel<<<grid_for(npix, 128, 148 * 8), 128, 0, st>>>(npix, n_items, g, k, opd_bar, phase_bar,
+                                                                   accumulate);
+  note_launch();
+  return check_launch("grad_reduce");
+}
+
 int launch_zero(float* p, size_t n, cudaStream_t st) {
   if (n == 0) return DLUX_OK;
   zero_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n);

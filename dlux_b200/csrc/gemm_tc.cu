@@ -163,27 +163,22 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
         p.out_planes[3][o] = im - ih;
       }
     }
-  } else if (p.mode == EPI_C64 || p.mode == EPI_PSF) {
+  } else if (p.mode == EPI_C64) {
     const size_t base = ((size_t)item * p.n_out + n0) * p.rows + m;
-    const float w = p.mode == EPI_PSF ? __ldg(p.w + item) : 0.0f;
-    float* psf = p.psf + (size_t)n0 * p.rows + m;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      if (j < nmax) {
-        const float re = tot[j] * sc, im = tot[NB + j] * sc;
-        if (p.out_c64) p.out_c64[base + (size_t)j * p.rows] = make_float2(re, im);
-        if (p.mode == EPI_PSF) atomicAdd(psf + (size_t)j * p.rows, w * (re * re + im * im));
-      }
+      if (j < nmax) p.out_c64[base + (size_t)j * p.rows] = make_float2(tot[j] * sc, tot[NB + j] * sc);
     }
   } else {  // EPI_GRAD
     const float kw = __ldg(p.w + item);
     const float amp = p.a0 * __ldg(p.amp_scale);
     const size_t base = (size_t)n0 * p.rows + m;
+    float* outg = p.out_g + (size_t)item * p.n_out * p.rows + base;
 #pragma unroll
-    for (int j0 = 0; j0 < NB; j0 += 8) {
-      float tv[8], ov[8], pv[8];
+    for (int j0 = 0; j0 < NB; j0 += 16) {
+      float tv[16], ov[16], pv[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 16; ++j) {
         const bool ok = (j0 + j) < nmax;
         const size_t o = base + (size_t)(j0 + j) * p.rows;
         tv[j] = (ok && p.pup_T) ? __ldg(p.pup_T + o) : 1.0f;
@@ -191,15 +186,12 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
         pv[j] = (ok && p.pup_phase) ? __ldg(p.pup_phase + o) : 0.0f;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 16; ++j) {
         if ((j0 + j) < nmax) {
           const float re = tot[j0 + j] * sc, im = tot[NB + j0 + j] * sc;
           float sn, cs;
           fast_sincos(__fmul_rn(kw, ov[j]) + pv[j], &sn, &cs);
-          const float g = amp * tv[j] * (cs * im - sn * re);  // Im(conj(P) * v)
-          const size_t o = base + (size_t)(j0 + j) * p.rows;
-          if (p.opd_bar) atomicAdd(p.opd_bar + o, kw * g);
-          if (p.phase_bar) atomicAdd(p.phase_bar + o, g);
+          outg[(size_t)(j0 + j) * p.rows] = amp * tv[j] * (cs * im - sn * re);  // Im(conj(P) * v)
         }
       }
     }
@@ -398,15 +390,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       const int n = (t / tp.tiles_m) * NB + nl;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
       const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
+      float xk[PH_PER_THREAD];  // this chunk's k coordinates, prefetched one chunk ahead
+#pragma unroll
+      for (int j = 0; j < PH_PER_THREAD; ++j) {
+        const int k = kg * PH_PER_THREAD + j;
+        xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
+      }
       for (int kc = 0; kc < tp.k_chunks; ++kc) {
-        const int k0 = kc * BK + kg * PH_PER_THREAD;
+        float xn[PH_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < PH_PER_THREAD; ++j) {
+          const int k = (kc + 1) * BK + kg * PH_PER_THREAD + j;
+          xn[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
+        }
         float c_hi[PH_PER_THREAD], c_lo[PH_PER_THREAD], s_hi[PH_PER_THREAD], s_lo[PH_PER_THREAD];
 #pragma unroll
         for (int j = 0; j < PH_PER_THREAD; ++j) {
-          const int k = k0 + j;
-          const float x = (k < p.K) ? __ldg(kv + k) : 0.0f;
           float sn, cs;
-          fast_sincos(phase_arg(p.sign2pi, x, u), &sn, &cs);
+          fast_sincos(phase_arg(p.sign2pi, xk[j], u), &sn, &cs);
+          xk[j] = xn[j];
           c_hi[j] = tf32_hi(cs);
           c_lo[j] = cs - c_hi[j];
           s_hi[j] = tf32_hi(sn);
