@@ -1,29 +1,36 @@
 // DLUX_PREC_3XTF32: the phasor GEMM stage on Blackwell tensor cores (sm_100a).
 //
-//   D[m][n] = sum_k Data[m][k] * G[k][n],   G[k][n] = exp(i * fl(sign2pi * fl(kvec[k]*nvec[n])))
+//   Out[n][m] = sum_k G[n][k] * Data[m][k],   G[n][k] = exp(i * fl(sign2pi * fl(kvec[k]*nvec[n])))
 //
-// * A operand (data): four planar fp32 planes (re_hi, re_lo, im_hi, im_lo; hi = rna-tf32,
-//   lo = exact residual) streamed by TMA (cp.async.bulk.tensor, SWIZZLE_64B, K-major).
-// * B operand (DFT phasors): never materialised in HBM.  Generator warps evaluate the
-//   reference's float32 phase argument, sincosf, split into tf32 hi/lo and write K-major
-//   SWIZZLE_64B tiles straight into shared memory (generic proxy -> fence.proxy.async ->
-//   mbarrier).  Two stacked arrangements of the same 64 phasor columns are written,
-//   B1 = [cos; sin] and B2 = [-sin; cos] (128 rows each), so that ONE N=128 MMA produces
-//   the real and the imaginary halves of the complex product:
-//       [Re | Im] += A_re * B1 + A_im * B2.
-// * 3xTF32: 6 tcgen05.mma kind::tf32 (M128 x N128 x K8) per k-step -- lo*hi, hi*lo and
-//   hi*hi for each of the two products; lo*lo is dropped (2^-22 relative).
-// * Tensor-core fp32 accumulation truncates (measured: ~2e-8 relative per accumulate,
-//   systematic), so long K chains are NOT kept in TMEM: every FLUSH_CHUNKS k-chunks the
-//   partial accumulator (one of four 128-column TMEM buffers) is drained by the epilogue
-//   warps with tcgen05.ld and added, round-to-nearest, into fp32 registers (the scheme of
-//   Ootomo & Yokota for error-corrected TF32 GEMM).  Draining overlaps the MMAs of the
-//   next partial.
+// One tile = 64 output coordinates n x 128 data rows m.  The MMA is issued in its "TS" form:
+//
+// * A operand = the DFT phasors, in TENSOR MEMORY.  They are never materialised in HBM nor
+//   in shared memory: generator warps evaluate the reference's float32 phase argument, a
+//   Cody-Waite/minimax sincos, split hi/lo (tf32) and write the operand tiles straight
+//   from registers with tcgen05.st.  TMEM lane 2j holds the "real" row of phasor column
+//   j and lane 2j+1 its "imaginary" row, in two arrangements
+//       G1 = (cos | sin),   G2 = (-sin | cos)        (row 2j | row 2j+1)
+//   so that  D = G1 * Re(Data)^T + G2 * Im(Data)^T  has Re(Out[j][:]) in lane 2j and
+//   Im(Out[j][:]) in lane 2j+1: one M128 x N128 x K8 MMA yields both complex parts and the
+//   pair of lanes that shares a phasor also shares its sincos (via __shfl_xor).
+// * B operand = the data: four planar fp32 planes (re_hi, re_lo, im_hi, im_lo) streamed by
+//   TMA (cp.async.bulk.tensor, SWIZZLE_64B, K-major) into a 6-deep shared-memory ring.
+//   Shared memory carries only this operand (32 KiB written + 48 KiB read per 16-k chunk,
+//   vs 64 + 96 KiB when the phasors also lived in smem), which is what bounded the
+//   previous SS-form kernel.
+// * 3xTF32: 6 tcgen05.mma kind::tf32 per k-step -- hi*lo, lo*hi, hi*hi for each of the two
+//   products; lo*lo is dropped (2^-22 relative).
+// * Tensor-core fp32 accumulation truncates (measured ~2e-8 relative systematic loss per
+//   accumulate), so K chains are cut every FLUSH_CHUNKS k-chunks: the partial accumulator
+//   (one of three 128-column TMEM buffers) is drained by the epilogue warpgroup with
+//   tcgen05.ld and added, round-to-nearest, into fp32 registers (Ootomo & Yokota's scheme
+//   for error-corrected TF32 GEMM).  Draining overlaps the MMAs of the next partial.
 // * Persistent CTAs, one per SM, 16 warps in 4 warpgroups: WG0 = drain + fused epilogue
-//   (one warp per TMEM lane quarter; setmaxnreg.inc, they hold the 128 running totals),
-//   WG1 = TMA producer + MMA issuer (setmaxnreg.dec), WG2/WG3 = phasor generators.
-//   The data (TMA) and phasor (generated) operands have separate shared-memory rings
-//   (4 x 32 KiB and 3 x 32 KiB) so that HBM/L2 latency gets the deeper prefetch.
+//   (setmaxnreg.inc: 128 running totals per thread), WG1 = TMA producer + MMA issuer
+//   (setmaxnreg.dec), WG2/WG3 = phasor generators (two warps per TMEM lane quarter, one per
+//   k-step of the chunk).
+// TMEM map (512 columns): [0,384) three partial accumulators, [384,512) two phasor stages
+// of 64 columns = 4 planes (G1_hi, G1_lo, G2_hi, G2_lo) x 16 k.
 #include <cuda.h>
 #include <cstdio>
 #include <mutex>
@@ -33,32 +40,29 @@ namespace dlux {
 
 namespace {
 
-constexpr int BM = 128;            // data rows per tile (UMMA M)
-constexpr int NB = 64;             // generated output coordinates per tile
-constexpr int BN = 2 * NB;         // UMMA N: [Re | Im] halves
+constexpr int BM = 128;            // data rows per tile  (UMMA N)
+constexpr int NB = 64;             // output coordinates per tile; 2*NB TMEM lanes (UMMA M = 128)
 constexpr int BK = 16;             // k per pipeline stage = one 64-byte swizzle row of fp32
 constexpr int UMMA_K = 8;          // kind::tf32
-constexpr int A_STAGES = 4;        // data ring (TMA)
-constexpr int B_STAGES = 3;        // phasor ring (generated)
+constexpr int A_STAGES = 6;        // data ring (TMA)
+constexpr int G_STAGES = 2;        // phasor ring (TMEM)
 constexpr int PLANE_BYTES = BM * BK * 4;            // 8 KiB
 constexpr int A_BYTES = 4 * PLANE_BYTES;            // 32 KiB: re_hi, re_lo, im_hi, im_lo
-constexpr int B_BYTES = 4 * BN * BK * 4;            // 32 KiB: B1_hi, B1_lo, B2_hi, B2_lo
-constexpr int B_BASE = A_STAGES * A_BYTES;
-constexpr int RING_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES;  // 224 KiB
+constexpr int RING_BYTES = A_STAGES * A_BYTES;      // 192 KiB
 constexpr int FLUSH_CHUNKS = 4;    // k-chunks accumulated in TMEM before draining to registers
-constexpr int NUM_ACC = 4;         // TMEM partial-accumulator ring
+constexpr int NUM_ACC = 3;         // TMEM partial-accumulator ring
+constexpr int ACC_COLS = BM;       // 128 fp32 columns per partial
+constexpr int G_COLS = 4 * BK;     // 64 columns per phasor stage
+constexpr int G_BASE_COL = NUM_ACC * ACC_COLS;      // 384
+constexpr int TMEM_COLS = 512;
+static_assert(G_BASE_COL + G_STAGES * G_COLS <= TMEM_COLS, "TMEM budget");
 constexpr int NUM_EPI_WARPS = 4;   // warps 0..3   (WG0)
 constexpr int WARP_TMA = 4;        // WG1
 constexpr int WARP_MMA = 5;
-constexpr int FIRST_GEN_WARP = 8;  // WG2, WG3
+constexpr int FIRST_GEN_WARP = 8;  // WG2 (k-step 0), WG3 (k-step 1)
 constexpr int NUM_GEN_WARPS = 8;
-constexpr int NUM_GEN_THREADS = 32 * NUM_GEN_WARPS;
-constexpr int PH_PER_THREAD = NB * BK / NUM_GEN_THREADS;  // phasors per generator thread per chunk (4)
 constexpr int NUM_THREADS = 32 * (FIRST_GEN_WARP + NUM_GEN_WARPS);  // 512
-constexpr int REGS_EPI = 232, REGS_CTRL = 40, REGS_GEN = 112;  // setmaxnreg budgets (launch: 128)
-constexpr int TMEM_COLS = NUM_ACC * BN;  // 512
-static_assert(TMEM_COLS == 512, "TMEM ring must be a power of two <= 512 columns");
-static_assert(PH_PER_THREAD % 4 == 0, "each generator thread writes whole 16-byte chunks");
+constexpr int REGS_EPI = 232, REGS_CTRL = 40, REGS_GEN = 112;       // setmaxnreg budgets (launch: 128)
 static_assert(128 * (REGS_EPI - 128) <= 128 * (128 - REGS_CTRL) + 256 * (128 - REGS_GEN), "register budget");
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
@@ -90,9 +94,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -105,14 +106,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]   (A: 128 lanes x 8 columns of tf32, K-major)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -128,70 +130,120 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// this thread's lane, 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// One lane of the (converged) warp is elected; the tcgen05/TMA issue blocks are guarded by
+// this instead of `lane == 0` so that the compiler keeps them on the uniform datapath.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 
 // K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused) | SBO>>4 [32,46) (8 rows * 64 B = 512)
 // | version=1 [46,48) | layout_type=4 (SWIZZLE_64B) [61,64)
+constexpr uint64_t DESC_SW64_HI = ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+                                  ((uint64_t)4 << 61);
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+  return DESC_SW64_HI | (uint64_t)(saddr >> 4);  // shared addresses are < 256 KiB: 14 bits after >> 4
 }
 
-// kind::tf32 instruction descriptor: D=f32, A=B=tf32, K-major both, N=128, M=128.
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                           ((uint32_t)(BM >> 4) << 24);
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32, K-major both, M=128 (lanes), N=128 (data rows)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BM >> 3) << 17) |
+                           ((uint32_t)((2 * NB) >> 4) << 24);
 
-// Fused epilogue of one tile row: thread = data row m, tot[0..NB) = Re, tot[NB..2NB) = Im
-// of the NB output coordinates n0.. .  Stores are transposed (m fastest), so a warp writes
-// 128 (fp32) or 256 (c64) contiguous bytes per output coordinate.  Global loads of the
-// gradient epilogue are issued in batches of 8 so that their latency overlaps.
-__device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int m, int n0,
-                                              float (&tot)[BN]) {
+// Fused epilogue of one tile.  Thread = TMEM lane: lane 2j carries Re(Out[n0+j][m0 + c]) and
+// lane 2j+1 Im(...) for the 128 data rows c.  Rows are contiguous in m, so every thread
+// writes whole 512-byte row segments.  Where real and imaginary parts must meet (complex64
+// output, gradient) the lane pair swaps halves with __shfl_xor and each lane finishes 64
+// of the 128 columns.
+__device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int n, int m0, bool is_im,
+                                              float (&tot)[BM]) {
   const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
-  const int nmax = p.n_out - n0;  // columns j < nmax are valid
+  const bool n_ok = n < p.n_out;
+  const int mmax = p.rows - m0;  // columns c < mmax are valid
   if (p.mode == EPI_PLANES) {
-    const size_t base = ((size_t)item * p.n_out + n0) * p.out_pitch + m;
+    if (!n_ok) return;
+    float* hi = p.out_planes[is_im ? 2 : 0] + ((size_t)item * p.n_out + n) * p.out_pitch + m0;
+    float* lo = p.out_planes[is_im ? 3 : 1] + ((size_t)item * p.n_out + n) * p.out_pitch + m0;
+    if (mmax >= BM) {  // out_pitch and m0 are multiples of 4: 16-byte aligned vector stores
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      if (j < nmax) {
-        const float re = tot[j] * sc, im = tot[NB + j] * sc;
-        const float rh = tf32_hi(re), ih = tf32_hi(im);
-        const size_t o = base + (size_t)j * p.out_pitch;
-        p.out_planes[0][o] = rh;
-        p.out_planes[1][o] = re - rh;
-        p.out_planes[2][o] = ih;
-        p.out_planes[3][o] = im - ih;
+      for (int c = 0; c < BM; c += 4) {
+        float4 h, l;
+        const float v0 = tot[c] * sc, v1 = tot[c + 1] * sc, v2 = tot[c + 2] * sc, v3 = tot[c + 3] * sc;
+        h.x = tf32_hi(v0); h.y = tf32_hi(v1); h.z = tf32_hi(v2); h.w = tf32_hi(v3);
+        l.x = v0 - h.x; l.y = v1 - h.y; l.z = v2 - h.z; l.w = v3 - h.w;
+        *reinterpret_cast<float4*>(hi + c) = h;
+        *reinterpret_cast<float4*>(lo + c) = l;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < BM; ++c) {
+        if (c < mmax) {
+          const float v = tot[c] * sc, h = tf32_hi(v);
+          hi[c] = h;
+          lo[c] = v - h;
+        }
       }
     }
-  } else if (p.mode == EPI_C64) {
-    const size_t base = ((size_t)item * p.n_out + n0) * p.rows + m;
+    return;
+  }
+  // modes that need (re, im) together: the even lane finishes columns [0, 64), the odd lane
+  // [64, 128); each sends the half it does not finish to its partner.
+  float re[BM / 2], im[BM / 2];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      if (j < nmax) p.out_c64[base + (size_t)j * p.rows] = make_float2(tot[j] * sc, tot[NB + j] * sc);
-    }
-  } else {  // EPI_GRAD
+  for (int c = 0; c < BM / 2; ++c) {
+    const float mine = is_im ? tot[c + BM / 2] : tot[c];      // the half I finish, my part
+    const float send = is_im ? tot[c] : tot[c + BM / 2];      // the half my partner finishes
+    const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+    re[c] = (is_im ? got : mine) * sc;
+    im[c] = (is_im ? mine : got) * sc;
+  }
+  if (!n_ok) return;
+  const int c0 = is_im ? BM / 2 : 0;
+  const int cmax = mmax - c0;
+  if (p.mode == EPI_C64) {
+    float2* out = p.out_c64 + ((size_t)item * p.n_out + n) * p.rows + m0 + c0;
+#pragma unroll
+    for (int c = 0; c < BM / 2; ++c)
+      if (c < cmax) out[c] = make_float2(re[c], im[c]);
+  } else {  // EPI_GRAD: g = Im(conj(P) * v), P = amp * T * exp(i (k * opd + phase))
     const float kw = __ldg(p.w + item);
     const float amp = p.a0 * __ldg(p.amp_scale);
-    const size_t base = (size_t)n0 * p.rows + m;
+    const size_t base = (size_t)n * p.rows + m0 + c0;
     float* outg = p.out_g + (size_t)item * p.n_out * p.rows + base;
 #pragma unroll
-    for (int j0 = 0; j0 < NB; j0 += 16) {
+    for (int j0 = 0; j0 < BM / 2; j0 += 16) {
       float tv[16], ov[16], pv[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const bool ok = (j0 + j) < nmax;
-        const size_t o = base + (size_t)(j0 + j) * p.rows;
-        tv[j] = (ok && p.pup_T) ? __ldg(p.pup_T + o) : 1.0f;
-        ov[j] = (ok && p.pup_opd) ? __ldg(p.pup_opd + o) : 0.0f;
-        pv[j] = (ok && p.pup_phase) ? __ldg(p.pup_phase + o) : 0.0f;
+        const bool ok = (j0 + j) < cmax;
+        tv[j] = (ok && p.pup_T) ? __ldg(p.pup_T + base + j0 + j) : 1.0f;
+        ov[j] = (ok && p.pup_opd) ? __ldg(p.pup_opd + base + j0 + j) : 0.0f;
+        pv[j] = (ok && p.pup_phase) ? __ldg(p.pup_phase + base + j0 + j) : 0.0f;
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        if ((j0 + j) < nmax) {
-          const float re = tot[j0 + j] * sc, im = tot[NB + j0 + j] * sc;
+        if ((j0 + j) < cmax) {
           float sn, cs;
           fast_sincos(__fmul_rn(kw, ov[j]) + pv[j], &sn, &cs);
-          outg[(size_t)(j0 + j) * p.rows] = amp * tv[j] * (cs * im - sn * re);  // Im(conj(P) * v)
+          outg[j0 + j] = amp * tv[j] * (cs * im[j0 + j] - sn * re[j0 + j]);
         }
       }
     }
@@ -214,12 +266,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   const uint32_t bar_base = smem_base + RING_BYTES;
   auto fullA_bar = [&](int s) { return bar_base + 8u * s; };
   auto emptyA_bar = [&](int s) { return bar_base + 8u * (A_STAGES + s); };
-  auto fullB_bar = [&](int s) { return bar_base + 8u * (2 * A_STAGES + s); };
-  auto emptyB_bar = [&](int s) { return bar_base + 8u * (2 * A_STAGES + B_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * A_STAGES + 2 * B_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * A_STAGES + 2 * B_STAGES + NUM_ACC + a); };
+  auto fullG_bar = [&](int s) { return bar_base + 8u * (2 * A_STAGES + s); };
+  auto emptyG_bar = [&](int s) { return bar_base + 8u * (2 * A_STAGES + G_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * A_STAGES + 2 * G_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * A_STAGES + 2 * G_STAGES + NUM_ACC + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(
-      smem_gen + RING_BYTES + 8 * (2 * A_STAGES + 2 * B_STAGES + 2 * NUM_ACC));
+      smem_gen + RING_BYTES + 8 * (2 * A_STAGES + 2 * G_STAGES + 2 * NUM_ACC));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -234,9 +286,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       mbar_init(fullA_bar(s), 1);   // TMA producer's arrive.expect_tx
       mbar_init(emptyA_bar(s), 1);  // tcgen05.commit
     }
-    for (int s = 0; s < B_STAGES; ++s) {
-      mbar_init(fullB_bar(s), NUM_GEN_WARPS);  // one arrive per generator warp
-      mbar_init(emptyB_bar(s), 1);             // tcgen05.commit
+    for (int s = 0; s < G_STAGES; ++s) {
+      mbar_init(fullG_bar(s), NUM_GEN_WARPS);  // one arrive per generator warp
+      mbar_init(emptyG_bar(s), 1);             // tcgen05.commit
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);                    // tcgen05.commit closing a partial
@@ -254,15 +306,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Register re-balancing between warpgroups: setmaxnreg is the first instruction of each
-  // warpgroup's branch (all four warps of a warpgroup execute it).
   const int tiles_per_item = tp.tiles_m * tp.tiles_n;
 
+  // Register re-balancing between warpgroups: setmaxnreg is the first instruction of each
+  // warpgroup's branch (all four warps of a warpgroup execute it).
   if (warp >= NUM_EPI_WARPS && warp < FIRST_GEN_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
     if (warp == WARP_TMA) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+      // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
@@ -272,67 +323,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         const int d = p.item_data ? __ldg(p.item_data + item) : item;
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           mbar_wait(emptyA_bar(stage), phase ^ 1);
-          const uint32_t a_dst = smem_base + stage * A_BYTES;
-          mbar_arrive_expect_tx(fullA_bar(stage), A_BYTES);
-          tma_load_3d(a_dst + 0 * PLANE_BYTES, &map0, fullA_bar(stage), kc * BK, m0, d);
-          tma_load_3d(a_dst + 1 * PLANE_BYTES, &map1, fullA_bar(stage), kc * BK, m0, d);
-          tma_load_3d(a_dst + 2 * PLANE_BYTES, &map2, fullA_bar(stage), kc * BK, m0, d);
-          tma_load_3d(a_dst + 3 * PLANE_BYTES, &map3, fullA_bar(stage), kc * BK, m0, d);
+          if (elect_one()) {
+            const uint32_t a_dst = smem_base + stage * A_BYTES;
+            mbar_arrive_expect_tx(fullA_bar(stage), A_BYTES);
+            tma_load_3d(a_dst + 0 * PLANE_BYTES, &map0, fullA_bar(stage), kc * BK, m0, d);
+            tma_load_3d(a_dst + 1 * PLANE_BYTES, &map1, fullA_bar(stage), kc * BK, m0, d);
+            tma_load_3d(a_dst + 2 * PLANE_BYTES, &map2, fullA_bar(stage), kc * BK, m0, d);
+            tma_load_3d(a_dst + 3 * PLANE_BYTES, &map3, fullA_bar(stage), kc * BK, m0, d);
+          }
+          __syncwarp();
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    }
     } else if (warp == WARP_MMA) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      // ===================== MMA issuer =====================
+      // The whole warp walks the loop (uniform control flow); one elected lane issues.
+      int sa = 0, sg = 0;
+      uint32_t pa = 0, pg = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           const int in_partial = kc % FLUSH_CHUNKS;
-          if (in_partial == 0) {
-            mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // drain warps are done with this buffer
-            tc_fence_after();
-          }
-          const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-          mbar_wait(fullB_bar(sb), pb);
+          if (in_partial == 0) mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // drain warps are done with this buffer
+          mbar_wait(fullG_bar(sg), pg);
           mbar_wait(fullA_bar(sa), pa);
           tc_fence_after();
-          const uint32_t a0 = smem_base + sa * A_BYTES;
-          const uint32_t b0 = smem_base + B_BASE + sb * B_BYTES;
+          const bool close_partial = (in_partial == FLUSH_CHUNKS - 1) || (kc == tp.k_chunks - 1);
+          if (elect_one()) {
+            const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS);
+            const uint32_t g0 = tmem_base + (uint32_t)(G_BASE_COL + sg * G_COLS);
+            const uint64_t b_rh = make_desc_sw64(smem_base + sa * A_BYTES);  // plane 0, k-step 0
+            constexpr uint64_t PL = PLANE_BYTES >> 4;                        // descriptor step per plane
+            constexpr uint64_t KS = (UMMA_K * 4) >> 4;                       // ... per k-step inside the swizzle row
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-            const uint32_t koff = ks * UMMA_K * 4;  // bytes inside the 64-byte swizzle row
-            const uint64_t a_rh = make_desc_sw64(a0 + 0 * PLANE_BYTES + koff);
-            const uint64_t a_rl = make_desc_sw64(a0 + 1 * PLANE_BYTES + koff);
-            const uint64_t a_ih = make_desc_sw64(a0 + 2 * PLANE_BYTES + koff);
-            const uint64_t a_il = make_desc_sw64(a0 + 3 * PLANE_BYTES + koff);
-            const uint64_t b1h = make_desc_sw64(b0 + 0 * PLANE_BYTES + koff);
-            const uint64_t b1l = make_desc_sw64(b0 + 1 * PLANE_BYTES + koff);
-            const uint64_t b2h = make_desc_sw64(b0 + 2 * PLANE_BYTES + koff);
-            const uint64_t b2l = make_desc_sw64(b0 + 3 * PLANE_BYTES + koff);
-            const uint32_t accum = (in_partial | ks) ? 1u : 0u;
-            // [Re | Im] += A_re * [cos; sin] + A_im * [-sin; cos]; small terms first
-            umma_tf32(d, a_rl, b1h, IDESC, accum);
-            umma_tf32(d, a_rh, b1l, IDESC, 1u);
-            umma_tf32(d, a_il, b2h, IDESC, 1u);
-            umma_tf32(d, a_ih, b2l, IDESC, 1u);
-            umma_tf32(d, a_rh, b1h, IDESC, 1u);
-            umma_tf32(d, a_ih, b2h, IDESC, 1u);
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t d_rh = b_rh + ks * KS, d_rl = d_rh + PL, d_ih = d_rh + 2 * PL, d_il = d_rh + 3 * PL;
+              const uint32_t g1h = g0 + ks * UMMA_K, g1l = g1h + BK, g2h = g1h + 2 * BK, g2l = g1h + 3 * BK;
+              // (Re | Im rows) += G1 * Re(Data)^T + G2 * Im(Data)^T; small terms first
+              umma_tf32_ts(d, g1l, d_rh, IDESC, (in_partial | ks) ? 1u : 0u);
+              umma_tf32_ts(d, g1h, d_rl, IDESC, 1u);
+              umma_tf32_ts(d, g2l, d_ih, IDESC, 1u);
+              umma_tf32_ts(d, g2h, d_il, IDESC, 1u);
+              umma_tf32_ts(d, g1h, d_rh, IDESC, 1u);
+              umma_tf32_ts(d, g2h, d_ih, IDESC, 1u);
+            }
+            umma_commit(emptyA_bar(sa));  // free the smem slot and the phasor stage when these MMAs retire
+            umma_commit(emptyG_bar(sg));
+            if (close_partial) umma_commit(tfull_bar(acc));  // partial complete -> drain warps
           }
-          umma_commit(emptyA_bar(sa));  // free both smem slots when these MMAs retire
-          umma_commit(emptyB_bar(sb));
-          if (in_partial == FLUSH_CHUNKS - 1 || kc == tp.k_chunks - 1) {
-            umma_commit(tfull_bar(acc));  // partial complete -> drain warps
-            if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
-          }
+          __syncwarp();
+          if (close_partial && ++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
-          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          if (++sg == G_STAGES) { sg = 0; pg ^= 1; }
         }
       }
-    }
     }
   } else if (warp < NUM_EPI_WARPS) {
     // ===================== drain + epilogue =====================
@@ -341,20 +386,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n_partials = (tp.k_chunks + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS;
+    const int tl = q * 32 + lane;  // TMEM lane = output row within the tile (2j: Re, 2j+1: Im)
     for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
       const int item = tile / tiles_per_item;
       const int t = tile % tiles_per_item;
-      const int m = (t % tp.tiles_m) * BM + q * 32 + lane;
-      const int n0 = (t / tp.tiles_m) * NB;
-      float tot[BN];
+      const int m0 = (t % tp.tiles_m) * BM;
+      const int n = (t / tp.tiles_m) * NB + (tl >> 1);
+      float tot[BM];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) tot[j] = 0.0f;
+      for (int j = 0; j < BM; ++j) tot[j] = 0.0f;
       for (int part = 0; part < n_partials; ++part) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 0; c < BM; c += 32) {
           uint32_t v0[16], v1[16];
           tmem_ld16(t0 + c, v0);
           tmem_ld16(t0 + c + 16, v1);
@@ -369,75 +415,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         mbar_arrive(tempty_bar(acc));
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
-      if (m < p.rows) tile_epilogue(p, item, m, n0, tot);
+      tile_epilogue(p, item, n, m0, (tl & 1) != 0, tot);
     }
   } else {
     // ===================== phasor generators =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GEN));
-    const int gt = threadIdx.x - 32 * FIRST_GEN_WARP;
-    const int nl = gt & (NB - 1);   // output coordinate within the tile
-    const int kg = gt / NB;         // which PH_PER_THREAD-wide k group of the chunk
+    const int gw = warp - FIRST_GEN_WARP;  // 0..7
+    const int q = warp & 3;                // TMEM lane quarter
+    const int ks = gw >> 2;                // which k-step (8 k) of the chunk this warp produces
+    const bool odd = (lane & 1) != 0;      // odd lane = imaginary row of the phasor column
+    const int jcol = (q * 32 + lane) >> 1; // phasor column within the tile
+    const int ksub = ks * UMMA_K + (odd ? 4 : 0);  // my 4 k's inside the chunk
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int stage = 0;
     uint32_t phase = 0;
-    // SWIZZLE_64B: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3).  Rows nl
-    // and nl + 64 share the same swizzle term (64 is a multiple of 8).
-    const uint32_t row_lo = (uint32_t)nl * 64u;          // rows [0, 64): cos (B1) / -sin (B2)
-    const uint32_t row_hi = (uint32_t)(nl + NB) * 64u;   // rows [64, 128): sin (B1) / cos (B2)
-    const uint32_t sw = ((uint32_t)nl >> 1) & 3u;
     for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
       const int item = tile / tiles_per_item;
       const int t = tile % tiles_per_item;
-      const int n = (t / tp.tiles_m) * NB + nl;
+      const int n = (t / tp.tiles_m) * NB + jcol;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
       const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
-      float xk[PH_PER_THREAD];  // this chunk's k coordinates, prefetched one chunk ahead
+      float xk[4];  // this chunk's k coordinates, prefetched one chunk ahead
 #pragma unroll
-      for (int j = 0; j < PH_PER_THREAD; ++j) {
-        const int k = kg * PH_PER_THREAD + j;
-        xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
-      }
+      for (int j = 0; j < 4; ++j) xk[j] = (ksub + j < p.K) ? __ldg(kv + ksub + j) : 0.0f;
       for (int kc = 0; kc < tp.k_chunks; ++kc) {
-        float xn[PH_PER_THREAD];
+        float xn[4];
 #pragma unroll
-        for (int j = 0; j < PH_PER_THREAD; ++j) {
-          const int k = (kc + 1) * BK + kg * PH_PER_THREAD + j;
+        for (int j = 0; j < 4; ++j) {
+          const int k = (kc + 1) * BK + ksub + j;
           xn[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
         }
-        float c_hi[PH_PER_THREAD], c_lo[PH_PER_THREAD], s_hi[PH_PER_THREAD], s_lo[PH_PER_THREAD];
+        // my 4 phasors, split; then swap with the partner lane (same column, other 4 k's)
+        float c_hi[8], c_lo[8], s_hi[8], s_lo[8];
 #pragma unroll
-        for (int j = 0; j < PH_PER_THREAD; ++j) {
+        for (int j = 0; j < 4; ++j) {
           float sn, cs;
           fast_sincos(phase_arg(p.sign2pi, xk[j], u), &sn, &cs);
           xk[j] = xn[j];
-          c_hi[j] = tf32_hi(cs);
-          c_lo[j] = cs - c_hi[j];
-          s_hi[j] = tf32_hi(sn);
-          s_lo[j] = sn - s_hi[j];
+          const float ch = tf32_hi(cs), sh = tf32_hi(sn);
+          const float cl = cs - ch, sl = sn - sh;
+          const float pch = __shfl_xor_sync(0xffffffffu, ch, 1), pcl = __shfl_xor_sync(0xffffffffu, cl, 1);
+          const float psh = __shfl_xor_sync(0xffffffffu, sh, 1), psl = __shfl_xor_sync(0xffffffffu, sl, 1);
+          // k order inside the k-step: even lane computed k 0..3, odd lane k 4..7
+          c_hi[j] = odd ? pch : ch;      c_lo[j] = odd ? pcl : cl;
+          s_hi[j] = odd ? psh : sh;      s_lo[j] = odd ? psl : sl;
+          c_hi[4 + j] = odd ? ch : pch;  c_lo[4 + j] = odd ? cl : pcl;
+          s_hi[4 + j] = odd ? sh : psh;  s_lo[4 + j] = odd ? sl : psl;
         }
-        mbar_wait(emptyB_bar(stage), phase ^ 1);
-        uint8_t* bb = smem_gen + B_BASE + stage * B_BYTES;
+        // even lane (Re row): G1 = cos, G2 = -sin; odd lane (Im row): G1 = sin, G2 = cos
+        float g1h[8], g1l[8], g2h[8], g2l[8];
 #pragma unroll
-        for (int h = 0; h < PH_PER_THREAD / 4; ++h) {
-          const uint32_t chunk = ((uint32_t)(kg * (PH_PER_THREAD / 4) + h) ^ sw) * 16u;
-          const float4 ch = make_float4(c_hi[4 * h], c_hi[4 * h + 1], c_hi[4 * h + 2], c_hi[4 * h + 3]);
-          const float4 cl = make_float4(c_lo[4 * h], c_lo[4 * h + 1], c_lo[4 * h + 2], c_lo[4 * h + 3]);
-          const float4 sh = make_float4(s_hi[4 * h], s_hi[4 * h + 1], s_hi[4 * h + 2], s_hi[4 * h + 3]);
-          const float4 sl = make_float4(s_lo[4 * h], s_lo[4 * h + 1], s_lo[4 * h + 2], s_lo[4 * h + 3]);
-          const float4 nsh = make_float4(-sh.x, -sh.y, -sh.z, -sh.w);
-          const float4 nsl = make_float4(-sl.x, -sl.y, -sl.z, -sl.w);
-          *reinterpret_cast<float4*>(bb + 0 * PLANE_BYTES + row_lo + chunk) = ch;   // B1_hi: cos
-          *reinterpret_cast<float4*>(bb + 0 * PLANE_BYTES + row_hi + chunk) = sh;   //        sin
-          *reinterpret_cast<float4*>(bb + 1 * PLANE_BYTES + row_lo + chunk) = cl;   // B1_lo
-          *reinterpret_cast<float4*>(bb + 1 * PLANE_BYTES + row_hi + chunk) = sl;
-          *reinterpret_cast<float4*>(bb + 2 * PLANE_BYTES + row_lo + chunk) = nsh;  // B2_hi: -sin
-          *reinterpret_cast<float4*>(bb + 2 * PLANE_BYTES + row_hi + chunk) = ch;   //        cos
-          *reinterpret_cast<float4*>(bb + 3 * PLANE_BYTES + row_lo + chunk) = nsl;  // B2_lo
-          *reinterpret_cast<float4*>(bb + 3 * PLANE_BYTES + row_hi + chunk) = cl;
+        for (int j = 0; j < 8; ++j) {
+          g1h[j] = odd ? s_hi[j] : c_hi[j];
+          g1l[j] = odd ? s_lo[j] : c_lo[j];
+          g2h[j] = odd ? c_hi[j] : -s_hi[j];
+          g2l[j] = odd ? c_lo[j] : -s_lo[j];
         }
-        fence_proxy_async();
+        mbar_wait(emptyG_bar(stage), phase ^ 1);
+        tc_fence_after();
+        const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS + ks * UMMA_K);
+        tmem_st8(g0 + 0 * BK, g1h);
+        tmem_st8(g0 + 1 * BK, g1l);
+        tmem_st8(g0 + 2 * BK, g2h);
+        tmem_st8(g0 + 3 * BK, g2l);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(fullB_bar(stage));
-        if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(fullG_bar(stage));
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -497,6 +542,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   TcState& s = tc_state();
   if (s.rc != DLUX_OK) return s.rc;
   if (p.a_pitch % 4 != 0) return DLUX_ERR_SHAPE;  // TMA global strides are multiples of 16 bytes
+  if (p.mode == EPI_PLANES && p.out_pitch % 4 != 0) return DLUX_ERR_SHAPE;
 
   const cuuint64_t n_data = (cuuint64_t)(p.n_data > 0 ? p.n_data : p.n_items);
   CUtensorMap maps[4];
