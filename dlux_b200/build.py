@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("DLUX_NVCC_EXTRA", "").split()
 
 
 def _stale() -> bool:

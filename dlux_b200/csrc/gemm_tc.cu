@@ -2,7 +2,10 @@
 //
 //   Out[n][m] = sum_k G[n][k] * Data[m][k],   G[n][k] = exp(i * fl(sign2pi * fl(kvec[k]*nvec[n])))
 //
-// One tile = 64 output coordinates n x 128 data rows m.  The MMA is issued in its "TS" form:
+// One work unit = 64 output coordinates n x 256 data rows m, computed as TWO 64 x 128 tiles
+// (a, b) that share every generated phasor -- generation, not the tensor pipe, is the
+// scarce resource, so each phasor is used for 256 data rows.  The MMA is issued in its
+// "TS" form:
 //
 // * A operand = the DFT phasors, in TENSOR MEMORY.  They are never materialised in HBM nor
 //   in shared memory: generator warps evaluate the reference's float32 phase argument, a
@@ -14,21 +17,20 @@
 //   Im(Out[j][:]) in lane 2j+1: one M128 x N128 x K8 MMA yields both complex parts and the
 //   pair of lanes that shares a phasor also shares its sincos (via __shfl_xor).
 // * B operand = the data: four planar fp32 planes (re_hi, re_lo, im_hi, im_lo) streamed by
-//   TMA (cp.async.bulk.tensor, SWIZZLE_64B, K-major) into a 6-deep shared-memory ring.
-//   Shared memory carries only this operand (32 KiB written + 48 KiB read per 16-k chunk,
-//   vs 64 + 96 KiB when the phasors also lived in smem), which is what bounded the
-//   previous SS-form kernel.
+//   TMA (cp.async.bulk.tensor, SWIZZLE_64B, K-major) into a 3-deep shared-memory ring of
+//   64 KiB stages (both tiles).  Shared memory carries only this operand.
 // * 3xTF32: 6 tcgen05.mma kind::tf32 per k-step -- hi*lo, lo*hi, hi*hi for each of the two
 //   products; lo*lo is dropped (2^-22 relative).
 // * Tensor-core fp32 accumulation truncates (measured ~2e-8 relative systematic loss per
-//   accumulate), so K chains are cut every FLUSH_CHUNKS k-chunks: the partial accumulator
-//   (one of three 128-column TMEM buffers) is drained by the epilogue warpgroup with
-//   tcgen05.ld and added, round-to-nearest, into fp32 registers (Ootomo & Yokota's scheme
-//   for error-corrected TF32 GEMM).  Draining overlaps the MMAs of the next partial.
-// * Persistent CTAs, one per SM, 16 warps in 4 warpgroups: WG0 = drain + fused epilogue
-//   (setmaxnreg.inc: 128 running totals per thread), WG1 = TMA producer + MMA issuer
-//   (setmaxnreg.dec), WG2/WG3 = phasor generators (two warps per TMEM lane quarter, one per
-//   k-step of the chunk).
+//   accumulate), so K chains are cut every FLUSH_CHUNKS k-chunks: the partial accumulators
+//   (three 128-column TMEM buffers used round-robin by the two tiles) are drained by the
+//   tile's epilogue warpgroup with tcgen05.ld and added, round-to-nearest, into fp32
+//   registers (Ootomo & Yokota's scheme for error-corrected TF32 GEMM).  Draining overlaps
+//   the MMAs of the other tile / next partial.
+// * Persistent CTAs, one per SM, 16 warps in 4 warpgroups: WG0 / WG1 = drain + fused
+//   epilogue of tile a / b (setmaxnreg.inc: 128 running totals per thread), WG2 = TMA
+//   producer + MMA issuer (setmaxnreg.dec), WG3 = phasor generators (one warp per TMEM lane
+//   quarter).
 // TMEM map (512 columns): [0,384) three partial accumulators, [384,512) two phasor stages
 // of 64 columns = 4 planes (G1_hi, G1_lo, G2_hi, G2_lo) x 16 k.
 #include <cuda.h>
@@ -44,26 +46,27 @@ constexpr int BM = 128;            // data rows per tile  (UMMA N)
 constexpr int NB = 64;             // output coordinates per tile; 2*NB TMEM lanes (UMMA M = 128)
 constexpr int BK = 16;             // k per pipeline stage = one 64-byte swizzle row of fp32
 constexpr int UMMA_K = 8;          // kind::tf32
-constexpr int A_STAGES = 6;        // data ring (TMA)
+constexpr int A_STAGES = 3;        // data ring (TMA), each stage holds both tiles
 constexpr int G_STAGES = 2;        // phasor ring (TMEM)
 constexpr int PLANE_BYTES = BM * BK * 4;            // 8 KiB
-constexpr int A_BYTES = 4 * PLANE_BYTES;            // 32 KiB: re_hi, re_lo, im_hi, im_lo
+constexpr int TILE_BYTES = 4 * PLANE_BYTES;         // 32 KiB: re_hi, re_lo, im_hi, im_lo of one tile
+constexpr int A_BYTES = 2 * TILE_BYTES;             // 64 KiB: tiles a and b
 constexpr int RING_BYTES = A_STAGES * A_BYTES;      // 192 KiB
 constexpr int FLUSH_CHUNKS = 4;    // k-chunks accumulated in TMEM before draining to registers
-constexpr int NUM_ACC = 3;         // TMEM partial-accumulator ring
+constexpr int NUM_ACC = 3;         // TMEM partial-accumulator buffers, used round-robin (a, b, a, b, ...)
 constexpr int ACC_COLS = BM;       // 128 fp32 columns per partial
 constexpr int G_COLS = 4 * BK;     // 64 columns per phasor stage
 constexpr int G_BASE_COL = NUM_ACC * ACC_COLS;      // 384
 constexpr int TMEM_COLS = 512;
 static_assert(G_BASE_COL + G_STAGES * G_COLS <= TMEM_COLS, "TMEM budget");
-constexpr int NUM_EPI_WARPS = 4;   // warps 0..3   (WG0)
-constexpr int WARP_TMA = 4;        // WG1
-constexpr int WARP_MMA = 5;
-constexpr int FIRST_GEN_WARP = 8;  // WG2 (k-step 0), WG3 (k-step 1)
-constexpr int NUM_GEN_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 8;   // warps 0..3 drain tile a (WG0), warps 4..7 tile b (WG1)
+constexpr int WARP_TMA = 8;        // WG2
+constexpr int WARP_MMA = 9;
+constexpr int FIRST_GEN_WARP = 12; // WG3
+constexpr int NUM_GEN_WARPS = 4;
 constexpr int NUM_THREADS = 32 * (FIRST_GEN_WARP + NUM_GEN_WARPS);  // 512
-constexpr int REGS_EPI = 232, REGS_CTRL = 40, REGS_GEN = 112;       // setmaxnreg budgets (launch: 128)
-static_assert(128 * (REGS_EPI - 128) <= 128 * (128 - REGS_CTRL) + 256 * (128 - REGS_GEN), "register budget");
+constexpr int REGS_EPI = 176, REGS_CTRL = 40, REGS_GEN = 120;       // setmaxnreg budgets (launch: 128)
+static_assert(256 * (REGS_EPI - 128) <= 128 * (128 - REGS_CTRL) + 128 * (128 - REGS_GEN), "register budget");
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
@@ -252,7 +255,7 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
 
 struct TcParams {
   GemmParams g;
-  int tiles_m, tiles_n, n_tiles, k_chunks;
+  int tiles_mp, tiles_n, n_units, k_chunks;  // tiles_mp: pairs of 128-row data tiles
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -291,8 +294,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       mbar_init(emptyG_bar(s), 1);             // tcgen05.commit
     }
     for (int a = 0; a < NUM_ACC; ++a) {
-      mbar_init(tfull_bar(a), 1);                    // tcgen05.commit closing a partial
-      mbar_init(tempty_bar(a), NUM_EPI_WARPS * 32);  // every drain thread
+      mbar_init(tfull_bar(a), 1);     // tcgen05.commit closing a partial
+      mbar_init(tempty_bar(a), 128);  // every thread of the draining warpgroup
     }
     fence_barrier_init();
   }
@@ -306,7 +309,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_item = tp.tiles_m * tp.tiles_n;
+  // work unit = (item, n-tile, pair of m-tiles)
+  const int units_per_item = tp.tiles_mp * tp.tiles_n;
+  const int n_partials = (tp.k_chunks + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS;
 
   // Register re-balancing between warpgroups: setmaxnreg is the first instruction of each
   // warpgroup's branch (all four warps of a warpgroup execute it).
@@ -316,20 +321,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
-        const int item = tile / tiles_per_item;
-        const int t = tile % tiles_per_item;
-        const int m0 = (t % tp.tiles_m) * BM;
+      for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
+        const int item = unit / units_per_item;
+        const int t = unit % units_per_item;
+        const int m0 = (t % tp.tiles_mp) * (2 * BM);
         const int d = p.item_data ? __ldg(p.item_data + item) : item;
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           mbar_wait(emptyA_bar(stage), phase ^ 1);
           if (elect_one()) {
-            const uint32_t a_dst = smem_base + stage * A_BYTES;
-            mbar_arrive_expect_tx(fullA_bar(stage), A_BYTES);
-            tma_load_3d(a_dst + 0 * PLANE_BYTES, &map0, fullA_bar(stage), kc * BK, m0, d);
-            tma_load_3d(a_dst + 1 * PLANE_BYTES, &map1, fullA_bar(stage), kc * BK, m0, d);
-            tma_load_3d(a_dst + 2 * PLANE_BYTES, &map2, fullA_bar(stage), kc * BK, m0, d);
-            tma_load_3d(a_dst + 3 * PLANE_BYTES, &map3, fullA_bar(stage), kc * BK, m0, d);
+            const uint32_t dst = smem_base + stage * A_BYTES;
+            const uint32_t bar = fullA_bar(stage);
+            mbar_arrive_expect_tx(bar, A_BYTES);
+            tma_load_3d(dst + 0 * PLANE_BYTES, &map0, bar, kc * BK, m0, d);
+            tma_load_3d(dst + 1 * PLANE_BYTES, &map1, bar, kc * BK, m0, d);
+            tma_load_3d(dst + 2 * PLANE_BYTES, &map2, bar, kc * BK, m0, d);
+            tma_load_3d(dst + 3 * PLANE_BYTES, &map3, bar, kc * BK, m0, d);
+            // tile b: rows beyond the matrix are zero-filled by TMA
+            tma_load_3d(dst + TILE_BYTES + 0 * PLANE_BYTES, &map0, bar, kc * BK, m0 + BM, d);
+            tma_load_3d(dst + TILE_BYTES + 1 * PLANE_BYTES, &map1, bar, kc * BK, m0 + BM, d);
+            tma_load_3d(dst + TILE_BYTES + 2 * PLANE_BYTES, &map2, bar, kc * BK, m0 + BM, d);
+            tma_load_3d(dst + TILE_BYTES + 3 * PLANE_BYTES, &map3, bar, kc * BK, m0 + BM, d);
           }
           __syncwarp();
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
@@ -340,22 +351,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       // The whole warp walks the loop (uniform control flow); one elected lane issues.
       int sa = 0, sg = 0;
       uint32_t pa = 0, pg = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
+      uint32_t seq = 0;  // partial sequence number: tile a uses seq, tile b seq + 1; buffer = seq % 3
+      for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           const int in_partial = kc % FLUSH_CHUNKS;
-          if (in_partial == 0) mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // drain warps are done with this buffer
+          const uint32_t buf_a = seq % NUM_ACC, buf_b = (seq + 1) % NUM_ACC;
+          const bool close_partial = (in_partial == FLUSH_CHUNKS - 1) || (kc == tp.k_chunks - 1);
           mbar_wait(fullG_bar(sg), pg);
           mbar_wait(fullA_bar(sa), pa);
+          if (in_partial == 0) mbar_wait(tempty_bar(buf_a), ((seq / NUM_ACC) & 1) ^ 1);
           tc_fence_after();
-          const bool close_partial = (in_partial == FLUSH_CHUNKS - 1) || (kc == tp.k_chunks - 1);
+          const uint32_t g0 = tmem_base + (uint32_t)(G_BASE_COL + sg * G_COLS);
+          constexpr uint64_t PL = PLANE_BYTES >> 4;   // descriptor step per plane
+          constexpr uint64_t KS = (UMMA_K * 4) >> 4;  // ... per k-step inside the swizzle row
           if (elect_one()) {
-            const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS);
-            const uint32_t g0 = tmem_base + (uint32_t)(G_BASE_COL + sg * G_COLS);
-            const uint64_t b_rh = make_desc_sw64(smem_base + sa * A_BYTES);  // plane 0, k-step 0
-            constexpr uint64_t PL = PLANE_BYTES >> 4;                        // descriptor step per plane
-            constexpr uint64_t KS = (UMMA_K * 4) >> 4;                       // ... per k-step inside the swizzle row
+            const uint32_t d = tmem_base + buf_a * ACC_COLS;
+            const uint64_t b_rh = make_desc_sw64(smem_base + sa * A_BYTES);
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ++ks) {
               const uint64_t d_rh = b_rh + ks * KS, d_rl = d_rh + PL, d_ih = d_rh + 2 * PL, d_il = d_rh + 3 * PL;
@@ -368,37 +379,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
               umma_tf32_ts(d, g1h, d_rh, IDESC, 1u);
               umma_tf32_ts(d, g2h, d_ih, IDESC, 1u);
             }
-            umma_commit(emptyA_bar(sa));  // free the smem slot and the phasor stage when these MMAs retire
-            umma_commit(emptyG_bar(sg));
-            if (close_partial) umma_commit(tfull_bar(acc));  // partial complete -> drain warps
+            if (close_partial) umma_commit(tfull_bar(buf_a));  // tile a's partial complete -> WG0
           }
           __syncwarp();
-          if (close_partial && ++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+          if (in_partial == 0) {
+            mbar_wait(tempty_bar(buf_b), (((seq + 1) / NUM_ACC) & 1) ^ 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint32_t d = tmem_base + buf_b * ACC_COLS;
+            const uint64_t b_rh = make_desc_sw64(smem_base + sa * A_BYTES + TILE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t d_rh = b_rh + ks * KS, d_rl = d_rh + PL, d_ih = d_rh + 2 * PL, d_il = d_rh + 3 * PL;
+              const uint32_t g1h = g0 + ks * UMMA_K, g1l = g1h + BK, g2h = g1h + 2 * BK, g2l = g1h + 3 * BK;
+              umma_tf32_ts(d, g1l, d_rh, IDESC, (in_partial | ks) ? 1u : 0u);
+              umma_tf32_ts(d, g1h, d_rl, IDESC, 1u);
+              umma_tf32_ts(d, g2l, d_ih, IDESC, 1u);
+              umma_tf32_ts(d, g2h, d_il, IDESC, 1u);
+              umma_tf32_ts(d, g1h, d_rh, IDESC, 1u);
+              umma_tf32_ts(d, g2h, d_ih, IDESC, 1u);
+            }
+            umma_commit(emptyA_bar(sa));  // free the smem slot and the phasor stage when these MMAs retire
+            umma_commit(emptyG_bar(sg));
+            if (close_partial) umma_commit(tfull_bar(buf_b));  // tile b's partial complete -> WG1
+          }
+          __syncwarp();
+          if (close_partial) seq += 2;
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
           if (++sg == G_STAGES) { sg = 0; pg ^= 1; }
         }
       }
     }
   } else if (warp < NUM_EPI_WARPS) {
-    // ===================== drain + epilogue =====================
+    // ===================== drain + epilogue (WG0: tile a, WG1: tile b) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const int n_partials = (tp.k_chunks + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS;
-    const int tl = q * 32 + lane;  // TMEM lane = output row within the tile (2j: Re, 2j+1: Im)
-    for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
-      const int item = tile / tiles_per_item;
-      const int t = tile % tiles_per_item;
-      const int m0 = (t % tp.tiles_m) * BM;
-      const int n = (t / tp.tiles_m) * NB + (tl >> 1);
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int which = warp >> 2;     // 0: tile a, 1: tile b
+    uint32_t seq = (uint32_t)which;  // my partials are seq, seq + 2, ...
+    const int tl = q * 32 + lane;    // TMEM lane = output row within the tile (2j: Re, 2j+1: Im)
+    for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
+      const int item = unit / units_per_item;
+      const int t = unit % units_per_item;
+      const int m0 = (t % tp.tiles_mp) * (2 * BM) + which * BM;
+      const int n = (t / tp.tiles_mp) * NB + (tl >> 1);
       float tot[BM];
 #pragma unroll
       for (int j = 0; j < BM; ++j) tot[j] = 0.0f;
       for (int part = 0; part < n_partials; ++part) {
-        mbar_wait(tfull_bar(acc), acc_phase);
+        const uint32_t buf = seq % NUM_ACC;
+        mbar_wait(tfull_bar(buf), (seq / NUM_ACC) & 1);
         tc_fence_after();
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
 #pragma unroll
         for (int c = 0; c < BM; c += 32) {
           uint32_t v0[16], v1[16];
@@ -412,72 +444,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
-        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+        mbar_arrive(tempty_bar(buf));
+        seq += 2;
       }
-      tile_epilogue(p, item, n, m0, (tl & 1) != 0, tot);
+      if (m0 < p.rows) tile_epilogue(p, item, n, m0, (tl & 1) != 0, tot);  // warp-uniform condition
     }
   } else {
     // ===================== phasor generators =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GEN));
-    const int gw = warp - FIRST_GEN_WARP;  // 0..7
     const int q = warp & 3;                // TMEM lane quarter
-    const int ks = gw >> 2;                // which k-step (8 k) of the chunk this warp produces
     const bool odd = (lane & 1) != 0;      // odd lane = imaginary row of the phasor column
     const int jcol = (q * 32 + lane) >> 1; // phasor column within the tile
-    const int ksub = ks * UMMA_K + (odd ? 4 : 0);  // my 4 k's inside the chunk
+    const int ksub = odd ? 4 : 0;          // my 4 k's inside each k-step
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
-      const int item = tile / tiles_per_item;
-      const int t = tile % tiles_per_item;
-      const int n = (t / tp.tiles_m) * NB + jcol;
+    for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
+      const int item = unit / units_per_item;
+      const int t = unit % units_per_item;
+      const int n = (t / tp.tiles_mp) * NB + jcol;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
       const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
-      float xk[4];  // this chunk's k coordinates, prefetched one chunk ahead
+      float xk[2][4];  // this chunk's k coordinates, prefetched one chunk ahead
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xk[j] = (ksub + j < p.K) ? __ldg(kv + ksub + j) : 0.0f;
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = ks * UMMA_K + ksub + j;
+          xk[ks][j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
+        }
       for (int kc = 0; kc < tp.k_chunks; ++kc) {
-        float xn[4];
+        float xn[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = (kc + 1) * BK + ksub + j;
-          xn[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
-        }
-        // my 4 phasors, split; then swap with the partner lane (same column, other 4 k's)
-        float c_hi[8], c_lo[8], s_hi[8], s_lo[8];
+        for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float sn, cs;
-          fast_sincos(phase_arg(p.sign2pi, xk[j], u), &sn, &cs);
-          xk[j] = xn[j];
-          const float ch = tf32_hi(cs), sh = tf32_hi(sn);
-          const float cl = cs - ch, sl = sn - sh;
-          const float pch = __shfl_xor_sync(0xffffffffu, ch, 1), pcl = __shfl_xor_sync(0xffffffffu, cl, 1);
-          const float psh = __shfl_xor_sync(0xffffffffu, sh, 1), psl = __shfl_xor_sync(0xffffffffu, sl, 1);
-          // k order inside the k-step: even lane computed k 0..3, odd lane k 4..7
-          c_hi[j] = odd ? pch : ch;      c_lo[j] = odd ? pcl : cl;
-          s_hi[j] = odd ? psh : sh;      s_lo[j] = odd ? psl : sl;
-          c_hi[4 + j] = odd ? ch : pch;  c_lo[4 + j] = odd ? cl : pcl;
-          s_hi[4 + j] = odd ? sh : psh;  s_lo[4 + j] = odd ? sl : psl;
-        }
-        // even lane (Re row): G1 = cos, G2 = -sin; odd lane (Im row): G1 = sin, G2 = cos
-        float g1h[8], g1l[8], g2h[8], g2l[8];
+          for (int j = 0; j < 4; ++j) {
+            const int k = (kc + 1) * BK + ks * UMMA_K + ksub + j;
+            xn[ks][j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
+          }
+        float g1h[2][8], g1l[2][8], g2h[2][8], g2l[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          g1h[j] = odd ? s_hi[j] : c_hi[j];
-          g1l[j] = odd ? s_lo[j] : c_lo[j];
-          g2h[j] = odd ? c_hi[j] : -s_hi[j];
-          g2l[j] = odd ? c_lo[j] : -s_lo[j];
+        for (int ks = 0; ks < 2; ++ks) {
+          // my 4 phasors of this k-step, split; swap with the partner lane (same column, other 4 k's)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float sn, cs;
+#ifdef DLUX_DEBUG_NOGEN
+            sn = xk[ks][j]; cs = u;
+#else
+            fast_sincos(phase_arg(p.sign2pi, xk[ks][j], u), &sn, &cs);
+#endif
+            xk[ks][j] = xn[ks][j];
+            const float ch = tf32_hi(cs), sh = tf32_hi(sn);
+            const float cl = cs - ch, sl = sn - sh;
+            const float pch = __shfl_xor_sync(0xffffffffu, ch, 1), pcl = __shfl_xor_sync(0xffffffffu, cl, 1);
+            const float psh = __shfl_xor_sync(0xffffffffu, sh, 1), psl = __shfl_xor_sync(0xffffffffu, sl, 1);
+            // k order inside the k-step: the even lane computed k 0..3, the odd lane k 4..7.
+            // even lane (Re row): G1 = cos, G2 = -sin; odd lane (Im row): G1 = sin, G2 = cos
+            g1h[ks][j] = odd ? psh : ch;      g1l[ks][j] = odd ? psl : cl;
+            g2h[ks][j] = odd ? pch : -sh;     g2l[ks][j] = odd ? pcl : -sl;
+            g1h[ks][4 + j] = odd ? sh : pch;  g1l[ks][4 + j] = odd ? sl : pcl;
+            g2h[ks][4 + j] = odd ? ch : -psh; g2l[ks][4 + j] = odd ? cl : -psl;
+          }
         }
         mbar_wait(emptyG_bar(stage), phase ^ 1);
         tc_fence_after();
-        const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS + ks * UMMA_K);
-        tmem_st8(g0 + 0 * BK, g1h);
-        tmem_st8(g0 + 1 * BK, g1l);
-        tmem_st8(g0 + 2 * BK, g2h);
-        tmem_st8(g0 + 3 * BK, g2l);
+        const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          tmem_st8(g0 + 0 * BK + ks * UMMA_K, g1h[ks]);
+          tmem_st8(g0 + 1 * BK + ks * UMMA_K, g1l[ks]);
+          tmem_st8(g0 + 2 * BK + ks * UMMA_K, g2h[ks]);
+          tmem_st8(g0 + 3 * BK + ks * UMMA_K, g2l[ks]);
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -561,13 +600,13 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   }
   TcParams tp;
   tp.g = p;
-  tp.tiles_m = (p.rows + BM - 1) / BM;
+  tp.tiles_mp = (p.rows + 2 * BM - 1) / (2 * BM);
   tp.tiles_n = (p.n_out + NB - 1) / NB;
-  const long long total = (long long)tp.tiles_m * tp.tiles_n * p.n_items;
+  const long long total = (long long)tp.tiles_mp * tp.tiles_n * p.n_items;
   if (total > 2147483647LL) return DLUX_ERR_SHAPE;
-  tp.n_tiles = (int)total;
+  tp.n_units = (int)total;
   tp.k_chunks = (p.K + BK - 1) / BK;
-  const int grid = tp.n_tiles < s.num_sms ? tp.n_tiles : s.num_sms;
+  const int grid = tp.n_units < s.num_sms ? tp.n_units : s.num_sms;
   gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], tp);
   note_launch();
   return check_launch("gemm_tc");
