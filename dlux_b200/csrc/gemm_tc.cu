@@ -67,7 +67,7 @@ constexpr int NUM_GEN_WARPS = 4;
 constexpr int NUM_THREADS = 32 * (FIRST_GEN_WARP + NUM_GEN_WARPS);  // 512
 constexpr int REGS_EPI = 176, REGS_CTRL = 40, REGS_GEN = 120;       // setmaxnreg budgets (launch: 128)
 static_assert(256 * (REGS_EPI - 128) <= 128 * (128 - REGS_CTRL) + 128 * (128 - REGS_GEN), "register budget");
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 2560 /*epilogue staging*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -171,85 +171,125 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BM >> 3) << 17) |
                            ((uint32_t)((2 * NB) >> 4) << 24);
 
-// Fused epilogue of one tile.  Thread = TMEM lane: lane 2j carries Re(Out[n0+j][m0 + c]) and
-// lane 2j+1 Im(...) for the 128 data rows c.  Rows are contiguous in m, so every thread
-// writes whole 512-byte row segments.  Where real and imaginary parts must meet (complex64
-// output, gradient) the lane pair swaps halves with __shfl_xor and each lane finishes 64
-// of the 128 columns.
-__device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int n, int m0, bool is_im,
-                                              float (&tot)[BM]) {
+// Fused epilogue of one tile, staged through shared memory so that every global access is
+// coalesced.  Thread = TMEM lane: within warp q, lane 2j' carries Re(Out[n][m0 + c]) and lane
+// 2j'+1 Im(...) of output row n = nq0 + j' for the 128 data rows c.  In slices of 16 columns
+// each lane drops its values (already scaled) into a [32 rows][16 cols] fp32 staging tile,
+// and the warp reads it back with lanes running along m: 64- or 128-byte row segments per
+// store instruction, real and imaginary parts of one element meeting in one thread.
+constexpr int STG_COLS = 16;
+constexpr int STG_PITCH = 20;                       // floats; conflict-free 128-bit row writes
+constexpr int STG_BYTES = 32 * STG_PITCH * 4;       // 2560 B per warp
+
+__device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int nq0, int m0, int lane,
+                                              float (&tot)[BM], float* stg) {
   const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
-  const bool n_ok = n < p.n_out;
-  const int mmax = p.rows - m0;  // columns c < mmax are valid
-  if (p.mode == EPI_PLANES) {
-    if (!n_ok) return;
-    float* hi = p.out_planes[is_im ? 2 : 0] + ((size_t)item * p.n_out + n) * p.out_pitch + m0;
-    float* lo = p.out_planes[is_im ? 3 : 1] + ((size_t)item * p.n_out + n) * p.out_pitch + m0;
-    if (mmax >= BM) {  // out_pitch and m0 are multiples of 4: 16-byte aligned vector stores
+  const int mmax = p.rows - m0;  // tile columns c < mmax are valid
+  const bool vec_ok = (p.rows & 3) == 0;  // 16-byte alignment of row starts in dense [n][rows] arrays
 #pragma unroll
-      for (int c = 0; c < BM; c += 4) {
-        float4 h, l;
-        const float v0 = tot[c] * sc, v1 = tot[c + 1] * sc, v2 = tot[c + 2] * sc, v3 = tot[c + 3] * sc;
-        h.x = tf32_hi(v0); h.y = tf32_hi(v1); h.z = tf32_hi(v2); h.w = tf32_hi(v3);
-        l.x = v0 - h.x; l.y = v1 - h.y; l.z = v2 - h.z; l.w = v3 - h.w;
-        *reinterpret_cast<float4*>(hi + c) = h;
-        *reinterpret_cast<float4*>(lo + c) = l;
-      }
-    } else {
+  for (int s = 0; s < BM / STG_COLS; ++s) {
+    const int c0 = s * STG_COLS;
 #pragma unroll
-      for (int c = 0; c < BM; ++c) {
-        if (c < mmax) {
-          const float v = tot[c] * sc, h = tf32_hi(v);
-          hi[c] = h;
-          lo[c] = v - h;
+    for (int v = 0; v < STG_COLS / 4; ++v)
+      *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * v) =
+          make_float4(tot[c0 + 4 * v] * sc, tot[c0 + 4 * v + 1] * sc, tot[c0 + 4 * v + 2] * sc,
+                      tot[c0 + 4 * v + 3] * sc);
+    __syncwarp();
+    if (c0 < mmax) {  // warp-uniform
+      if (p.mode == EPI_PLANES) {
+        // lane -> staging rows r = lane/4 + 8*it (it = 0..3), 4 columns at 4*(lane%4)
+        const int cc = 4 * (lane & 3);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = (lane >> 2) + 8 * it;
+          const int n = nq0 + (r >> 1);
+          const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + cc);
+          if (n < p.n_out) {
+            float4 h;
+            h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+            const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            const size_t o = ((size_t)item * p.n_out + n) * p.out_pitch + m0 + c0 + cc;
+            float* hp = p.out_planes[(r & 1) ? 2 : 0] + o;
+            float* lp = p.out_planes[(r & 1) ? 3 : 1] + o;
+            if (c0 + cc + 4 <= mmax) {  // out_pitch, m0, c0, cc are multiples of 4
+              *reinterpret_cast<float4*>(hp) = h;
+              *reinterpret_cast<float4*>(lp) = l;
+            } else {
+              const float hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c0 + cc + e < mmax) { hp[e] = hh[e]; lp[e] = ll[e]; }
+            }
+          }
+        }
+      } else if (p.mode == EPI_C64) {
+        // lane -> output row j = lane/8 + 4*it (it = 0..3), complex pair at columns 2*(lane%8)
+        const int cc = 2 * (lane & 7);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int j = (lane >> 3) + 4 * it;
+          const int n = nq0 + j;
+          const float2 re = *reinterpret_cast<const float2*>(stg + (2 * j) * STG_PITCH + cc);
+          const float2 im = *reinterpret_cast<const float2*>(stg + (2 * j + 1) * STG_PITCH + cc);
+          if (n < p.n_out) {
+            float2* out = p.out_c64 + ((size_t)item * p.n_out + n) * p.rows + m0 + c0 + cc;
+            if (((p.rows & 1) == 0) && c0 + cc + 2 <= mmax) {
+              *reinterpret_cast<float4*>(out) = make_float4(re.x, im.x, re.y, im.y);
+            } else {
+              if (c0 + cc < mmax) out[0] = make_float2(re.x, im.x);
+              if (c0 + cc + 1 < mmax) out[1] = make_float2(re.y, im.y);
+            }
+          }
+        }
+      } else {  // EPI_GRAD: g = Im(conj(P) * v), P = amp * T * exp(i (k * opd + phase))
+        const float kw = __ldg(p.w + item);
+        const float amp = p.a0 * __ldg(p.amp_scale);
+        const int cc = 4 * (lane & 3);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int j = (lane >> 2) + 8 * it;
+          const int n = nq0 + j;
+          const float4 re4 = *reinterpret_cast<const float4*>(stg + (2 * j) * STG_PITCH + cc);
+          const float4 im4 = *reinterpret_cast<const float4*>(stg + (2 * j + 1) * STG_PITCH + cc);
+          if (n < p.n_out) {
+            const size_t o = (size_t)n * p.rows + m0 + c0 + cc;
+            float* outg = p.out_g + (size_t)item * p.n_out * p.rows + o;
+            const float re[4] = {re4.x, re4.y, re4.z, re4.w}, im[4] = {im4.x, im4.y, im4.z, im4.w};
+            float tv[4] = {1.f, 1.f, 1.f, 1.f}, ov[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool vec = vec_ok && (c0 + cc + 4 <= mmax);
+            if (vec) {
+              if (p.pup_T) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.pup_T + o)); tv[0] = t.x; tv[1] = t.y; tv[2] = t.z; tv[3] = t.w; }
+              if (p.pup_opd) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.pup_opd + o)); ov[0] = t.x; ov[1] = t.y; ov[2] = t.z; ov[3] = t.w; }
+              if (p.pup_phase) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.pup_phase + o)); pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w; }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (c0 + cc + e < mmax) {
+                  if (p.pup_T) tv[e] = __ldg(p.pup_T + o + e);
+                  if (p.pup_opd) ov[e] = __ldg(p.pup_opd + o + e);
+                  if (p.pup_phase) pv[e] = __ldg(p.pup_phase + o + e);
+                }
+              }
+            }
+            float g[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float sn, cs;
+              fast_sincos(__fmul_rn(kw, ov[e]) + pv[e], &sn, &cs);
+              g[e] = amp * tv[e] * (cs * im[e] - sn * re[e]);
+            }
+            if (vec) {
+              *reinterpret_cast<float4*>(outg) = make_float4(g[0], g[1], g[2], g[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c0 + cc + e < mmax) outg[e] = g[e];
+            }
+          }
         }
       }
     }
-    return;
-  }
-  // modes that need (re, im) together: the even lane finishes columns [0, 64), the odd lane
-  // [64, 128); each sends the half it does not finish to its partner.
-  float re[BM / 2], im[BM / 2];
-#pragma unroll
-  for (int c = 0; c < BM / 2; ++c) {
-    const float mine = is_im ? tot[c + BM / 2] : tot[c];      // the half I finish, my part
-    const float send = is_im ? tot[c] : tot[c + BM / 2];      // the half my partner finishes
-    const float got = __shfl_xor_sync(0xffffffffu, send, 1);
-    re[c] = (is_im ? got : mine) * sc;
-    im[c] = (is_im ? mine : got) * sc;
-  }
-  if (!n_ok) return;
-  const int c0 = is_im ? BM / 2 : 0;
-  const int cmax = mmax - c0;
-  if (p.mode == EPI_C64) {
-    float2* out = p.out_c64 + ((size_t)item * p.n_out + n) * p.rows + m0 + c0;
-#pragma unroll
-    for (int c = 0; c < BM / 2; ++c)
-      if (c < cmax) out[c] = make_float2(re[c], im[c]);
-  } else {  // EPI_GRAD: g = Im(conj(P) * v), P = amp * T * exp(i (k * opd + phase))
-    const float kw = __ldg(p.w + item);
-    const float amp = p.a0 * __ldg(p.amp_scale);
-    const size_t base = (size_t)n * p.rows + m0 + c0;
-    float* outg = p.out_g + (size_t)item * p.n_out * p.rows + base;
-#pragma unroll
-    for (int j0 = 0; j0 < BM / 2; j0 += 16) {
-      float tv[16], ov[16], pv[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const bool ok = (j0 + j) < cmax;
-        tv[j] = (ok && p.pup_T) ? __ldg(p.pup_T + base + j0 + j) : 1.0f;
-        ov[j] = (ok && p.pup_opd) ? __ldg(p.pup_opd + base + j0 + j) : 0.0f;
-        pv[j] = (ok && p.pup_phase) ? __ldg(p.pup_phase + base + j0 + j) : 0.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if ((j0 + j) < cmax) {
-          float sn, cs;
-          fast_sincos(__fmul_rn(kw, ov[j]) + pv[j], &sn, &cs);
-          outg[j0 + j] = amp * tv[j] * (cs * im[j0 + j] - sn * re[j0 + j]);
-        }
-      }
-    }
+    __syncwarp();
   }
 }
 
@@ -417,12 +457,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int which = warp >> 2;     // 0: tile a, 1: tile b
     uint32_t seq = (uint32_t)which;  // my partials are seq, seq + 2, ...
-    const int tl = q * 32 + lane;    // TMEM lane = output row within the tile (2j: Re, 2j+1: Im)
+    float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256 + warp * STG_BYTES);
     for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
       const int item = unit / units_per_item;
       const int t = unit % units_per_item;
       const int m0 = (t % tp.tiles_mp) * (2 * BM) + which * BM;
-      const int n = (t / tp.tiles_mp) * NB + (tl >> 1);
+      const int nq0 = (t / tp.tiles_mp) * NB + q * 16;  // first output row of this warp's lane quarter
       float tot[BM];
 #pragma unroll
       for (int j = 0; j < BM; ++j) tot[j] = 0.0f;
@@ -447,7 +487,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         mbar_arrive(tempty_bar(buf));
         seq += 2;
       }
-      if (m0 < p.rows) tile_epilogue(p, item, n, m0, (tl & 1) != 0, tot);  // warp-uniform condition
+#ifdef DLUX_DEBUG_NOEPI
+      if (m0 < p.rows && tot[5] == 123.456f) tile_epilogue(p, item, nq0, m0, lane, tot, stg);
+#else
+      if (m0 < p.rows) tile_epilogue(p, item, nq0, m0, lane, tot, stg);  // warp-uniform condition
+#endif
     }
   } else {
     // ===================== phasor generators =====================
