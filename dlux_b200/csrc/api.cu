@@ -280,7 +280,7 @@ struct PolyScratch {
   float *xin, *uout;  // per chunk
   float* mid_pl[4];   // per chunk [c][M*N]
   float* ebar_pl[4];  // per chunk [c][M*M]  (bwd only; sized always for simplicity)
-  float* gbuf;        // per chunk [c][N*N]: per-item gradient contributions (bwd)
+  float2* qbuf;       // per chunk [c][N*N]: adjoint field Q per item (bwd)
   float2* fbuf;       // per chunk [c][M*M]: field, when the caller does not keep it (fwd)
   int chunk;
 };
@@ -288,7 +288,7 @@ struct PolyScratch {
 static int poly_chunk(const dlux_polypsf_desc* d) {
   const size_t N = d->n_pupil, M = d->n_psf;
   const size_t per_item = 16 * mid_elems((int)N, (int)M) + 16 * M * pitch4((int)M) + 8 * (N + M) +
-                          4 * N * N + 8 * M * M;
+                          8 * N * N + 8 * M * M;
   const size_t items = (size_t)d->n_sources * d->n_wavels;
   return (int)balanced_chunk(items, kChunkBudget / per_item);
 }
@@ -309,7 +309,7 @@ static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, 
   s->uout = b.take<float>(c * 2 * M);
   for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * mid_elems((int)N, (int)M));
   for (int i = 0; i < 4; ++i) s->ebar_pl[i] = b.take<float>(c * M * pitch4((int)M));
-  s->gbuf = b.take<float>(c * N * N);
+  s->qbuf = b.take<float2>(c * N * N);
   s->fbuf = b.take<float2>(c * M * M);
   b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
   if (ok) *ok = b.ok;
@@ -438,18 +438,13 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     GemmParams h{};
     fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
     for (int i = 0; i < 4; ++i) h.a_planes[i] = s.mid_pl[i];
-    h.mode = EPI_GRAD;
+    h.mode = EPI_C64;
     h.scale = s.norm_item + b0;
-    h.w = s.k_item + b0;
-    h.pup_T = T;
-    h.pup_opd = opd;
-    h.pup_phase = phase;
-    h.amp_scale = s.amp_scale;
-    h.a0 = 1.0f / (float)((long long)N * N);
-    h.out_g = s.gbuf;
+    h.out_c64 = s.qbuf;
     rc = run_gemm(h, d->precision, st);
     if (rc) return rc;
-    rc = launch_grad_reduce((size_t)N * N, c, s.gbuf, s.k_item + b0, opd_bar, phase_bar, b0 > 0, st);
+    rc = launch_grad_reduce((size_t)N * N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale,
+                            1.0f / (float)((long long)N * N), opd_bar, phase_bar, b0 > 0, st);
     if (rc) return rc;
   }
   return DLUX_OK;

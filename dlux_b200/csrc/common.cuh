@@ -19,8 +19,7 @@ namespace dlux {
 // ---------------------------------------------------------------------------
 enum EpilogueMode : int {
   EPI_PLANES = 0,  // out_planes[p][item][n][m], p = re_hi, re_lo, im_hi, im_lo  (feeds the next stage)
-  EPI_C64 = 1,     // out_c64[item][n][m]
-  EPI_GRAD = 3     // out_g[item][n][m] = Im(conj(P[n][m]) * v)  (summed over items by grad_reduce)
+  EPI_C64 = 1      // out_c64[item][n][m]
 };
 
 struct GemmParams {
@@ -42,15 +41,6 @@ struct GemmParams {
   float* out_planes[4];  // EPI_PLANES: [n_items][n_out][out_pitch]
   int out_pitch;
   float2* out_c64;       // EPI_C64: [n_items][n_out][rows]
-  const float* w;        // EPI_GRAD: wavenumber per item
-  // EPI_GRAD: the pupil phasor P = amp * T * exp(i (k * opd + phase)) is re-evaluated in the
-  // epilogue from the (L2-resident) pupil arrays instead of being re-read per wavelength
-  const float* pup_T;      // [n_out][rows] or nullptr (= 1)
-  const float* pup_opd;    // [n_out][rows] or nullptr
-  const float* pup_phase;  // [n_out][rows] or nullptr
-  const float* amp_scale;  // device scalar (power normalisation)
-  float a0;                // 1 / N^2
-  float* out_g;            // EPI_GRAD: [n_items][n_out][rows]
 };
 
 __device__ __forceinline__ float tf32_hi(float x) {
@@ -111,18 +101,8 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
     p.out_planes[1][po] = re - rh;
     p.out_planes[2][po] = ih;
     p.out_planes[3][po] = im - ih;
-  } else if (p.mode == EPI_C64) {
+  } else {  // EPI_C64
     p.out_c64[idx] = make_float2(re, im);
-  } else {  // EPI_GRAD
-    const size_t oi = (size_t)n * p.rows + m;
-    const float kw = __ldg(p.w + item);
-    float a = p.a0 * __ldg(p.amp_scale);
-    if (p.pup_T) a *= __ldg(p.pup_T + oi);
-    float th = p.pup_opd ? __fmul_rn(kw, __ldg(p.pup_opd + oi)) : 0.0f;
-    if (p.pup_phase) th += __ldg(p.pup_phase + oi);
-    float sn, cs;
-    fast_sincos(th, &sn, &cs);
-    p.out_g[idx] = a * (cs * im - sn * re);  // Im(conj(P) * v)
   }
 }
 
@@ -157,8 +137,11 @@ int launch_zero(float* p, size_t n, cudaStream_t st);
 // psf[i] (+)= sum_item w[item] |field[item][i]|^2
 int launch_psf_reduce(size_t npix, int n_items, const float2* field, const float* w, float* psf,
                       int accumulate, cudaStream_t st);
-// opd_bar[i] (+)= sum_item k[item] g[item][i];  phase_bar[i] (+)= sum_item g[item][i]
-int launch_grad_reduce(size_t npix, int n_items, const float* g, const float* k, float* opd_bar,
-                       float* phase_bar, int accumulate, cudaStream_t st);
+// Gradient of the pupil phase from the adjoint field Q = MFT^H(Ebar), summed over items:
+//   g = Im(conj(P) Q),  P = a0 * amp_scale * T * exp(i (k * opd + phase))
+//   opd_bar[i] (+)= sum_item k[item] g[item][i];  phase_bar[i] (+)= sum_item g[item][i]
+int launch_grad_reduce(size_t npix, int n_items, const float2* q, const float* k, const float* T,
+                       const float* opd, const float* phase, const float* amp_scale, float a0,
+                       float* opd_bar, float* phase_bar, int accumulate, cudaStream_t st);
 
 }  // namespace dlux

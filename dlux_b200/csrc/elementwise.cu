@@ -335,28 +335,47 @@ int launch_psf_reduce(size_t npix, int n_items, const float2* field, const float
   return check_launch("psf_reduce");
 }
 
-__global__ void grad_reduce_kernel(size_t npix, int n_items, const float* __restrict__ g,
-                                   const float* __restrict__ k, float* __restrict__ opd_bar,
-                                   float* __restrict__ phase_bar, int accumulate) {
+// VJP of the pupil phasor (wavefronts.py:349,368): the adjoint stage leaves Q = MFT^H(Ebar)
+// per (source, wavelength); dL/d(phase) = Im(conj(P) Q) with P re-evaluated here from the
+// L2-resident pupil arrays.  Pixels outside the aperture (T == 0) cost nothing.
+__global__ void grad_reduce_kernel(size_t npix, int n_items, const float2* __restrict__ q,
+                                   const float* __restrict__ k, const float* __restrict__ T,
+                                   const float* __restrict__ opd, const float* __restrict__ phase,
+                                   const float* __restrict__ amp_scale, float a0,
+                                   float* __restrict__ opd_bar, float* __restrict__ phase_bar,
+                                   int accumulate) {
+  const float amp = a0 * amp_scale[0];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (size_t)gridDim.x * blockDim.x) {
     float ao = (accumulate && opd_bar) ? opd_bar[i] : 0.0f;
     float ap = (accumulate && phase_bar) ? phase_bar[i] : 0.0f;
-#pragma unroll 8
-    for (int it = 0; it < n_items; ++it) {
-      const float v = g[(size_t)it * npix + i];
-      ao = fmaf(__ldg(k + it), v, ao);
-      ap += v;
+    const float t = T ? T[i] : 1.0f;
+    if (t != 0.0f) {
+      const float a = amp * t;
+      const float o = opd ? opd[i] : 0.0f;
+      const float ph = phase ? phase[i] : 0.0f;
+#pragma unroll 4
+      for (int it = 0; it < n_items; ++it) {
+        const float2 v = q[(size_t)it * npix + i];
+        const float kw = __ldg(k + it);
+        float sn, cs;
+        fast_sincos(__fmul_rn(kw, o) + ph, &sn, &cs);
+        const float g = a * (cs * v.y - sn * v.x);
+        ao = fmaf(kw, g, ao);
+        ap += g;
+      }
     }
     if (opd_bar) opd_bar[i] = ao;
     if (phase_bar) phase_bar[i] = ap;
   }
 }
 
-int launch_grad_reduce(size_t npix, int n_items, const float* g, const float* k, float* opd_bar,
-                       float* phase_bar, int accumulate, cudaStream_t st) {
-  grad_reduce_kernel<<<grid_for(npix, 128, 148 * 8), 128, 0, st>>>(npix, n_items, g, k, opd_bar, phase_bar,
-                                                                   accumulate);
+int launch_grad_reduce(size_t npix, int n_items, const float2* q, const float* k, const float* T,
+                       const float* opd, const float* phase, const float* amp_scale, float a0,
+                       float* opd_bar, float* phase_bar, int accumulate, cudaStream_t st) {
+  grad_reduce_kernel<<<grid_for(npix, 128, 148 * 16), 128, 0, st>>>(npix, n_items, q, k, T, opd, phase,
+                                                                    amp_scale, a0, opd_bar, phase_bar,
+                                                                    accumulate);
   note_launch();
   return check_launch("grad_reduce");
 }

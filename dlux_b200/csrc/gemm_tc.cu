@@ -185,7 +185,6 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
                                               float (&tot)[BM], float* stg) {
   const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
   const int mmax = p.rows - m0;  // tile columns c < mmax are valid
-  const bool vec_ok = (p.rows & 3) == 0;  // 16-byte alignment of row starts in dense [n][rows] arrays
 #pragma unroll
   for (int s = 0; s < BM / STG_COLS; ++s) {
     const int c0 = s * STG_COLS;
@@ -222,7 +221,7 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
             }
           }
         }
-      } else if (p.mode == EPI_C64) {
+      } else {  // EPI_C64
         // lane -> output row j = lane/8 + 4*it (it = 0..3), complex pair at columns 2*(lane%8)
         const int cc = 2 * (lane & 7);
 #pragma unroll
@@ -238,52 +237,6 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
             } else {
               if (c0 + cc < mmax) out[0] = make_float2(re.x, im.x);
               if (c0 + cc + 1 < mmax) out[1] = make_float2(re.y, im.y);
-            }
-          }
-        }
-      } else {  // EPI_GRAD: g = Im(conj(P) * v), P = amp * T * exp(i (k * opd + phase))
-        const float kw = __ldg(p.w + item);
-        const float amp = p.a0 * __ldg(p.amp_scale);
-        const int cc = 4 * (lane & 3);
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int j = (lane >> 2) + 8 * it;
-          const int n = nq0 + j;
-          const float4 re4 = *reinterpret_cast<const float4*>(stg + (2 * j) * STG_PITCH + cc);
-          const float4 im4 = *reinterpret_cast<const float4*>(stg + (2 * j + 1) * STG_PITCH + cc);
-          if (n < p.n_out) {
-            const size_t o = (size_t)n * p.rows + m0 + c0 + cc;
-            float* outg = p.out_g + (size_t)item * p.n_out * p.rows + o;
-            const float re[4] = {re4.x, re4.y, re4.z, re4.w}, im[4] = {im4.x, im4.y, im4.z, im4.w};
-            float tv[4] = {1.f, 1.f, 1.f, 1.f}, ov[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
-            const bool vec = vec_ok && (c0 + cc + 4 <= mmax);
-            if (vec) {
-              if (p.pup_T) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.pup_T + o)); tv[0] = t.x; tv[1] = t.y; tv[2] = t.z; tv[3] = t.w; }
-              if (p.pup_opd) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.pup_opd + o)); ov[0] = t.x; ov[1] = t.y; ov[2] = t.z; ov[3] = t.w; }
-              if (p.pup_phase) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.pup_phase + o)); pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w; }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (c0 + cc + e < mmax) {
-                  if (p.pup_T) tv[e] = __ldg(p.pup_T + o + e);
-                  if (p.pup_opd) ov[e] = __ldg(p.pup_opd + o + e);
-                  if (p.pup_phase) pv[e] = __ldg(p.pup_phase + o + e);
-                }
-              }
-            }
-            float g[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float sn, cs;
-              fast_sincos(__fmul_rn(kw, ov[e]) + pv[e], &sn, &cs);
-              g[e] = amp * tv[e] * (cs * im[e] - sn * re[e]);
-            }
-            if (vec) {
-              *reinterpret_cast<float4*>(outg) = make_float4(g[0], g[1], g[2], g[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (c0 + cc + e < mmax) outg[e] = g[e];
             }
           }
         }
