@@ -120,10 +120,16 @@ __global__ void power_partial_kernel(int N, const float* __restrict__ T, double*
 
 __global__ void power_final_kernel(const double* __restrict__ partial, int n, int normalise,
                                    float* __restrict__ amp_scale) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) s += partial[i];
-    const float power = (float)s;
+  // fixed-order tree over 256 partials: deterministic
+  __shared__ double sm[256];
+  sm[threadIdx.x] = threadIdx.x < n ? partial[threadIdx.x] : 0.0;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float power = (float)sm[0];
     amp_scale[0] = normalise ? sqrtf(1.0f / power) : 1.0f;
   }
 }
@@ -132,7 +138,7 @@ int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStr
   // amp_scale points at: [float amp_scale][pad to 8][double partial[256]]
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(amp_scale) + 16);
   power_partial_kernel<<<256, 256, 0, st>>>(N, T, partial);
-  power_final_kernel<<<1, 32, 0, st>>>(partial, 256, normalise, amp_scale);
+  power_final_kernel<<<1, 256, 0, st>>>(partial, 256, normalise, amp_scale);
   note_launch(2);
   return check_launch("power");
 }
@@ -144,46 +150,59 @@ __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const fl
                              const float* __restrict__ phase, const float* __restrict__ wavenumber,
                              const float* __restrict__ amp_scale, float* __restrict__ p0,
                              float* __restrict__ p1, float* __restrict__ p2, float* __restrict__ p3) {
-  const size_t n = (size_t)N * N;
+  // one thread = 4 consecutive pixels of one row (pitch4(N) >= N, both multiples of 4 in the
+  // vector path); the 4 planes get 16-byte stores
   const int pitch = pitch4(N);
+  const int groups_per_row = pitch / 4;
+  const size_t n_groups = (size_t)N * groups_per_row;
   const float a0 = 1.0f / (float)((long long)N * N);
   const float sc = amp_scale[0];
   const int l = blockIdx.y;
   const float k = wavenumber[l];
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const float a = T ? a0 * T[i] : a0;
-    float re = a, im = 0.0f;
-    if (opd) {
-      float s, c;
-      sincosf(__fmul_rn(k, opd[i]), &s, &c);
-      re = a * c;
-      im = a * s;
+  for (size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_groups;
+       gidx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(gidx / groups_per_row);
+    const int c = (int)(gidx - (size_t)r * groups_per_row) * 4;
+    float rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float re = 0.0f, im = 0.0f;
+      if (c + e < N) {
+        const size_t i = (size_t)r * N + c + e;
+        const float a = T ? a0 * __ldg(T + i) : a0;
+        re = a;
+        if (opd) {
+          float sn, cs;
+          fast_sincos(__fmul_rn(k, __ldg(opd + i)), &sn, &cs);
+          re = a * cs;
+          im = a * sn;
+        }
+        if (phase) {
+          float sn, cs;
+          fast_sincos(__ldg(phase + i), &sn, &cs);
+          const float r2 = __fsub_rn(__fmul_rn(re, cs), __fmul_rn(im, sn));
+          const float i2 = __fadd_rn(__fmul_rn(re, sn), __fmul_rn(im, cs));
+          re = r2;
+          im = i2;
+        }
+        re *= sc;
+        im *= sc;
+      }
+      rh[e] = tf32_hi(re); rl[e] = re - rh[e];
+      ih[e] = tf32_hi(im); il[e] = im - ih[e];
     }
-    if (phase) {
-      float s, c;
-      sincosf(phase[i], &s, &c);
-      const float r2 = __fsub_rn(__fmul_rn(re, c), __fmul_rn(im, s));
-      const float i2 = __fadd_rn(__fmul_rn(re, s), __fmul_rn(im, c));
-      re = r2;
-      im = i2;
-    }
-    re *= sc;
-    im *= sc;
-    const size_t r = i / N;
-    const size_t o = ((size_t)l * N + r) * pitch + (i - r * N);
-    const float rh = tf32_hi(re), ih = tf32_hi(im);
-    p0[o] = rh;
-    p1[o] = re - rh;
-    p2[o] = ih;
-    p3[o] = im - ih;
+    const size_t o = ((size_t)l * N + r) * pitch + c;
+    *reinterpret_cast<float4*>(p0 + o) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+    *reinterpret_cast<float4*>(p1 + o) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+    *reinterpret_cast<float4*>(p2 + o) = make_float4(ih[0], ih[1], ih[2], ih[3]);
+    *reinterpret_cast<float4*>(p3 + o) = make_float4(il[0], il[1], il[2], il[3]);
   }
 }
 
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
                  const float* wavenumber, const float* amp_scale, float* p0, float* p1, float* p2,
                  float* p3, cudaStream_t st) {
-  dim3 grid(grid_for((size_t)N * N, 256, 148 * 4), L);
+  dim3 grid(grid_for((size_t)N * (pitch4(N) / 4), 256, 148 * 8), L);
   pupil_kernel<<<grid, 256, 0, st>>>(N, L, T, opd, phase, wavenumber, amp_scale, p0, p1, p2, p3);
   note_launch();
   return check_launch("pupil");
@@ -316,21 +335,39 @@ int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* o
 // kernels reduce them (optical_systems.py:222-223 `psf.sum(0)`, sources.py:409-411).
 __global__ void psf_reduce_kernel(size_t npix, int n_items, const float2* __restrict__ field,
                                   const float* __restrict__ w, float* __restrict__ psf, int accumulate) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
-       i += (size_t)gridDim.x * blockDim.x) {
-    float acc = accumulate ? psf[i] : 0.0f;
+  if ((npix & 1) == 0) {  // two pixels (one float4 of field) per thread; item stride stays 16-B aligned
+    const size_t npair = npix / 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair;
+         i += (size_t)gridDim.x * blockDim.x) {
+      float a0 = accumulate ? psf[2 * i] : 0.0f, a1 = accumulate ? psf[2 * i + 1] : 0.0f;
+      const float4* f = reinterpret_cast<const float4*>(field) + i;
 #pragma unroll 8
-    for (int it = 0; it < n_items; ++it) {
-      const float2 e = field[(size_t)it * npix + i];
-      acc = fmaf(__ldg(w + it), e.x * e.x + e.y * e.y, acc);
+      for (int it = 0; it < n_items; ++it) {
+        const float4 e = f[(size_t)it * npair];
+        const float wt = __ldg(w + it);
+        a0 = fmaf(wt, e.x * e.x + e.y * e.y, a0);
+        a1 = fmaf(wt, e.z * e.z + e.w * e.w, a1);
+      }
+      psf[2 * i] = a0;
+      psf[2 * i + 1] = a1;
     }
-    psf[i] = acc;
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+         i += (size_t)gridDim.x * blockDim.x) {
+      float acc = accumulate ? psf[i] : 0.0f;
+#pragma unroll 8
+      for (int it = 0; it < n_items; ++it) {
+        const float2 e = field[(size_t)it * npix + i];
+        acc = fmaf(__ldg(w + it), e.x * e.x + e.y * e.y, acc);
+      }
+      psf[i] = acc;
+    }
   }
 }
 
 int launch_psf_reduce(size_t npix, int n_items, const float2* field, const float* w, float* psf,
                       int accumulate, cudaStream_t st) {
-  psf_reduce_kernel<<<grid_for(npix, 128, 148 * 8), 128, 0, st>>>(npix, n_items, field, w, psf, accumulate);
+  psf_reduce_kernel<<<grid_for(npix / 2 + 1, 128, 148 * 16), 128, 0, st>>>(npix, n_items, field, w, psf, accumulate);
   note_launch();
   return check_launch("psf_reduce");
 }
