@@ -1,6 +1,7 @@
 // extern "C" surface of libdlux_b200.so (see include/dlux_b200.h).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -81,7 +82,17 @@ static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
   return rc;
 }
 
-static const size_t kChunkBudget = (size_t)2 << 30;  // per-chunk intermediates, bytes
+// per-chunk intermediates, bytes (DLUX_B200_CHUNK_MB overrides; the tests use it to force
+// the multi-chunk paths at small sizes)
+static size_t chunk_budget() {
+  static const size_t v = [] {
+    const char* e = getenv("DLUX_B200_CHUNK_MB");
+    const long mb = e ? atol(e) : 0;
+    return mb > 0 ? (size_t)mb << 20 : (size_t)2 << 30;
+  }();
+  return v;
+}
+#define kChunkBudget chunk_budget()
 
 // largest chunk <= cmax that splits `n` items into equal-sized chunks (no small tail launch)
 static size_t balanced_chunk(size_t n, size_t cmax) {
@@ -401,7 +412,8 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
                      const float* phase, const float* wavenumber, const float* scale_out,
                      const float* norm, const float* weights, const float* delta_xy,
                      const void* field, const float* psf_bar, float* opd_bar, float* phase_bar,
-                     float* weights_bar, void* scratch, size_t scratch_bytes, void* cuda_stream) {
+                     float* weights_bar, float* delta_bar, void* scratch, size_t scratch_bytes,
+                     void* cuda_stream) {
   int rc = check_poly_desc(d);
   if (rc != DLUX_OK) return rc;
   if (!wavenumber || !scale_out || !weights || !field || !psf_bar || !scratch) return DLUX_ERR_ARG;
@@ -417,7 +429,8 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, false, st);
   if (rc) return rc;
   if (weights_bar && (rc = launch_zero(weights_bar, (size_t)items, st))) return rc;
-  const bool need_pupil_grad = opd_bar || phase_bar;
+  if (delta_bar && (rc = launch_zero(delta_bar, (size_t)items * 2, st))) return rc;
+  const bool need_pupil_grad = opd_bar || phase_bar || delta_bar;
   const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
@@ -443,9 +456,17 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     h.out_c64 = s.qbuf;
     rc = run_gemm(h, d->precision, st);
     if (rc) return rc;
-    rc = launch_grad_reduce((size_t)N * N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale,
-                            1.0f / (float)((long long)N * N), opd_bar, phase_bar, b0 > 0, st);
-    if (rc) return rc;
+    const float a0 = 1.0f / (float)((long long)N * N);
+    if (opd_bar || phase_bar) {
+      rc = launch_grad_reduce((size_t)N * N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
+                              opd_bar, phase_bar, b0 > 0, st);
+      if (rc) return rc;
+    }
+    if (delta_bar) {
+      rc = launch_pos_grad(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
+                           delta_bar + 2 * (size_t)b0, st);
+      if (rc) return rc;
+    }
   }
   return DLUX_OK;
 }

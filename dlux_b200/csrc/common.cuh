@@ -134,6 +134,9 @@ int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coe
 int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,
                         float* coeff_bar, cudaStream_t st);
 int launch_zero(float* p, size_t n, cudaStream_t st);
+// delta_bar[item][axis] = 2 pi sum_ij x_axis(i or j) * Im(conj(P_ij) Q_ij[item])  (source-offset VJP)
+int launch_pos_grad(int N, int n_items, const float2* q, const float* k, const float* T, const float* opd,
+                    const float* phase, const float* amp_scale, float a0, float* delta_bar, cudaStream_t st);
 // psf[i] (+)= sum_item w[item] |field[item][i]|^2
 int launch_psf_reduce(size_t npix, int n_items, const float2* field, const float* w, float* psf,
                       int accumulate, cudaStream_t st);

@@ -417,6 +417,62 @@ int launch_grad_reduce(size_t npix, int n_items, const float2* q, const float* k
   return check_launch("grad_reduce");
 }
 
+// VJP w.r.t. the source offset: the offset delta (fringes) shifts the output coordinates,
+// d(phasor)/d(delta_x) = 2 pi i x_j * phasor, hence dL/d(delta_x) = 2 pi sum_ij x_j g_ij with
+// the same g = Im(conj(P) Q) as the phase gradient (x = the MFT input coordinate
+// (j - (N-1)/2) / N; rows for the y offset).  This is how PointSources.position gets its
+// gradient (wavefronts.py:370-395 tilt, folded into the coordinates).
+__global__ void pos_grad_kernel(int N, const float2* __restrict__ q, const float* __restrict__ k,
+                                const float* __restrict__ T, const float* __restrict__ opd,
+                                const float* __restrict__ phase, const float* __restrict__ amp_scale,
+                                float a0, float* __restrict__ delta_bar) {
+  __shared__ float smx[8], smy[8];
+  const int item = blockIdx.y;
+  const size_t npix = (size_t)N * N;
+  const float amp = a0 * amp_scale[0];
+  const float kw = k[item];
+  const float half = 0.5f * (float)(N - 1), inv = 1.0f / (float)N;
+  float ax = 0.0f, ay = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float t = T ? T[i] : 1.0f;
+    if (t != 0.0f) {
+      const float2 v = q[(size_t)item * npix + i];
+      float sn, cs;
+      fast_sincos(__fmul_rn(kw, opd ? opd[i] : 0.0f) + (phase ? phase[i] : 0.0f), &sn, &cs);
+      const float g = amp * t * (cs * v.y - sn * v.x);
+      const int r = (int)(i / N), c = (int)(i - (size_t)r * N);
+      ax = fmaf(((float)c - half) * inv, g, ax);
+      ay = fmaf(((float)r - half) * inv, g, ay);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ax += __shfl_xor_sync(0xffffffffu, ax, o);
+    ay += __shfl_xor_sync(0xffffffffu, ay, o);
+  }
+  if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = ax; smy[threadIdx.x >> 5] = ay; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sx = 0.0f, sy = 0.0f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) { sx += smx[wv]; sy += smy[wv]; }
+    const float two_pi = 6.283185307179586f;
+    atomicAdd(delta_bar + 2 * item, two_pi * sx);
+    atomicAdd(delta_bar + 2 * item + 1, two_pi * sy);
+  }
+}
+
+int launch_pos_grad(int N, int n_items, const float2* q, const float* k, const float* T, const float* opd,
+                    const float* phase, const float* amp_scale, float a0, float* delta_bar, cudaStream_t st) {
+  for (int b0 = 0; b0 < n_items; b0 += 65535) {
+    const int nb = n_items - b0 < 65535 ? n_items - b0 : 65535;
+    dim3 grid(grid_for((size_t)N * N, 256, 32), nb);
+    pos_grad_kernel<<<grid, 256, 0, st>>>(N, q + (size_t)b0 * N * N, k + b0, T, opd, phase, amp_scale, a0,
+                                          delta_bar + 2 * (size_t)b0);
+    note_launch();
+  }
+  return check_launch("pos_grad");
+}
+
 int launch_zero(float* p, size_t n, cudaStream_t st) {
   if (n == 0) return DLUX_OK;
   zero_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n);

@@ -201,8 +201,8 @@ class _FocalSystem(LayeredOpticalSystem):
         weights_t = weights.to(dev, torch.float32) if torch.is_tensor(weights) else up(_np32(weights))
         weights_t = weights_t.reshape(offsets_t.shape[0], len(wavelengths))
         cont = lambda t: None if t is None else t.contiguous()
-        return ops.PolyPSFFunction.apply(cont(opd), cont(phase), weights_t.contiguous(), cont(T), up(k),
-                                         up(scale_out), up(norm), delta.contiguous(), self.wf_npixels,
+        return ops.PolyPSFFunction.apply(cont(opd), cont(phase), weights_t.contiguous(), delta.contiguous(),
+                                         cont(T), up(k), up(scale_out), up(norm), self.wf_npixels,
                                          npix, normalise, self.precision)
 
     def _propagate(self, wavelengths, offset, weights, return_wf):

@@ -148,8 +148,10 @@ DLUX_API int dlux_polypsf_fwd(const dlux_polypsf_desc* desc,
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
 /* VJP of dlux_polypsf_fwd w.r.t. opd (-> Zernike coefficients through
- * dlux_basis_reduce), phase and weights, given psf_bar = dL/dpsf and the saved field.
- * Stands in for jax.grad through the same lines (docs/phase_retrieval.md:269-287). */
+ * dlux_basis_reduce), phase, weights (-> flux, spectrum) and the source offsets delta_xy
+ * (-> PointSources.position through delta = theta * D / lambda), given psf_bar = dL/dpsf and
+ * the saved field.  Stands in for jax.grad through the same lines
+ * (docs/phase_retrieval.md:269-287). */
 DLUX_API int dlux_polypsf_bwd(const dlux_polypsf_desc* desc,
                      const float* transmission, const float* opd, const float* phase,
                      const float* wavenumber, const float* scale_out, const float* norm,
@@ -159,6 +161,7 @@ DLUX_API int dlux_polypsf_bwd(const dlux_polypsf_desc* desc,
                      float* opd_bar,           /* [N, N] or NULL */
                      float* phase_bar,         /* [N, N] or NULL */
                      float* weights_bar,       /* [S, L] or NULL */
+                     float* delta_bar,         /* [S, L, 2] or NULL */
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------

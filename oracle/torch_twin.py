@@ -38,7 +38,10 @@ def poly_psf(transmission, opd, wavelengths, weights, *, diameter, psf_npixels,
     wf0 = O.OracleWavefront(1.0, N, diameter, dtype)
     xs = wf0.xs
     X, Y = np.meshgrid(xs, xs)
-    tilt = _t(F(offset[0]) * X + F(offset[1]) * Y, rdt)
+    if torch.is_tensor(offset):      # differentiable source position
+        tilt = offset[0] * _t(X, rdt) + offset[1] * _t(Y, rdt)
+    else:
+        tilt = _t(F(offset[0]) * X + F(offset[1]) * Y, rdt)
     w = weights if torch.is_tensor(weights) else _t(weights, rdt)
     psf = 0.0
     for l, wl in enumerate(np.asarray(wavelengths, dtype=dtype)):

@@ -251,6 +251,74 @@ def test_phase_retrieval_gradient(dev, prec):
     assert rel_l2(wt.grad.cpu().numpy(), w_ref.grad.numpy()) < TOL
 
 
+@pytest.mark.parametrize("prec", PRECS)
+def test_point_sources_position_and_flux_gradients(dev, prec):
+    # PointSources.position / flux gradients (north_star: "PointSources position/flux sum")
+    import dlux_b200 as dl
+    from oracle import torch_twin
+    N, M, nz = 96, 48, 3
+    od = _optics_dict(N, M, nz, 6)
+    wls = np.linspace(0.95e-6, 1.05e-6, 3).astype(np.float32)
+    w = np.full(3, 1 / 3, np.float32)
+    pos0 = np.array([[1.5e-7, -2.0e-7], [-3.0e-7, 0.5e-7]], np.float32)
+    flux0 = np.array([2.0, 0.75], np.float32)
+    G = np.random.default_rng(31).standard_normal((M, M)).astype(np.float32)
+
+    pos = torch.as_tensor(pos0, device=dev).requires_grad_(True)
+    flux = torch.as_tensor(flux0, device=dev).requires_grad_(True)
+    sys_ = _system(od, dev, True, prec)
+    psf = sys_.model(dl.PointSources(wls, pos, flux))
+    (psf * torch.as_tensor(G, device=dev)).sum().backward()
+
+    pos_r = torch.tensor(pos0, dtype=torch.float64, requires_grad=True)
+    flux_r = torch.tensor(flux0, dtype=torch.float64, requires_grad=True)
+    tot = 0.0
+    for s in range(2):
+        tot = tot + torch_twin.poly_psf(od["transmission"], None, wls, torch.tensor(w, dtype=torch.float64) * flux_r[s],
+                                        diameter=1.0, psf_npixels=M, pixel_scale_rad=O.arcsec2rad(0.05),
+                                        offset=pos_r[s], basis=od["basis"], coefficients=od["coefficients"],
+                                        dtype=np.float64)
+    (tot * torch.tensor(G, dtype=torch.float64)).sum().backward()
+    assert rel_l2(psf.detach().cpu().numpy(), tot.detach().numpy()) < TOL
+    assert rel_l2(flux.grad.cpu().numpy(), flux_r.grad.numpy()) < TOL
+    assert rel_l2(pos.grad.cpu().numpy(), pos_r.grad.numpy()) < 5e-5   # position: float32 tilt scale 1e-7 rad
+
+
+def test_multi_chunk_paths(dev):
+    # force the item-chunk loops (DLUX_B200_CHUNK_MB is read once per process, so run a child)
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import numpy as np, torch, sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+        from test_gpu_parity import _optics_dict, _system
+        from oracle import mft_oracle as O
+        import dlux_b200 as dl
+        dev = torch.device('cuda:0')
+        od = _optics_dict(64, 32, 3, 7)
+        wls = np.linspace(0.9e-6, 1.1e-6, 5).astype(np.float32)
+        pos = np.array([[1e-7, -2e-7], [-3e-7, 0.5e-7], [0, 0]], np.float32)
+        flux = np.array([3.0, 0.25, 1.0], np.float32)
+        c = torch.as_tensor(od['coefficients'], device=dev).requires_grad_(True)
+        layer = dl.BasisOptic(od['basis'], od['transmission'], c, 'opd', normalise=True, device=dev)
+        s = dl.AngularOpticalSystem(64, 1.0, [('a', layer)], 32, 0.05, device=dev)
+        psf = s.model(dl.PointSources(wls, pos, flux))
+        psf.sum().backward()
+        ref = O.point_sources_model(od, wls, pos, flux)
+        err = np.linalg.norm(psf.detach().cpu().numpy() - ref) / np.linalg.norm(ref)
+        x = torch.as_tensor((np.random.default_rng(0).standard_normal((7, 64, 64)) + 0j).astype(np.complex64), device=dev)
+        out = dl.utils.MFT(x, np.full(7, 1e-6, np.float32), np.float32(1 / 64), 32, np.float32(2e-7))
+        e2 = max(np.linalg.norm(out[i].cpu().numpy() - O.MFT(x[i].cpu().numpy(), 1e-6, 1 / 64, 32, 2e-7)) /
+                 np.linalg.norm(out[i].cpu().numpy()) for i in range(7))
+        print('ERR', err, e2, float(c.grad.abs().sum()))
+        assert err < 1e-5 and e2 < 1e-5
+    """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+           os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    env = dict(os.environ, DLUX_B200_CHUNK_MB="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ERR" in r.stdout
+
+
 # ------------------------------------------------------------------ full-size properties (C3)
 @pytest.mark.parametrize("prec", ["3xtf32"])
 def test_c3_size_properties(dev, prec):
