@@ -5,15 +5,15 @@ propagator layer, ``Wavefront.propagate`` and ``OpticalSystem.propagate/model``.
 Importing the package does not need a GPU; calling any operator does, and there is no
 CPU fallback (the native library is loaded lazily and its absence is an error)."""
 from . import utils
-from .layers import (AberratedLayer, BasisLayer, BasisOptic, MFT, Normalise, Optic, OpticalLayer,
+from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, MFT, Normalise, Optic, OpticalLayer,
                      Tilt, TransmissiveLayer)
 from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, CartesianOpticalSystem,
                               LayeredOpticalSystem)
 from .sources import PointSource, PointSources
-from .wavefronts import Wavefront
+from .wavefronts import CoordSpec, Wavefront
 
 __version__ = "0.1.0"
 __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer",
-           "Tilt", "Normalise", "Optic", "BasisOptic", "MFT", "BaseOpticalSystem",
+           "Tilt", "Normalise", "Optic", "BasisOptic", "MFT", "FFT", "CoordSpec", "BaseOpticalSystem",
            "LayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
            "PointSources"]

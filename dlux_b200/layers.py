@@ -8,10 +8,10 @@ import numpy as np
 import torch
 
 from .utils import propagation as _prop
-from .wavefronts import Wavefront
+from .wavefronts import CoordSpec, Wavefront
 
 __all__ = ["OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer", "Tilt", "Normalise",
-           "Optic", "BasisOptic", "MFT"]
+           "Optic", "BasisOptic", "MFT", "FFT"]
 
 
 def _arr(x, device=None):
@@ -140,3 +140,21 @@ class MFT(OpticalLayer):
 
     def __call__(self, wavefront):                     # layers/propagators.py:198-217
         return wavefront.propagate(self.npixels, self.pixel_scale, self.focal_length, self.inverse)
+
+
+class FFT(OpticalLayer):
+    """layers/propagators.py:57-142: padded FFT propagation followed by a centre crop."""
+
+    def __init__(self, focal_length=None, inverse: bool = False, pad: int = 1, crop: int = 1,
+                 center: bool = True):
+        self.focal_length = None if focal_length is None else np.float32(focal_length)
+        self.inverse = bool(inverse)
+        self.pad = int(pad)
+        self.crop = int(crop)
+        self.center = bool(center)
+
+    def __call__(self, wavefront):                     # layers/propagators.py:118-142
+        spec = CoordSpec(c=0.0) if self.center else None
+        size_out = wavefront.npixels * self.pad // self.crop
+        return wavefront.propagate_FFT(pad=self.pad, focal_length=self.focal_length, inverse=self.inverse,
+                                       spec_out=spec).resize(size_out)

@@ -1,5 +1,7 @@
 """Mirror of the slice of ``dLux.utils`` that sits on the diffraction hot path."""
 from . import propagation
-from .propagation import MFT, calc_nfringes, mft_geometry, arcsec2rad, eval_basis
+from .propagation import (MFT, FFT, calc_nfringes, mft_geometry, arcsec2rad, eval_basis, fft_spec,
+                          fft_phase_ramp)
 
-__all__ = ["propagation", "MFT", "calc_nfringes", "mft_geometry", "arcsec2rad", "eval_basis"]
+__all__ = ["propagation", "MFT", "FFT", "calc_nfringes", "mft_geometry", "arcsec2rad", "eval_basis",
+           "fft_spec", "fft_phase_ramp"]

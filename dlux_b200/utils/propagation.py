@@ -16,7 +16,8 @@ import torch
 
 from .. import ops
 
-__all__ = ["MFT", "calc_nfringes", "mft_geometry", "arcsec2rad", "eval_basis"]
+__all__ = ["MFT", "FFT", "calc_nfringes", "mft_geometry", "arcsec2rad", "eval_basis", "fft_spec",
+           "fft_phase_ramp"]
 
 _ARCSEC = math.pi / (180.0 * 3600.0)   # dLux/utils/units.py _BASE_TO_RAD["arcsec"]
 
@@ -118,6 +119,61 @@ def MFT(phasor, wavelength, pixel_scale_in, npixels_out, pixel_scale_out, focal_
     norm = _to_dev(norm, dev)
     return ops.MFTFunction.apply(phasor, scale_out, npixels_out, shift, None, norm, bool(inverse),
                                  precision)
+
+
+def FFT(phasor, wavelength, pixel_scale, focal_length=None, pad: int = 2, inverse: bool = False,
+        precision=None):
+    """Drop-in for ``dlu.FFT`` (propagation.py:8-64): zero-pad by ``(N*(pad-1))//2`` per side,
+    ``fftshift(fft2(ifftshift(.)))/N_pad`` (inverse: ``ifft2 * N_pad``).  Returns
+    ``(phasor, new_pixel_scale)``.
+
+    The padded, centred DFT is evaluated by the same phasor-GEMM kernels as the MFT (SURVEY 8f
+    NEXT-2): with N_pad output samples it is exactly an MFT at ``scale_out = N / N_pad`` whose
+    input / output index origins sit at ``N_pad//2 - npad`` and ``N_pad//2`` (numpy's
+    fftshift convention) and whose normalisation is ``1 / N_pad``.  This costs O(N^2 N_pad)
+    instead of O(N_pad^2 log N_pad) but runs on the tensor cores and shares the adjoint."""
+    if not torch.is_tensor(phasor):
+        raise TypeError("phasor must be a torch CUDA tensor")
+    n = phasor.shape[-1]
+    pad = int(pad)
+    wl, ps, fl = _coerce(wavelength, pixel_scale, focal_length)
+    fringe_size = wl / (ps * np.float32(n))
+    new_pixel_scale = fringe_size / np.float32(pad)
+    if fl is not None:
+        new_pixel_scale = new_pixel_scale * fl
+    npad = (n * (pad - 1)) // 2
+    n_out = n + 2 * npad
+    s = np.float32(n) / np.float32(n_out)
+    sh_in = np.float32(n_out // 2 - npad - (n - 1) / 2)        # input origin: padded index N_pad//2
+    sh_out = np.float32(n_out // 2 - (n_out - 1) / 2)          # output origin: index N_pad//2
+    dev = phasor.device
+    batch = int(np.prod(phasor.shape[:-2])) if phasor.dim() > 2 else 1
+    f = lambda v, w: torch.full((batch, w), float(v), dtype=torch.float32, device=dev)
+    out = ops.MFTFunction.apply(phasor, f(s, 1).reshape(batch), n_out, f(sh_in, 2),
+                                f((sh_out - sh_in) * s, 2), f(np.float32(1.0) / np.float32(n_out), 1),
+                                bool(inverse), precision)
+    return out, new_pixel_scale
+
+
+def fft_spec(npixels_in, pixel_scale_in, wavelength, focal_length=None):
+    """dLux.utils.fourier.fft_spec (utils/fourier.py:14-45): FFT output pixel scale and centre."""
+    wl, ps, fl = _coerce(wavelength, pixel_scale_in, focal_length)
+    d_out = wl / (np.float32(npixels_in) * ps)
+    if fl is not None:
+        d_out = d_out * fl
+    if npixels_in % 2 != 0:
+        return d_out, np.float32(0.0)
+    return d_out, np.float32(-0.5) * d_out
+
+
+def fft_phase_ramp(xs, wavelength, shift, focal_length=None, inverse=False):
+    """dLux.utils.fourier.fft_phase_ramp (utils/fourier.py:48-78), torch tensors."""
+    sign = -1.0 if inverse else 1.0
+    to_t = lambda v: v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v, dtype=np.float32), device=xs.device)
+    alpha = to_t(wavelength) if focal_length is None else to_t(wavelength) * to_t(focal_length)
+    ang = (np.float32(sign * 2 * math.pi) * xs * to_t(shift) / alpha).to(torch.float32)
+    ramp = torch.polar(torch.ones_like(ang), ang)
+    return ramp[None, :] * ramp[:, None]
 
 
 def eval_basis(basis, coefficients):

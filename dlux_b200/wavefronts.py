@@ -12,7 +12,28 @@ import torch
 
 from .utils import propagation as _prop
 
-__all__ = ["Wavefront"]
+__all__ = ["Wavefront", "CoordSpec"]
+
+
+class CoordSpec:
+    """Minimal mirror of ``dLux.coordinates.CoordSpec`` (coordinates.py:74-157): n pixels of
+    size d centred on c."""
+
+    def __init__(self, n=None, d=None, c=0.0):
+        self.n, self.d, self.c = n, d, c
+
+    def set(self, **kw):
+        new = copy.copy(self)
+        for k, v in kw.items():
+            setattr(new, k, v)
+        return new
+
+    def xs(self, device):
+        if self.d is None:
+            raise ValueError("d must be specified to calculate coordinates.")
+        idx = torch.arange(self.n, dtype=torch.float32, device=device)
+        to_t = lambda v: v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v, dtype=np.float32), device=device)
+        return to_t(self.c) + (idx - np.float32((self.n - 1) / 2)) * to_t(self.d)
 
 
 class Wavefront:
@@ -140,7 +161,49 @@ class Wavefront:
         """wavefronts.py:774-805; ``spec_out`` needs attributes ``n`` and ``d``."""
         return self.propagate(spec_out.n, spec_out.d, focal_length, bool(inverse), precision)
 
-    def propagate_FFT(self, *a, **k):
-        raise NotImplementedError(
-            "FFT propagation is the NEXT-2 row of the scope table (SURVEY.md 8f); "
-            "only the MFT path is implemented")
+    def propagate_FFT(self, pad: int = 2, focal_length=None, inverse: bool = False, spec_out=None,
+                      precision=None):
+        """wavefronts.py:654-727 -> dlu.FFT, with the optional input/output phase ramps that
+        re-centre the FFT grid on ``spec_out.c``."""
+        wl = self.wavelength
+        n_out = self.npixels * pad
+        d_fft, c_fft = _prop.fft_spec(n_out, self.pixel_scale, wl, focal_length)
+        in_ramp = out_ramp = None
+        if spec_out is not None:
+            if spec_out.d is not None:
+                raise ValueError("Output spec cannot specify d; FFT output d is fixed.")
+            if spec_out.n is not None:
+                raise ValueError("Output spec cannot specify n; FFT output n is determined by the "
+                                 "pad parameter.")
+            dev = self.phasor.device
+            to_t = lambda v: v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v, dtype=np.float32), device=dev)
+            shift = to_t(c_fft) - to_t(spec_out.c)
+            in_ramp = _prop.fft_phase_ramp(self.xs, wl, shift, focal_length, inverse)
+            spec_out = spec_out.set(n=n_out, d=d_fft)
+            shift = _prop.fft_spec(spec_out.n, spec_out.d, wl, focal_length)[1]
+            out_ramp = _prop.fft_phase_ramp(spec_out.xs(dev), wl, shift, focal_length, inverse)
+            center = to_t(spec_out.c).reshape(1)
+        else:
+            center = torch.as_tensor(np.asarray(c_fft.detach().cpu() if torch.is_tensor(c_fft) else c_fft,
+                                                dtype=np.float32), device=self.phasor.device).reshape(1)
+        phasor = self.phasor if in_ramp is None else self.phasor * in_ramp
+        phasor, pixel_scale = _prop.FFT(phasor, wl, self.pixel_scale, focal_length, pad, inverse, precision)
+        if out_ramp is not None:
+            phasor = phasor * out_ramp
+        ps = pixel_scale if torch.is_tensor(pixel_scale) else torch.as_tensor(
+            np.asarray(pixel_scale, dtype=np.float32), device=phasor.device)
+        return self.set(phasor=phasor, pixel_scale=ps, center=center)
+
+    def resize(self, npixels: int):
+        """wavefronts.py:562-582 -> dlu.resize: centre-preserving crop / zero pad."""
+        n_in = self.npixels
+        if npixels == n_in:
+            return self
+        if n_in % 2 != npixels % 2:
+            raise ValueError("Center-preserving resizing requires parity consistency, i.e. even -> even "
+                             f"or odd -> odd: {n_in} -> {npixels}.")
+        if npixels < n_in:
+            a, b = (n_in - npixels) // 2, (n_in + npixels) // 2
+            return self.set(phasor=self.phasor[..., a:b, a:b])
+        p = (npixels - n_in) // 2
+        return self.set(phasor=torch.nn.functional.pad(self.phasor, (p, p, p, p)))

@@ -346,6 +346,47 @@ def test_c3_size_properties(dev, prec):
     assert rel_l2(out.cpu().numpy(), O.MFT(x[0].cpu().numpy(), 4.3e-6, ps_in, M, pso)) < TOL
 
 
+# ------------------------------------------------------------------ FFT (SURVEY 8f NEXT-2)
+@pytest.mark.parametrize("prec", PRECS)
+def test_fft_golden_reference_vectors(dev, golden, prec):
+    import dlux_b200 as dl
+    for j in range(int(golden["n_fft"])):
+        pad, inverse, ps = golden[f"fft_{j}_meta"]
+        ph = torch.as_tensor(golden[f"fft_{j}_in"], device=dev)
+        out, gps = dl.utils.FFT(ph, np.float32(1.0e-6), np.float32(0.01), None, int(pad), bool(inverse),
+                                precision=prec)
+        ref = golden[f"fft_{j}_out"]
+        assert tuple(out.shape) == ref.shape
+        assert rel_l2(out.cpu().numpy(), ref) < TOL, (j, rel_l2(out.cpu().numpy(), ref))
+        assert abs(float(gps) - ps) <= 1e-6 * abs(ps)
+
+
+def test_fft_roundtrip_and_layer(dev):
+    # /root/reference/tests/utils/test_propagation.py:74-92 and tests/layers/test_propagators.py:48-63
+    import dlux_b200 as dl
+    ph = torch.ones((32, 32), dtype=torch.complex64, device=dev)
+    f, _ = dl.utils.FFT(ph, 1.0, 0.1, 2.0, pad=1)
+    b, _ = dl.utils.FFT(f, 1.0, 0.1, 2.0, pad=1, inverse=True)
+    assert torch.allclose(b, ph, rtol=1e-5, atol=1e-5)
+    # odd sizes and padding follow numpy's fftshift conventions
+    rng = np.random.default_rng(12)
+    for n, pad in ((31, 2), (32, 3), (15, 3)):
+        x = _rand_c64(rng, n, n)
+        out, _ = dl.utils.FFT(torch.as_tensor(x, device=dev), 1e-6, 0.01, None, pad)
+        ref, _ = O.FFT(x, 1e-6, 0.01, None, pad)
+        assert rel_l2(out.cpu().numpy(), ref) < TOL, (n, pad)
+    wf = dl.Wavefront(1e-6, 16, diameter=1.0, device=dev)
+    out = dl.FFT(pad=2, crop=2, center=False)(wf)
+    assert isinstance(out, dl.Wavefront) and out.phasor.shape == (16, 16)
+    cen = dl.FFT(pad=2, center=True)(wf)
+    assert cen.phasor.shape == (32, 32)
+    # re-centring only applies phase ramps: a centred FFT has the intensity of the centred MFT
+    mft = wf.propagate(32, float(cen.pixel_scale))
+    assert rel_l2(cen.psf.cpu().numpy(), mft.psf.cpu().numpy()) < 1e-4
+    with pytest.raises(ValueError, match="cannot specify d"):
+        wf.propagate_FFT(spec_out=dl.CoordSpec(d=1.0))
+
+
 # ------------------------------------------------------------------ API behaviour
 def test_api_errors_and_shapes(dev):
     import dlux_b200 as dl
