@@ -246,6 +246,23 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
   }
 }
 
+// Where the TMEM partial accumulators of the two tiles open and close along the k-chunks of
+// a unit.  Tile a: [0,4) [4,8) ...; tile b: [0,2) [2,6) [6,10) ... (staggered by half a
+// partial).  Both close at the last chunk.  Acquisition order inside a chunk: a, then b.
+struct PartialSchedule {
+  bool a_open, a_close, b_open, b_close;
+};
+__device__ __forceinline__ PartialSchedule partial_schedule(int kc, int k_chunks) {
+  PartialSchedule ps;
+  const int r = kc % FLUSH_CHUNKS;
+  const bool last = kc == k_chunks - 1;
+  ps.a_open = r == 0;
+  ps.a_close = (r == FLUSH_CHUNKS - 1) || last;
+  ps.b_open = (kc == 0) || (r == FLUSH_CHUNKS / 2);
+  ps.b_close = (r == FLUSH_CHUNKS / 2 - 1) || last;
+  return ps;
+}
+
 struct TcParams {
   GemmParams g;
   int tiles_mp, tiles_n, n_units, k_chunks;  // tiles_mp: pairs of 128-row data tiles
@@ -344,49 +361,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       // The whole warp walks the loop (uniform control flow); one elected lane issues.
       int sa = 0, sg = 0;
       uint32_t pa = 0, pg = 0;
-      uint32_t seq = 0;  // partial sequence number: tile a uses seq, tile b seq + 1; buffer = seq % 3
+      uint32_t take = 0;         // running count of partial-accumulator acquisitions; buffer = take % 3
+      uint32_t ta = 0, tb = 0;   // acquisition numbers of the open partials of tiles a and b
       for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
-          const int in_partial = kc % FLUSH_CHUNKS;
-          const uint32_t buf_a = seq % NUM_ACC, buf_b = (seq + 1) % NUM_ACC;
-          const bool close_partial = (in_partial == FLUSH_CHUNKS - 1) || (kc == tp.k_chunks - 1);
+          // Partials are FLUSH_CHUNKS long; tile b's boundaries are staggered by half a partial so
+          // that the three TMEM buffers are re-acquired >= 2 chunks after they were handed to a
+          // drain warpgroup (see partial_schedule()).
+          const PartialSchedule ps = partial_schedule(kc, tp.k_chunks);
           mbar_wait(fullG_bar(sg), pg);
           mbar_wait(fullA_bar(sa), pa);
-          if (in_partial == 0) mbar_wait(tempty_bar(buf_a), ((seq / NUM_ACC) & 1) ^ 1);
+          if (ps.a_open) {
+            ta = take++;
+            mbar_wait(tempty_bar(ta % NUM_ACC), ((ta / NUM_ACC) & 1) ^ 1);
+          }
           tc_fence_after();
           const uint32_t g0 = tmem_base + (uint32_t)(G_BASE_COL + sg * G_COLS);
           constexpr uint64_t PL = PLANE_BYTES >> 4;   // descriptor step per plane
           constexpr uint64_t KS = (UMMA_K * 4) >> 4;  // ... per k-step inside the swizzle row
           if (elect_one()) {
-            const uint32_t d = tmem_base + buf_a * ACC_COLS;
+            const uint32_t d = tmem_base + (ta % NUM_ACC) * ACC_COLS;
             const uint64_t b_rh = make_desc_sw64(smem_base + sa * A_BYTES);
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ++ks) {
               const uint64_t d_rh = b_rh + ks * KS, d_rl = d_rh + PL, d_ih = d_rh + 2 * PL, d_il = d_rh + 3 * PL;
               const uint32_t g1h = g0 + ks * UMMA_K, g1l = g1h + BK, g2h = g1h + 2 * BK, g2l = g1h + 3 * BK;
               // (Re | Im rows) += G1 * Re(Data)^T + G2 * Im(Data)^T; small terms first
-              umma_tf32_ts(d, g1l, d_rh, IDESC, (in_partial | ks) ? 1u : 0u);
+              umma_tf32_ts(d, g1l, d_rh, IDESC, (ps.a_open && ks == 0) ? 0u : 1u);
               umma_tf32_ts(d, g1h, d_rl, IDESC, 1u);
               umma_tf32_ts(d, g2l, d_ih, IDESC, 1u);
               umma_tf32_ts(d, g2h, d_il, IDESC, 1u);
               umma_tf32_ts(d, g1h, d_rh, IDESC, 1u);
               umma_tf32_ts(d, g2h, d_ih, IDESC, 1u);
             }
-            if (close_partial) umma_commit(tfull_bar(buf_a));  // tile a's partial complete -> WG0
+            if (ps.a_close) umma_commit(tfull_bar(ta % NUM_ACC));  // tile a's partial complete -> WG0
           }
           __syncwarp();
-          if (in_partial == 0) {
-            mbar_wait(tempty_bar(buf_b), (((seq + 1) / NUM_ACC) & 1) ^ 1);
+          if (ps.b_open) {
+            tb = take++;
+            mbar_wait(tempty_bar(tb % NUM_ACC), ((tb / NUM_ACC) & 1) ^ 1);
             tc_fence_after();
           }
           if (elect_one()) {
-            const uint32_t d = tmem_base + buf_b * ACC_COLS;
+            const uint32_t d = tmem_base + (tb % NUM_ACC) * ACC_COLS;
             const uint64_t b_rh = make_desc_sw64(smem_base + sa * A_BYTES + TILE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ++ks) {
               const uint64_t d_rh = b_rh + ks * KS, d_rl = d_rh + PL, d_ih = d_rh + 2 * PL, d_il = d_rh + 3 * PL;
               const uint32_t g1h = g0 + ks * UMMA_K, g1l = g1h + BK, g2h = g1h + 2 * BK, g2l = g1h + 3 * BK;
-              umma_tf32_ts(d, g1l, d_rh, IDESC, (in_partial | ks) ? 1u : 0u);
+              umma_tf32_ts(d, g1l, d_rh, IDESC, (ps.b_open && ks == 0) ? 0u : 1u);
               umma_tf32_ts(d, g1h, d_rl, IDESC, 1u);
               umma_tf32_ts(d, g2l, d_ih, IDESC, 1u);
               umma_tf32_ts(d, g2h, d_il, IDESC, 1u);
@@ -395,10 +418,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             }
             umma_commit(emptyA_bar(sa));  // free the smem slot and the phasor stage when these MMAs retire
             umma_commit(emptyG_bar(sg));
-            if (close_partial) umma_commit(tfull_bar(buf_b));  // tile b's partial complete -> WG1
+            if (ps.b_close) umma_commit(tfull_bar(tb % NUM_ACC));  // tile b's partial complete -> WG1
           }
           __syncwarp();
-          if (close_partial) seq += 2;
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
           if (++sg == G_STAGES) { sg = 0; pg ^= 1; }
         }
@@ -409,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int which = warp >> 2;     // 0: tile a, 1: tile b
-    uint32_t seq = (uint32_t)which;  // my partials are seq, seq + 2, ...
+    uint32_t take = 0, ta = 0, tb = 0;  // mirrors the MMA issuer's acquisition counter
     float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256 + warp * STG_BYTES);
     for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
       const int item = unit / units_per_item;
@@ -419,9 +441,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       float tot[BM];
 #pragma unroll
       for (int j = 0; j < BM; ++j) tot[j] = 0.0f;
-      for (int part = 0; part < n_partials; ++part) {
-        const uint32_t buf = seq % NUM_ACC;
-        mbar_wait(tfull_bar(buf), (seq / NUM_ACC) & 1);
+      for (int kc = 0; kc < tp.k_chunks; ++kc) {
+        const PartialSchedule ps = partial_schedule(kc, tp.k_chunks);
+        if (ps.a_open) ta = take++;
+        if (ps.b_open) tb = take++;
+        if (!(which ? ps.b_close : ps.a_close)) continue;
+        const uint32_t mine = which ? tb : ta;
+        const uint32_t buf = mine % NUM_ACC;
+        mbar_wait(tfull_bar(buf), (mine / NUM_ACC) & 1);
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
 #pragma unroll
@@ -438,7 +465,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
-        seq += 2;
       }
 #ifdef DLUX_DEBUG_NOEPI
       if (m0 < p.rows && tot[5] == 123.456f) tile_epilogue(p, item, nq0, m0, lane, tot, stg);
