@@ -1,4 +1,5 @@
 // extern "C" surface of libdlux_b200.so (see include/dlux_b200.h).
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -61,6 +62,31 @@ static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static std::atomic<int> g_prof_on{0};
 
+// one split complex matrix stack of `count` rows x cols elements
+static PlaneSet take_planes(Bump& b, size_t n_rows, int cols) {
+  PlaneSet ps;
+  for (int i = 0; i < 2; ++i) ps.hi[i] = b.take<float>(n_rows * pitch4(cols));
+  for (int i = 0; i < 4; ++i) ps.b[i] = b.take<__nv_bfloat16>(n_rows * pitch8(cols));
+  return ps;
+}
+static size_t plane_bytes(size_t n_rows, int cols) {
+  return n_rows * (8 * (size_t)pitch4(cols) + 8 * (size_t)pitch8(cols));
+}
+// the stage-1 output of the forward ([M][N]) and of the adjoint ([N][M]) share one buffer,
+// sized for the larger, and are indexed with their own pitches
+static PlaneSet take_mid_planes(Bump& b, size_t c, int N, int M) {
+  PlaneSet ps;
+  const size_t f4 = std::max((size_t)M * pitch4(N), (size_t)N * pitch4(M));
+  const size_t f8 = std::max((size_t)M * pitch8(N), (size_t)N * pitch8(M));
+  for (int i = 0; i < 2; ++i) ps.hi[i] = b.take<float>(c * f4);
+  for (int i = 0; i < 4; ++i) ps.b[i] = b.take<__nv_bfloat16>(c * f8);
+  return ps;
+}
+static size_t mid_bytes(int N, int M) {
+  return 8 * std::max((size_t)M * pitch4(N), (size_t)N * pitch4(M)) +
+         8 * std::max((size_t)M * pitch8(N), (size_t)N * pitch8(M));
+}
+
 static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
   ProfRec r{};
   const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
@@ -102,21 +128,16 @@ static size_t balanced_chunk(size_t n, size_t cmax) {
   return (n + parts - 1) / parts;
 }
 
-// intermediate planes hold [M][pitch(N)] (forward) or [N][pitch(M)] (adjoint)
-static size_t mid_elems(int N, int M) {
-  const size_t a = (size_t)M * pitch4(N), b = (size_t)N * pitch4(M);
-  return a > b ? a : b;
-}
-
 static int mft_chunk(const dlux_mft_desc* d) {
   const size_t n_src = d->adjoint ? d->n_out : d->n_in;
-  const size_t per_item = 16 * n_src * pitch4((int)n_src) + 16 * mid_elems(d->n_in, d->n_out) +
-                          8 * (size_t)(d->n_in + d->n_out);
+  const size_t per_item = plane_bytes(n_src, (int)n_src) + mid_bytes(d->n_in, d->n_out) +
+                          8 * (size_t)(d->n_in + d->n_out) + 8192;
   return (int)balanced_chunk((size_t)d->batch, kChunkBudget / per_item);
 }
 
 struct MftScratch {
-  float *xin, *uout, *in_pl[4], *mid_pl[4];
+  float *xin, *uout;
+  PlaneSet in_pl, mid_pl;
 };
 
 static size_t carve_mft(const dlux_mft_desc* d, void* scratch, size_t cap, MftScratch* s, bool* ok) {
@@ -125,8 +146,8 @@ static size_t carve_mft(const dlux_mft_desc* d, void* scratch, size_t cap, MftSc
   const size_t n_src = d->adjoint ? d->n_out : d->n_in;
   s->xin = b.take<float>(c * 2 * d->n_in);
   s->uout = b.take<float>(c * 2 * d->n_out);
-  for (int i = 0; i < 4; ++i) s->in_pl[i] = b.take<float>(c * n_src * pitch4((int)n_src));
-  for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * mid_elems(d->n_in, d->n_out));
+  s->in_pl = take_planes(b, c * n_src, (int)n_src);
+  s->mid_pl = take_mid_planes(b, c, d->n_in, d->n_out);
   b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
   if (ok) *ok = b.ok;
   return b.used();
@@ -167,8 +188,6 @@ static void fill_stage(GemmParams& g, bool adjoint, int stage, int N, int M, int
     g.nvec = xin + (size_t)axis * N;
     g.nvec_stride = 2 * N;
   }
-  g.a_pitch = pitch4(g.K);
-  g.out_pitch = pitch4(g.rows);  // EPI_PLANES output is the next stage's data: its K is this stage's rows
 }
 
 }  // namespace dlux
@@ -260,19 +279,23 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
     rc = launch_coords(N, M, c, scale_out + b0, shift_xy ? shift_xy + 2 * (size_t)b0 : nullptr,
                        delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr, 1, s.xin, s.uout, st);
     if (rc) return rc;
+    const int exact = d->precision == DLUX_PREC_FP32;
     rc = launch_split_c64((const float2*)in + (size_t)b0 * n_src * n_src, (size_t)c * n_src, (int)n_src,
-                          s.in_pl[0], s.in_pl[1], s.in_pl[2], s.in_pl[3], st);
+                          s.in_pl, exact, st);
     if (rc) return rc;
     GemmParams g{};
     fill_stage(g, adj, 0, N, M, c, s.xin, s.uout, sign2pi);
-    for (int i = 0; i < 4; ++i) { g.a_planes[i] = s.in_pl[i]; g.out_planes[i] = s.mid_pl[i]; }
+    g.a = s.in_pl;
+    g.out = s.mid_pl;
+    g.exact = exact;
     g.mode = EPI_PLANES;
     g.scale = nullptr;
     rc = run_gemm(g, d->precision, st);
     if (rc) return rc;
     GemmParams h{};
     fill_stage(h, adj, 1, N, M, c, s.xin, s.uout, sign2pi);
-    for (int i = 0; i < 4; ++i) h.a_planes[i] = s.mid_pl[i];
+    h.a = s.mid_pl;
+    h.exact = exact;
     h.mode = EPI_C64;
     h.scale = norm ? norm + b0 : nullptr;
     h.out_c64 = (float2*)out + (size_t)b0 * n_dst * n_dst;
@@ -285,12 +308,12 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
 // ------------------------------------------------------------------ fused poly-PSF
 struct PolyScratch {
   float* amp_scale;  // 16 B + 256 doubles
-  float* p_pl[4];    // [L][N][N]
+  PlaneSet p_pl;     // [L][N][N]
   int* item_l;
   float *s_item, *norm_item, *k_item;
   float *xin, *uout;  // per chunk
-  float* mid_pl[4];   // per chunk [c][M*N]
-  float* ebar_pl[4];  // per chunk [c][M*M]  (bwd only; sized always for simplicity)
+  PlaneSet mid_pl;    // per chunk [c][M*N]
+  PlaneSet ebar_pl;   // per chunk [c][M*M]  (bwd only; sized always for simplicity)
   float2* qbuf;       // per chunk [c][N*N]: adjoint field Q per item (bwd)
   float2* fbuf;       // per chunk [c][M*M]: field, when the caller does not keep it (fwd)
   int chunk;
@@ -298,8 +321,8 @@ struct PolyScratch {
 
 static int poly_chunk(const dlux_polypsf_desc* d) {
   const size_t N = d->n_pupil, M = d->n_psf;
-  const size_t per_item = 16 * mid_elems((int)N, (int)M) + 16 * M * pitch4((int)M) + 8 * (N + M) +
-                          8 * N * N + 8 * M * M;
+  const size_t per_item = mid_bytes((int)N, (int)M) + plane_bytes(M, (int)M) + 8 * (N + M) +
+                          8 * N * N + 8 * M * M + 16384;
   const size_t items = (size_t)d->n_sources * d->n_wavels;
   return (int)balanced_chunk(items, kChunkBudget / per_item);
 }
@@ -311,15 +334,15 @@ static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, 
   const size_t c = poly_chunk(d);
   s->chunk = (int)c;
   s->amp_scale = b.take<float>(4 + 512);
-  for (int i = 0; i < 4; ++i) s->p_pl[i] = b.take<float>(L * N * pitch4((int)N));
+  s->p_pl = take_planes(b, L * N, (int)N);
   s->item_l = b.take<int>(items);
   s->s_item = b.take<float>(items);
   s->norm_item = b.take<float>(items);
   s->k_item = b.take<float>(items);
   s->xin = b.take<float>(c * 2 * N);
   s->uout = b.take<float>(c * 2 * M);
-  for (int i = 0; i < 4; ++i) s->mid_pl[i] = b.take<float>(c * mid_elems((int)N, (int)M));
-  for (int i = 0; i < 4; ++i) s->ebar_pl[i] = b.take<float>(c * M * pitch4((int)M));
+  s->mid_pl = take_mid_planes(b, c, (int)N, (int)M);
+  s->ebar_pl = take_planes(b, c * M, (int)M);
   s->qbuf = b.take<float2>(c * N * N);
   s->fbuf = b.take<float2>(c * M * M);
   b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
@@ -351,8 +374,8 @@ static int poly_prologue(const dlux_polypsf_desc* d, const PolyScratch& s, const
   int rc = launch_power(N, T, d->normalise, s.amp_scale, st);
   if (rc) return rc;
   if (need_planes) {
-    rc = launch_pupil(N, L, T, opd, phase, wavenumber, s.amp_scale, s.p_pl[0], s.p_pl[1], s.p_pl[2],
-                      s.p_pl[3], st);
+    rc = launch_pupil(N, L, T, opd, phase, wavenumber, s.amp_scale, s.p_pl,
+                      d->precision == DLUX_PREC_FP32, st);
     if (rc) return rc;
   }
   expand_items_kernel<<<(items + 255) / 256 > 1024 ? 1024 : (items + 255) / 256, 256, 0, st>>>(
@@ -380,6 +403,7 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
   rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, true, st);
   if (rc) return rc;
   const float sign2pi = (float)(-2.0 * 3.14159265358979323846);
+  const int exact = d->precision == DLUX_PREC_FP32;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
     rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
@@ -389,13 +413,16 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
     fill_stage(g, false, 0, N, M, c, s.xin, s.uout, sign2pi);
     g.item_data = s.item_l + b0;
     g.n_data = L;
-    for (int i = 0; i < 4; ++i) { g.a_planes[i] = s.p_pl[i]; g.out_planes[i] = s.mid_pl[i]; }
+    g.a = s.p_pl;
+    g.out = s.mid_pl;
+    g.exact = exact;
     g.mode = EPI_PLANES;
     rc = run_gemm(g, d->precision, st);
     if (rc) return rc;
     GemmParams h{};
     fill_stage(h, false, 1, N, M, c, s.xin, s.uout, sign2pi);
-    for (int i = 0; i < 4; ++i) h.a_planes[i] = s.mid_pl[i];
+    h.a = s.mid_pl;
+    h.exact = exact;
     h.mode = EPI_C64;
     h.scale = s.norm_item + b0;
     h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * M * M : s.fbuf;
@@ -432,11 +459,11 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   if (delta_bar && (rc = launch_zero(delta_bar, (size_t)items * 2, st))) return rc;
   const bool need_pupil_grad = opd_bar || phase_bar || delta_bar;
   const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
+  const int exact = d->precision == DLUX_PREC_FP32;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
     rc = launch_cotangent(M, c, (const float2*)field + (size_t)b0 * M * M, psf_bar, weights + b0,
-                          s.ebar_pl[0], s.ebar_pl[1], s.ebar_pl[2], s.ebar_pl[3],
-                          weights_bar ? weights_bar + b0 : nullptr, st);
+                          s.ebar_pl, exact, weights_bar ? weights_bar + b0 : nullptr, st);
     if (rc) return rc;
     if (!need_pupil_grad) continue;
     rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
@@ -444,13 +471,16 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     if (rc) return rc;
     GemmParams g{};
     fill_stage(g, true, 0, N, M, c, s.xin, s.uout, sign2pi);
-    for (int i = 0; i < 4; ++i) { g.a_planes[i] = s.ebar_pl[i]; g.out_planes[i] = s.mid_pl[i]; }
+    g.a = s.ebar_pl;
+    g.out = s.mid_pl;
+    g.exact = exact;
     g.mode = EPI_PLANES;
     rc = run_gemm(g, d->precision, st);
     if (rc) return rc;
     GemmParams h{};
     fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
-    for (int i = 0; i < 4; ++i) h.a_planes[i] = s.mid_pl[i];
+    h.a = s.mid_pl;
+    h.exact = exact;
     h.mode = EPI_C64;
     h.scale = s.norm_item + b0;
     h.out_c64 = s.qbuf;

@@ -1,5 +1,6 @@
 // Shared declarations of the dlux_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/dlux_b200.h"
@@ -11,22 +12,36 @@ namespace dlux {
 //
 //   Out[item][n][m] = scale[item] * sum_k Data[d(item)][m][k] * exp(i * sign2pi * fl(kvec[k] * nvec[n]))
 //
-// i.e. a complex contraction of a data matrix (planar, hi/lo-split fp32 planes)
+// i.e. a complex contraction of a data matrix (planar, split operand planes, see PlaneSet)
 // with a DFT phasor matrix that is generated on the fly from two float32
 // coordinate vectors, written TRANSPOSED (m fastest) so that two stages chain.
 // The phase argument is formed exactly as the reference does
 // (/root/reference/src/dLux/utils/propagation.py:124): fl32(fl32(-2pi) * fl32(x*u)).
 // ---------------------------------------------------------------------------
 enum EpilogueMode : int {
-  EPI_PLANES = 0,  // out_planes[p][item][n][m], p = re_hi, re_lo, im_hi, im_lo  (feeds the next stage)
+  EPI_PLANES = 0,  // out planes [item][n][m]  (feeds the next stage)
   EPI_C64 = 1      // out_c64[item][n][m]
 };
 
+// Split representation of a complex matrix Z[n][rows][K], 16 bytes per element:
+//   hi[0], hi[1] : float32 planes [n][rows][pitch4(K)]  = tf32(Re Z), tf32(Im Z)  (rna)
+//   b[0..3]      : bfloat16 planes [n][rows][pitch8(K)] = bf16(hi_re), bf16(Re Z - hi_re),
+//                                                         bf16(hi_im), bf16(Im Z - hi_im)
+// The tensor kernel forms  z*g = hi*g_hi (tf32 MMA) + hi*g_lo + lo*g_hi (bf16 MMAs): the
+// correction terms are 2^-11 of the product, so bf16's 2^-9 leaves ~2^-20 (measured 5.6e-7
+// relative per contraction; tf32 corrections gave 6.6e-8) at 2/3 of the tensor work.
+// In `exact` mode (DLUX_PREC_FP32) hi[] hold the unrounded float32 values and b[] is unused.
+struct PlaneSet {
+  float* hi[2];
+  __nv_bfloat16* b[4];
+};
+__host__ __device__ inline int pitch4(int k) { return (k + 3) & ~3; }
+__host__ __device__ inline int pitch8(int k) { return (k + 7) & ~7; }
+
 struct GemmParams {
-  // data operand: 4 planes, each [n_data][rows][K] float32
-  const float* a_planes[4];
-  int a_pitch;  // floats per data row (>= K, multiple of 4 so TMA can stride it)
-  int n_data;   // number of data matrices in a_planes
+  PlaneSet a;   // data operand, [n_data][rows][K]
+  int exact;    // planes hold unsplit float32 (CUDA-core path)
+  int n_data;   // number of data matrices in `a`
   int rows;    // M dimension of the data matrix (rows m)
   int K;       // contraction length
   int n_out;   // number of generated output coordinates (n)
@@ -38,8 +53,7 @@ struct GemmParams {
   float sign2pi;         // float32(-2*pi) forward, float32(+2*pi) inverse / adjoint-of-forward
   const float* scale;    // [n_items] or nullptr
   int mode;
-  float* out_planes[4];  // EPI_PLANES: [n_items][n_out][out_pitch]
-  int out_pitch;
+  PlaneSet out;          // EPI_PLANES: [n_items][n_out][rows] (pitch4 / pitch8 of rows)
   float2* out_c64;       // EPI_C64: [n_items][n_out][rows]
 };
 
@@ -87,6 +101,23 @@ __device__ __forceinline__ void fast_sincos(float a, float* sn, float* cs) {
   *cs = ((q + 1) & 2) ? -co : co;
 }
 
+// (re, im) -> the six operand planes at element offsets o4 (float32 pitch) / o8 (bf16 pitch)
+__device__ __forceinline__ void plane_store(const PlaneSet& ps, size_t o4, size_t o8, float re, float im,
+                                            int exact) {
+  if (exact) {
+    ps.hi[0][o4] = re;
+    ps.hi[1][o4] = im;
+    return;
+  }
+  const float rh = tf32_hi(re), ih = tf32_hi(im);
+  ps.hi[0][o4] = rh;
+  ps.hi[1][o4] = ih;
+  ps.b[0][o8] = __float2bfloat16_rn(rh);
+  ps.b[1][o8] = __float2bfloat16_rn(re - rh);
+  ps.b[2][o8] = __float2bfloat16_rn(ih);
+  ps.b[3][o8] = __float2bfloat16_rn(im - ih);
+}
+
 // Shared epilogue for one output element D[m][n] = (re, im) of `item`.
 __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, int m, int n,
                                                float re, float im) {
@@ -95,12 +126,8 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
   im *= sc;
   const size_t idx = ((size_t)item * p.n_out + n) * p.rows + m;
   if (p.mode == EPI_PLANES) {
-    const size_t po = ((size_t)item * p.n_out + n) * p.out_pitch + m;
-    const float rh = tf32_hi(re), ih = tf32_hi(im);
-    p.out_planes[0][po] = rh;
-    p.out_planes[1][po] = re - rh;
-    p.out_planes[2][po] = ih;
-    p.out_planes[3][po] = im - ih;
+    const size_t row = (size_t)item * p.n_out + n;
+    plane_store(p.out, row * pitch4(p.rows) + m, row * pitch8(p.rows) + m, re, im, p.exact);
   } else {  // EPI_C64
     p.out_c64[idx] = make_float2(re, im);
   }
@@ -118,17 +145,15 @@ size_t gemm_tc_workspace_bytes();
 int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const float* shift_xy,
                   const float* delta_xy, int delta_stride_items, float* xin, float* uout,
                   cudaStream_t st);
-__host__ __device__ inline int pitch4(int k) { return (k + 3) & ~3; }
-// in: [n_mat][rows][cols] c64 -> planes [n_mat][rows][pitch4(cols)]
-int launch_split_c64(const float2* in, size_t n_mat_rows, int cols, float* p0, float* p1, float* p2,
-                     float* p3, cudaStream_t st);
+// in: [n_mat][rows][cols] c64 -> split planes
+int launch_split_c64(const float2* in, size_t n_mat_rows, int cols, const PlaneSet& out, int exact,
+                     cudaStream_t st);
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
                  const float* wavenumber, const float* amp_scale /*device scalar*/,
-                 float* p0, float* p1, float* p2, float* p3, cudaStream_t st);
+                 const PlaneSet& out, int exact, cudaStream_t st);
 int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStream_t st);
 int launch_cotangent(int M, int n_items, const float2* field, const float* psf_bar,
-                     const float* w, float* p0, float* p1, float* p2, float* p3, float* w_bar,
-                     cudaStream_t st);
+                     const float* w, const PlaneSet& out, int exact, float* w_bar, cudaStream_t st);
 int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coeffs,
                       const float* base, float* out, cudaStream_t st);
 int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,

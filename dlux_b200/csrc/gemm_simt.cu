@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p, int t
   const int t = blockIdx.x % tiles;
   const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
   const int d = p.item_data ? __ldg(p.item_data + item) : item;
-  const size_t a_off = (size_t)d * p.rows * p.a_pitch;
+  const int a_pitch = pitch4(p.K);
+  const size_t a_off = (size_t)d * p.rows * a_pitch;
   const float* kv = p.kvec + (size_t)item * p.kvec_stride;
   const float* nv = p.nvec + (size_t)item * p.nvec_stride;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -35,9 +36,9 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p, int t
       const int m = m0 + ml, k = k0 + kl;
       float re = 0.0f, im = 0.0f;
       if (m < p.rows && k < p.K) {
-        const size_t o = a_off + (size_t)m * p.a_pitch + k;
-        re = __ldg(p.a_planes[0] + o) + __ldg(p.a_planes[1] + o);
-        im = __ldg(p.a_planes[2] + o) + __ldg(p.a_planes[3] + o);
+        const size_t o = a_off + (size_t)m * a_pitch + k;
+        re = __ldg(p.a.hi[0] + o);  // exact mode: unsplit float32
+        im = __ldg(p.a.hi[1] + o);
       }
       As_re[kl][ml] = re;
       As_im[kl][ml] = im;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p, int t
 
 int launch_gemm_simt(const GemmParams& p, cudaStream_t st) {
   if (p.n_items <= 0) return DLUX_OK;
+  if (!p.exact) return DLUX_ERR_ARG;  // this path reads unsplit float32 planes
   const int tiles_m = (p.rows + BM - 1) / BM, tiles_n = (p.n_out + BN - 1) / BN;
   const long long total = (long long)tiles_m * tiles_n * p.n_items;
   if (total > 2147483647LL) return DLUX_ERR_SHAPE;

@@ -16,11 +16,15 @@
 //   so that  D = G1 * Re(Data)^T + G2 * Im(Data)^T  has Re(Out[j][:]) in lane 2j and
 //   Im(Out[j][:]) in lane 2j+1: one M128 x N128 x K8 MMA yields both complex parts and the
 //   pair of lanes that shares a phasor also shares its sincos (via __shfl_xor).
-// * B operand = the data: four planar fp32 planes (re_hi, re_lo, im_hi, im_lo) streamed by
-//   TMA (cp.async.bulk.tensor, SWIZZLE_64B, K-major) into a 3-deep shared-memory ring of
-//   64 KiB stages (both tiles).  Shared memory carries only this operand.
-// * 3xTF32: 6 tcgen05.mma kind::tf32 per k-step -- hi*lo, lo*hi, hi*hi for each of the two
-//   products; lo*lo is dropped (2^-22 relative).
+// * B operand = the data (PlaneSet, common.cuh): tf32 "hi" planes in float32 plus bf16 copies
+//   of hi and of the residual lo, streamed by TMA (cp.async.bulk.tensor, K-major, SWIZZLE_64B
+//   for the 64-byte fp32 rows and SWIZZLE_32B for the 32-byte bf16 rows) into a 3-deep
+//   shared-memory ring of 64 KiB stages (both tiles).  Shared memory carries only this
+//   operand.
+// * Split precision ("TF32 + 2xBF16"): per 16-k chunk and tile, 4 tcgen05.mma kind::tf32
+//   (hi*hi, K=8) + 4 kind::f16 bf16 MMAs (hi*lo and lo*hi, K=16) accumulate into the same
+//   fp32 TMEM accumulator -- 8 MMA slots instead of the 12 of 3xTF32; lo*lo is dropped.
+//   Measured error of the scheme: 5.6e-7 relative per contraction (3xTF32: 6.6e-8).
 // * Tensor-core fp32 accumulation truncates (measured ~2e-8 relative systematic loss per
 //   accumulate), so K chains are cut every FLUSH_CHUNKS k-chunks: the partial accumulators
 //   (three 128-column TMEM buffers used round-robin by the two tiles) are drained by the
@@ -32,7 +36,8 @@
 //   producer + MMA issuer (setmaxnreg.dec), WG3 = phasor generators (one warp per TMEM lane
 //   quarter).
 // TMEM map (512 columns): [0,384) three partial accumulators, [384,512) two phasor stages
-// of 64 columns = 4 planes (G1_hi, G1_lo, G2_hi, G2_lo) x 16 k.
+// of 64 columns: G1_hi, G2_hi as tf32 (16 k -> 16 columns each) and G1_hi, G1_lo, G2_hi,
+// G2_lo as packed bf16 (16 k -> 8 columns each).
 #include <cuda.h>
 #include <cstdio>
 #include <mutex>
@@ -48,14 +53,18 @@ constexpr int BK = 16;             // k per pipeline stage = one 64-byte swizzle
 constexpr int UMMA_K = 8;          // kind::tf32
 constexpr int A_STAGES = 3;        // data ring (TMA), each stage holds both tiles
 constexpr int G_STAGES = 2;        // phasor ring (TMEM)
-constexpr int PLANE_BYTES = BM * BK * 4;            // 8 KiB
-constexpr int TILE_BYTES = 4 * PLANE_BYTES;         // 32 KiB: re_hi, re_lo, im_hi, im_lo of one tile
+constexpr int PLANE_BYTES = BM * BK * 4;            // 8 KiB: one fp32 (tf32) plane of a tile-chunk
+constexpr int BPLANE_BYTES = BM * BK * 2;           // 4 KiB: one bf16 plane
+constexpr int BPL_BASE = 2 * PLANE_BYTES;           // bf16 planes follow the two fp32 planes
+constexpr int TILE_BYTES = 2 * PLANE_BYTES + 4 * BPLANE_BYTES;  // 32 KiB per tile-chunk
 constexpr int A_BYTES = 2 * TILE_BYTES;             // 64 KiB: tiles a and b
 constexpr int RING_BYTES = A_STAGES * A_BYTES;      // 192 KiB
 constexpr int FLUSH_CHUNKS = 4;    // k-chunks accumulated in TMEM before draining to registers
 constexpr int NUM_ACC = 3;         // TMEM partial-accumulator buffers, used round-robin (a, b, a, b, ...)
 constexpr int ACC_COLS = BM;       // 128 fp32 columns per partial
 constexpr int G_COLS = 4 * BK;     // 64 columns per phasor stage
+constexpr int GB_BASE = 2 * BK;    // packed-bf16 planes start after the two tf32 planes
+constexpr int GB_COLS = BK / 2;    // 8 columns per bf16 plane
 constexpr int G_BASE_COL = NUM_ACC * ACC_COLS;      // 384
 constexpr int TMEM_COLS = 512;
 static_assert(G_BASE_COL + G_STAGES * G_COLS <= TMEM_COLS, "TMEM budget");
@@ -119,6 +128,16 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with bf16 operands: A 128 lanes x 8 columns (16 packed bf16), B K-major 16 x bf16
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -132,6 +151,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+      : "memory");
+}
+// two floats -> packed bf16x2, `lo` in bits [0,16) (the lower k index), `hi` in bits [16,32)
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 // this thread's lane, 8 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
@@ -167,9 +198,18 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
   return DESC_SW64_HI | (uint64_t)(saddr >> 4);  // shared addresses are < 256 KiB: 14 bits after >> 4
 }
 
-// kind::tf32 instruction descriptor: D=f32, A=B=tf32, K-major both, M=128 (lanes), N=128 (data rows)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BM >> 3) << 17) |
-                           ((uint32_t)((2 * NB) >> 4) << 24);
+// K-major SWIZZLE_32B descriptor for the bf16 planes (rows of 16 bf16 = 32 bytes; 8 rows = 256 B)
+constexpr uint64_t DESC_SW32_HI = ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
+                                  ((uint64_t)6 << 61);
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
+  return DESC_SW32_HI | (uint64_t)(saddr >> 4);
+}
+
+// instruction descriptors: D=f32, K-major both, M=128 (lanes), N=128 (data rows);
+// A=B=tf32 (format 2, kind::tf32) or A=B=bf16 (format 1, kind::f16)
+constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BM >> 3) << 17) | ((uint32_t)((2 * NB) >> 4) << 24);
+constexpr uint32_t IDESC = IDESC_SHAPE | (2u << 7) | (2u << 10);
+constexpr uint32_t IDESC_BF16 = IDESC_SHAPE | (1u << 7) | (1u << 10);
 
 // Fused epilogue of one tile, staged through shared memory so that every global access is
 // coalesced.  Thread = TMEM lane: within warp q, lane 2j' carries Re(Out[n][m0 + c]) and lane
@@ -206,18 +246,27 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
           if (n < p.n_out) {
             float4 h;
             h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-            const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-            const size_t o = ((size_t)item * p.n_out + n) * p.out_pitch + m0 + c0 + cc;
-            float* hp = p.out_planes[(r & 1) ? 2 : 0] + o;
-            float* lp = p.out_planes[(r & 1) ? 3 : 1] + o;
-            if (c0 + cc + 4 <= mmax) {  // out_pitch, m0, c0, cc are multiples of 4
+            const size_t row = (size_t)item * p.n_out + n;
+            const int col = m0 + c0 + cc;  // multiple of 4
+            float* hp = p.out.hi[r & 1] + row * pitch4(p.rows) + col;
+            __nv_bfloat16* hb = p.out.b[(r & 1) * 2] + row * pitch8(p.rows) + col;
+            __nv_bfloat16* lb = p.out.b[(r & 1) * 2 + 1] + row * pitch8(p.rows) + col;
+            if (c0 + cc + 4 <= mmax) {
               *reinterpret_cast<float4*>(hp) = h;
-              *reinterpret_cast<float4*>(lp) = l;
+              uint2 wh, wl;
+              wh.x = pack_bf16(h.x, h.y); wh.y = pack_bf16(h.z, h.w);
+              wl.x = pack_bf16(v.x - h.x, v.y - h.y); wl.y = pack_bf16(v.z - h.z, v.w - h.w);
+              *reinterpret_cast<uint2*>(hb) = wh;
+              *reinterpret_cast<uint2*>(lb) = wl;
             } else {
-              const float hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+              const float hh[4] = {h.x, h.y, h.z, h.w}, vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (c0 + cc + e < mmax) { hp[e] = hh[e]; lp[e] = ll[e]; }
+                if (c0 + cc + e < mmax) {
+                  hp[e] = hh[e];
+                  hb[e] = __float2bfloat16_rn(hh[e]);
+                  lb[e] = __float2bfloat16_rn(vv[e] - hh[e]);
+                }
             }
           }
         }
@@ -246,6 +295,30 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
   }
 }
 
+// The 8 MMAs of one tile and one 16-k chunk:
+//   D (+)= G1_hi * Re_hi^T + G2_hi * Im_hi^T                                  (tf32, two k-steps)
+//        + G1_hi * Re_lo^T + G1_lo * Re_hi^T + G2_hi * Im_lo^T + G2_lo * Im_hi^T   (bf16, K = 16)
+// `tile_smem`: shared address of the tile-chunk's planes; `g0`: TMEM address of the phasor stage.
+__device__ __forceinline__ void issue_tile_chunk(uint32_t d, uint32_t g0, uint32_t tile_smem, bool fresh) {
+  constexpr uint64_t KS = (UMMA_K * 4) >> 4;  // descriptor step per k-step inside the 64-byte swizzle row
+  const uint64_t d_rh = make_desc_sw64(tile_smem), d_ih = make_desc_sw64(tile_smem + PLANE_BYTES);
+  const uint64_t b_rh = make_desc_sw32(tile_smem + BPL_BASE + 0 * BPLANE_BYTES);
+  const uint64_t b_rl = make_desc_sw32(tile_smem + BPL_BASE + 1 * BPLANE_BYTES);
+  const uint64_t b_ih = make_desc_sw32(tile_smem + BPL_BASE + 2 * BPLANE_BYTES);
+  const uint64_t b_il = make_desc_sw32(tile_smem + BPL_BASE + 3 * BPLANE_BYTES);
+  const uint32_t gb = g0 + GB_BASE;  // packed bf16: G1_hi, G1_lo, G2_hi, G2_lo
+  // small terms first
+  umma_bf16_ts(d, gb + 1 * GB_COLS, b_rh, IDESC_BF16, fresh ? 0u : 1u);  // G1_lo * Re_hi
+  umma_bf16_ts(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);                // G1_hi * Re_lo
+  umma_bf16_ts(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);                // G2_lo * Im_hi
+  umma_bf16_ts(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);                // G2_hi * Im_lo
+#pragma unroll
+  for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+    umma_tf32_ts(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);        // G1_hi * Re_hi
+    umma_tf32_ts(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);   // G2_hi * Im_hi
+  }
+}
+
 // Where the TMEM partial accumulators of the two tiles open and close along the k-chunks of
 // a unit.  Tile a: [0,4) [4,8) ...; tile b: [0,2) [2,6) [6,10) ... (staggered by half a
 // partial).  Both close at the last chunk.  Acquisition order inside a chunk: a, then b.
@@ -270,7 +343,8 @@ struct TcParams {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-               const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
+               const __grid_constant__ CUtensorMap mapb0, const __grid_constant__ CUtensorMap mapb1,
+               const __grid_constant__ CUtensorMap mapb2, const __grid_constant__ CUtensorMap mapb3,
                const TcParams tp) {
   extern __shared__ uint8_t smem_raw[];
   const GemmParams& p = tp.g;
@@ -291,8 +365,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   if (warp == WARP_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map0));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map1));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map2));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map3));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb0));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb1));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb2));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb3));
   }
   if (warp == WARP_MMA && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
@@ -342,15 +418,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             const uint32_t dst = smem_base + stage * A_BYTES;
             const uint32_t bar = fullA_bar(stage);
             mbar_arrive_expect_tx(bar, A_BYTES);
-            tma_load_3d(dst + 0 * PLANE_BYTES, &map0, bar, kc * BK, m0, d);
-            tma_load_3d(dst + 1 * PLANE_BYTES, &map1, bar, kc * BK, m0, d);
-            tma_load_3d(dst + 2 * PLANE_BYTES, &map2, bar, kc * BK, m0, d);
-            tma_load_3d(dst + 3 * PLANE_BYTES, &map3, bar, kc * BK, m0, d);
-            // tile b: rows beyond the matrix are zero-filled by TMA
-            tma_load_3d(dst + TILE_BYTES + 0 * PLANE_BYTES, &map0, bar, kc * BK, m0 + BM, d);
-            tma_load_3d(dst + TILE_BYTES + 1 * PLANE_BYTES, &map1, bar, kc * BK, m0 + BM, d);
-            tma_load_3d(dst + TILE_BYTES + 2 * PLANE_BYTES, &map2, bar, kc * BK, m0 + BM, d);
-            tma_load_3d(dst + TILE_BYTES + 3 * PLANE_BYTES, &map3, bar, kc * BK, m0 + BM, d);
+#pragma unroll
+            for (int tb = 0; tb < 2; ++tb) {  // tile a, tile b (rows beyond the matrix are zero-filled)
+              const uint32_t t0 = dst + tb * TILE_BYTES;
+              const int mr = m0 + tb * BM;
+              tma_load_3d(t0 + 0 * PLANE_BYTES, &map0, bar, kc * BK, mr, d);   // tf32 hi: re, im
+              tma_load_3d(t0 + 1 * PLANE_BYTES, &map1, bar, kc * BK, mr, d);
+              tma_load_3d(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, bar, kc * BK, mr, d);  // bf16: re_hi, re_lo,
+              tma_load_3d(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, bar, kc * BK, mr, d);  //       im_hi, im_lo
+              tma_load_3d(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, bar, kc * BK, mr, d);
+              tma_load_3d(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, bar, kc * BK, mr, d);
+            }
           }
           __syncwarp();
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
@@ -377,23 +455,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           }
           tc_fence_after();
           const uint32_t g0 = tmem_base + (uint32_t)(G_BASE_COL + sg * G_COLS);
-          constexpr uint64_t PL = PLANE_BYTES >> 4;   // descriptor step per plane
-          constexpr uint64_t KS = (UMMA_K * 4) >> 4;  // ... per k-step inside the swizzle row
           if (elect_one()) {
-            const uint32_t d = tmem_base + (ta % NUM_ACC) * ACC_COLS;
-            const uint64_t b_rh = make_desc_sw64(smem_base + sa * A_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-              const uint64_t d_rh = b_rh + ks * KS, d_rl = d_rh + PL, d_ih = d_rh + 2 * PL, d_il = d_rh + 3 * PL;
-              const uint32_t g1h = g0 + ks * UMMA_K, g1l = g1h + BK, g2h = g1h + 2 * BK, g2l = g1h + 3 * BK;
-              // (Re | Im rows) += G1 * Re(Data)^T + G2 * Im(Data)^T; small terms first
-              umma_tf32_ts(d, g1l, d_rh, IDESC, (ps.a_open && ks == 0) ? 0u : 1u);
-              umma_tf32_ts(d, g1h, d_rl, IDESC, 1u);
-              umma_tf32_ts(d, g2l, d_ih, IDESC, 1u);
-              umma_tf32_ts(d, g2h, d_il, IDESC, 1u);
-              umma_tf32_ts(d, g1h, d_rh, IDESC, 1u);
-              umma_tf32_ts(d, g2h, d_ih, IDESC, 1u);
-            }
+            issue_tile_chunk(tmem_base + (ta % NUM_ACC) * ACC_COLS, g0, smem_base + sa * A_BYTES, ps.a_open);
             if (ps.a_close) umma_commit(tfull_bar(ta % NUM_ACC));  // tile a's partial complete -> WG0
           }
           __syncwarp();
@@ -403,19 +466,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             tc_fence_after();
           }
           if (elect_one()) {
-            const uint32_t d = tmem_base + (tb % NUM_ACC) * ACC_COLS;
-            const uint64_t b_rh = make_desc_sw64(smem_base + sa * A_BYTES + TILE_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-              const uint64_t d_rh = b_rh + ks * KS, d_rl = d_rh + PL, d_ih = d_rh + 2 * PL, d_il = d_rh + 3 * PL;
-              const uint32_t g1h = g0 + ks * UMMA_K, g1l = g1h + BK, g2h = g1h + 2 * BK, g2l = g1h + 3 * BK;
-              umma_tf32_ts(d, g1l, d_rh, IDESC, (ps.b_open && ks == 0) ? 0u : 1u);
-              umma_tf32_ts(d, g1h, d_rl, IDESC, 1u);
-              umma_tf32_ts(d, g2l, d_ih, IDESC, 1u);
-              umma_tf32_ts(d, g2h, d_il, IDESC, 1u);
-              umma_tf32_ts(d, g1h, d_rh, IDESC, 1u);
-              umma_tf32_ts(d, g2h, d_ih, IDESC, 1u);
-            }
+            issue_tile_chunk(tmem_base + (tb % NUM_ACC) * ACC_COLS, g0, smem_base + sa * A_BYTES + TILE_BYTES,
+                             ps.b_open);
             umma_commit(emptyA_bar(sa));  // free the smem slot and the phasor stage when these MMAs retire
             umma_commit(emptyG_bar(sg));
             if (ps.b_close) umma_commit(tfull_bar(tb % NUM_ACC));  // tile b's partial complete -> WG1
@@ -533,12 +585,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         mbar_wait(emptyG_bar(stage), phase ^ 1);
         tc_fence_after();
         const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS);
+        // tf32 planes: G1_hi at columns [0,16), G2_hi at [16,32)
+        tmem_st8(g0 + 0, g1h[0]);
+        tmem_st8(g0 + UMMA_K, g1h[1]);
+        tmem_st8(g0 + BK, g2h[0]);
+        tmem_st8(g0 + BK + UMMA_K, g2h[1]);
+        // packed bf16 planes (16 k -> 8 columns): G1_hi, G1_lo, G2_hi, G2_lo
+        {
+          uint32_t pk[4][8];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          tmem_st8(g0 + 0 * BK + ks * UMMA_K, g1h[ks]);
-          tmem_st8(g0 + 1 * BK + ks * UMMA_K, g1l[ks]);
-          tmem_st8(g0 + 2 * BK + ks * UMMA_K, g2h[ks]);
-          tmem_st8(g0 + 3 * BK + ks * UMMA_K, g2l[ks]);
+          for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              pk[0][ks * 4 + j] = pack_bf16(g1h[ks][2 * j], g1h[ks][2 * j + 1]);
+              pk[1][ks * 4 + j] = pack_bf16(g1l[ks][2 * j], g1l[ks][2 * j + 1]);
+              pk[2][ks * 4 + j] = pack_bf16(g2h[ks][2 * j], g2h[ks][2 * j + 1]);
+              pk[3][ks * 4 + j] = pack_bf16(g2l[ks][2 * j], g2l[ks][2 * j + 1]);
+            }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) tmem_st8u(g0 + GB_BASE + q4 * GB_COLS, pk[q4]);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -603,18 +668,22 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   if (p.n_items <= 0) return DLUX_OK;
   TcState& s = tc_state();
   if (s.rc != DLUX_OK) return s.rc;
-  if (p.a_pitch % 4 != 0) return DLUX_ERR_SHAPE;  // TMA global strides are multiples of 16 bytes
-  if (p.mode == EPI_PLANES && p.out_pitch % 4 != 0) return DLUX_ERR_SHAPE;
+  if (p.exact) return DLUX_ERR_ARG;  // needs the split operand planes
 
   const cuuint64_t n_data = (cuuint64_t)(p.n_data > 0 ? p.n_data : p.n_items);
-  CUtensorMap maps[4];
-  for (int i = 0; i < 4; ++i) {
+  CUtensorMap maps[6];
+  for (int i = 0; i < 6; ++i) {
+    const bool bf = i >= 2;
+    const cuuint64_t esz = bf ? 2 : 4;
+    const cuuint64_t pitch = bf ? pitch8(p.K) : pitch4(p.K);  // row strides are multiples of 16 bytes
     cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.rows, n_data};
-    cuuint64_t strides[2] = {(cuuint64_t)p.a_pitch * 4, (cuuint64_t)p.a_pitch * 4 * (cuuint64_t)p.rows};
+    cuuint64_t strides[2] = {pitch * esz, pitch * esz * (cuuint64_t)p.rows};
     cuuint32_t box[3] = {BK, BM, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = s.encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.a_planes[i], dims, strides,
-                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+    void* base = bf ? (void*)p.a.b[i - 2] : (void*)p.a.hi[i];
+    CUresult r = s.encode(&maps[i], bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          bf ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       fprintf(stderr, "[dlux_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
@@ -630,7 +699,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   tp.n_units = (int)total;
   tp.k_chunks = (p.K + BK - 1) / BK;
   const int grid = tp.n_units < s.num_sms ? tp.n_units : s.num_sms;
-  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], tp);
+  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], tp);
   note_launch();
   return check_launch("gemm_tc");
 }
