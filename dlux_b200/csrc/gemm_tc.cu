@@ -31,10 +31,10 @@
 //   tile's epilogue warpgroup with tcgen05.ld and added, round-to-nearest, into fp32
 //   registers (Ootomo & Yokota's scheme for error-corrected TF32 GEMM).  Draining overlaps
 //   the MMAs of the other tile / next partial.
-// * Persistent CTAs, one per SM, 16 warps in 4 warpgroups: WG0 / WG1 = drain + fused
+// * Persistent CTAs, one per SM, 20 warps in 5 warpgroups: WG0 / WG1 = drain + fused
 //   epilogue of tile a / b (setmaxnreg.inc: 128 running totals per thread), WG2 = TMA
-//   producer + MMA issuer (setmaxnreg.dec), WG3 = phasor generators (one warp per TMEM lane
-//   quarter).
+//   producer + MMA issuer (setmaxnreg.dec), WG3 / WG4 = phasor generators (two warps per TMEM
+//   lane quarter, one per k-step of the chunk).
 // TMEM map (512 columns): [0,384) three partial accumulators, [384,512) two phasor stages
 // of 64 columns: G1_hi, G2_hi as tf32 (16 k -> 16 columns each) and G1_hi, G1_lo, G2_hi,
 // G2_lo as packed bf16 (16 k -> 8 columns each).
@@ -71,11 +71,13 @@ static_assert(G_BASE_COL + G_STAGES * G_COLS <= TMEM_COLS, "TMEM budget");
 constexpr int NUM_EPI_WARPS = 8;   // warps 0..3 drain tile a (WG0), warps 4..7 tile b (WG1)
 constexpr int WARP_TMA = 8;        // WG2
 constexpr int WARP_MMA = 9;
-constexpr int FIRST_GEN_WARP = 12; // WG3
-constexpr int NUM_GEN_WARPS = 4;
-constexpr int NUM_THREADS = 32 * (FIRST_GEN_WARP + NUM_GEN_WARPS);  // 512
-constexpr int REGS_EPI = 176, REGS_CTRL = 40, REGS_GEN = 120;       // setmaxnreg budgets (launch: 128)
-static_assert(256 * (REGS_EPI - 128) <= 128 * (128 - REGS_CTRL) + 128 * (128 - REGS_GEN), "register budget");
+constexpr int FIRST_GEN_WARP = 12; // WG3 (k-step 0 of each chunk), WG4 (k-step 1)
+constexpr int NUM_GEN_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (FIRST_GEN_WARP + NUM_GEN_WARPS);  // 640
+constexpr int REGS_LAUNCH = 96;    // 65536 / 640 rounded down to a multiple of 8
+constexpr int REGS_EPI = 152, REGS_CTRL = 40, REGS_GEN = 64;        // setmaxnreg budgets
+static_assert(256 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_GEN),
+              "register budget");
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 2560 /*epilogue staging*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
@@ -152,11 +154,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-      : "memory");
+__device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 // two floats -> packed bf16x2, `lo` in bits [0,16) (the lower k index), `hi` in bits [16,32)
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -526,11 +526,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     }
   } else {
     // ===================== phasor generators =====================
+    // Two warps per TMEM lane quarter: WG3 produces k-step 0 (k 0..7) of every chunk, WG4
+    // k-step 1.  Inside a warp the lane pair (2j, 2j+1) = (Re row, Im row) of phasor column j
+    // splits the 8 k's of the k-step 4 + 4 and swaps results with __shfl_xor.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GEN));
-    const int q = warp & 3;                // TMEM lane quarter
-    const bool odd = (lane & 1) != 0;      // odd lane = imaginary row of the phasor column
-    const int jcol = (q * 32 + lane) >> 1; // phasor column within the tile
-    const int ksub = odd ? 4 : 0;          // my 4 k's inside each k-step
+    const int q = warp & 3;                          // TMEM lane quarter
+    const int ks = (warp - FIRST_GEN_WARP) >> 2;     // which k-step of the chunk
+    const bool odd = (lane & 1) != 0;                // odd lane = imaginary row of the phasor column
+    const int jcol = (q * 32 + lane) >> 1;           // phasor column within the tile
+    const int ksub = ks * UMMA_K + (odd ? 4 : 0);    // my 4 k's inside the chunk
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int stage = 0;
     uint32_t phase = 0;
@@ -540,71 +544,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       const int n = (t / tp.tiles_mp) * NB + jcol;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
       const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
-      float xk[2][4];  // this chunk's k coordinates, prefetched one chunk ahead
+      float xk[4];  // this chunk's k coordinates, prefetched one chunk ahead
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
+      for (int j = 0; j < 4; ++j) xk[j] = (ksub + j < p.K) ? __ldg(kv + ksub + j) : 0.0f;
+      for (int kc = 0; kc < tp.k_chunks; ++kc) {
+        float xn[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int k = ks * UMMA_K + ksub + j;
-          xk[ks][j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
+          const int k = (kc + 1) * BK + ksub + j;
+          xn[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
         }
-      for (int kc = 0; kc < tp.k_chunks; ++kc) {
-        float xn[2][4];
+        float g1h[8], g1l[8], g2h[8], g2l[8];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = (kc + 1) * BK + ks * UMMA_K + ksub + j;
-            xn[ks][j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
-          }
-        float g1h[2][8], g1l[2][8], g2h[2][8], g2l[2][8];
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          // my 4 phasors of this k-step, split; swap with the partner lane (same column, other 4 k's)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float sn, cs;
+        for (int j = 0; j < 4; ++j) {
+          float sn, cs;
 #ifdef DLUX_DEBUG_NOGEN
-            sn = xk[ks][j]; cs = u;
+          sn = xk[j]; cs = u;
 #else
-            fast_sincos(phase_arg(p.sign2pi, xk[ks][j], u), &sn, &cs);
+          fast_sincos(phase_arg(p.sign2pi, xk[j], u), &sn, &cs);
 #endif
-            xk[ks][j] = xn[ks][j];
-            const float ch = tf32_hi(cs), sh = tf32_hi(sn);
-            const float cl = cs - ch, sl = sn - sh;
-            const float pch = __shfl_xor_sync(0xffffffffu, ch, 1), pcl = __shfl_xor_sync(0xffffffffu, cl, 1);
-            const float psh = __shfl_xor_sync(0xffffffffu, sh, 1), psl = __shfl_xor_sync(0xffffffffu, sl, 1);
-            // k order inside the k-step: the even lane computed k 0..3, the odd lane k 4..7.
-            // even lane (Re row): G1 = cos, G2 = -sin; odd lane (Im row): G1 = sin, G2 = cos
-            g1h[ks][j] = odd ? psh : ch;      g1l[ks][j] = odd ? psl : cl;
-            g2h[ks][j] = odd ? pch : -sh;     g2l[ks][j] = odd ? pcl : -sl;
-            g1h[ks][4 + j] = odd ? sh : pch;  g1l[ks][4 + j] = odd ? sl : pcl;
-            g2h[ks][4 + j] = odd ? ch : -psh; g2l[ks][4 + j] = odd ? cl : -psl;
-          }
+          xk[j] = xn[j];
+          const float ch = tf32_hi(cs), sh = tf32_hi(sn);
+          const float cl = cs - ch, sl = sn - sh;
+          const float pch = __shfl_xor_sync(0xffffffffu, ch, 1), pcl = __shfl_xor_sync(0xffffffffu, cl, 1);
+          const float psh = __shfl_xor_sync(0xffffffffu, sh, 1), psl = __shfl_xor_sync(0xffffffffu, sl, 1);
+          // k order inside the k-step: the even lane computed k 0..3, the odd lane k 4..7.
+          // even lane (Re row): G1 = cos, G2 = -sin; odd lane (Im row): G1 = sin, G2 = cos
+          g1h[j] = odd ? psh : ch;      g1l[j] = odd ? psl : cl;
+          g2h[j] = odd ? pch : -sh;     g2l[j] = odd ? pcl : -sl;
+          g1h[4 + j] = odd ? sh : pch;  g1l[4 + j] = odd ? sl : pcl;
+          g2h[4 + j] = odd ? ch : -psh; g2l[4 + j] = odd ? cl : -psl;
+        }
+        uint32_t pk[4][4];  // packed bf16: G1_hi, G1_lo, G2_hi, G2_lo, 8 k -> 4 columns each
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pk[0][j] = pack_bf16(g1h[2 * j], g1h[2 * j + 1]);
+          pk[1][j] = pack_bf16(g1l[2 * j], g1l[2 * j + 1]);
+          pk[2][j] = pack_bf16(g2h[2 * j], g2h[2 * j + 1]);
+          pk[3][j] = pack_bf16(g2l[2 * j], g2l[2 * j + 1]);
         }
         mbar_wait(emptyG_bar(stage), phase ^ 1);
         tc_fence_after();
         const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS);
-        // tf32 planes: G1_hi at columns [0,16), G2_hi at [16,32)
-        tmem_st8(g0 + 0, g1h[0]);
-        tmem_st8(g0 + UMMA_K, g1h[1]);
-        tmem_st8(g0 + BK, g2h[0]);
-        tmem_st8(g0 + BK + UMMA_K, g2h[1]);
-        // packed bf16 planes (16 k -> 8 columns): G1_hi, G1_lo, G2_hi, G2_lo
-        {
-          uint32_t pk[4][8];
+        tmem_st8(g0 + ks * UMMA_K, g1h);        // tf32 G1_hi: columns [0,16)
+        tmem_st8(g0 + BK + ks * UMMA_K, g2h);   // tf32 G2_hi: columns [16,32)
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              pk[0][ks * 4 + j] = pack_bf16(g1h[ks][2 * j], g1h[ks][2 * j + 1]);
-              pk[1][ks * 4 + j] = pack_bf16(g1l[ks][2 * j], g1l[ks][2 * j + 1]);
-              pk[2][ks * 4 + j] = pack_bf16(g2h[ks][2 * j], g2h[ks][2 * j + 1]);
-              pk[3][ks * 4 + j] = pack_bf16(g2l[ks][2 * j], g2l[ks][2 * j + 1]);
-            }
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) tmem_st8u(g0 + GB_BASE + q4 * GB_COLS, pk[q4]);
-        }
+        for (int q4 = 0; q4 < 4; ++q4) tmem_st4u(g0 + GB_BASE + q4 * GB_COLS + ks * (UMMA_K / 2), pk[q4]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
