@@ -101,6 +101,27 @@ __device__ __forceinline__ void fast_sincos(float a, float* sn, float* cs) {
   *cs = ((q + 1) & 2) ? -co : co;
 }
 
+// Lean variant for the in-kernel phasor generators: the same exact Cody-Waite reduction,
+// then MUFU.SIN / MUFU.COS on the reduced argument |r| <= pi/4 (abs. error ~3e-7, about 4x
+// the polynomial's; the parity tests bound the end-to-end effect) and branch-free quadrant
+// logic on the sign bits.  `qshift` rotates the result by quarter turns exactly: returns
+// sincos(a + qshift * pi/2).  No slow path: the 3-term reduction is accurate for
+// |a| < ~1e5 rad (MFT phases are ~ pi * nfringes / 2) and degrades gracefully beyond.
+__device__ __forceinline__ void fast_sincos_mufu(float a, int qshift, float* sn, float* cs) {
+  float j = fmaf(a, 0.636619747f, 12582912.0f);
+  const uint32_t q = (uint32_t)(__float_as_int(j) + qshift);
+  j -= 12582912.0f;
+  float r = fmaf(j, -1.57079601e+00f, a);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const float s = __sinf(r), c = __cosf(r);
+  const bool swap = (q & 1u) != 0;
+  const uint32_t so = __float_as_uint(swap ? c : s);
+  const uint32_t co = __float_as_uint(swap ? s : c);
+  *sn = __uint_as_float(so ^ ((q & 2u) << 30));          // negate in quadrants 2, 3
+  *cs = __uint_as_float(co ^ (((q + 1u) & 2u) << 30));   // negate in quadrants 1, 2
+}
+
 // (re, im) -> the six operand planes at element offsets o4 (float32 pitch) / o8 (bf16 pitch)
 __device__ __forceinline__ void plane_store(const PlaneSet& ps, size_t o4, size_t o8, float re, float im,
                                             int exact) {

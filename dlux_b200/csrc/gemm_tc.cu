@@ -14,8 +14,7 @@
 //   j and lane 2j+1 its "imaginary" row, in two arrangements
 //       G1 = (cos | sin),   G2 = (-sin | cos)        (row 2j | row 2j+1)
 //   so that  D = G1 * Re(Data)^T + G2 * Im(Data)^T  has Re(Out[j][:]) in lane 2j and
-//   Im(Out[j][:]) in lane 2j+1: one M128 x N128 x K8 MMA yields both complex parts and the
-//   pair of lanes that shares a phasor also shares its sincos (via __shfl_xor).
+//   Im(Out[j][:]) in lane 2j+1: one M128 x N128 MMA yields both complex parts.
 // * B operand = the data (PlaneSet, common.cuh): tf32 "hi" planes in float32 plus bf16 copies
 //   of hi and of the residual lo, streamed by TMA (cp.async.bulk.tensor, K-major, SWIZZLE_64B
 //   for the 64-byte fp32 rows and SWIZZLE_32B for the 32-byte bf16 rows) into a 3-deep
@@ -154,9 +153,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t (&v)[4]) {
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+               ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st2u(uint32_t taddr, uint32_t v0, uint32_t v1) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(v0), "r"(v1) : "memory");
 }
 // two floats -> packed bf16x2, `lo` in bits [0,16) (the lower k index), `hi` in bits [16,32)
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -527,14 +529,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   } else {
     // ===================== phasor generators =====================
     // Two warps per TMEM lane quarter: WG3 produces k-step 0 (k 0..7) of every chunk, WG4
-    // k-step 1.  Inside a warp the lane pair (2j, 2j+1) = (Re row, Im row) of phasor column j
-    // splits the 8 k's of the k-step 4 + 4 and swaps results with __shfl_xor.
+    // k-step 1.  Lane 2j (Re row of phasor column j) needs (G1, G2) = (cos, -sin), lane 2j+1
+    // (Im row) needs (sin, cos) = (cos, -sin) of the angle minus a quarter turn: every lane
+    // evaluates its own 8 phasors with an exact quadrant shift and stores (c, -s) -- no
+    // shuffles, no selects.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GEN));
     const int q = warp & 3;                          // TMEM lane quarter
     const int ks = (warp - FIRST_GEN_WARP) >> 2;     // which k-step of the chunk
-    const bool odd = (lane & 1) != 0;                // odd lane = imaginary row of the phasor column
+    const int qshift = (lane & 1) ? -1 : 0;          // odd lane = imaginary row of the phasor column
     const int jcol = (q * 32 + lane) >> 1;           // phasor column within the tile
-    const int ksub = ks * UMMA_K + (odd ? 4 : 0);    // my 4 k's inside the chunk
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int stage = 0;
     uint32_t phase = 0;
@@ -544,52 +547,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       const int n = (t / tp.tiles_mp) * NB + jcol;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
       const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
-      float xk[4];  // this chunk's k coordinates, prefetched one chunk ahead
+      float xk[8];  // this chunk's k coordinates (warp-uniform), prefetched one chunk ahead
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xk[j] = (ksub + j < p.K) ? __ldg(kv + ksub + j) : 0.0f;
+      for (int j = 0; j < 8; ++j) xk[j] = (ks * UMMA_K + j < p.K) ? __ldg(kv + ks * UMMA_K + j) : 0.0f;
       for (int kc = 0; kc < tp.k_chunks; ++kc) {
-        float xn[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = (kc + 1) * BK + ksub + j;
-          xn[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
-        }
-        float g1h[8], g1l[8], g2h[8], g2l[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float sn, cs;
-#ifdef DLUX_DEBUG_NOGEN
-          sn = xk[j]; cs = u;
-#else
-          fast_sincos(phase_arg(p.sign2pi, xk[j], u), &sn, &cs);
-#endif
-          xk[j] = xn[j];
-          const float ch = tf32_hi(cs), sh = tf32_hi(sn);
-          const float cl = cs - ch, sl = sn - sh;
-          const float pch = __shfl_xor_sync(0xffffffffu, ch, 1), pcl = __shfl_xor_sync(0xffffffffu, cl, 1);
-          const float psh = __shfl_xor_sync(0xffffffffu, sh, 1), psl = __shfl_xor_sync(0xffffffffu, sl, 1);
-          // k order inside the k-step: the even lane computed k 0..3, the odd lane k 4..7.
-          // even lane (Re row): G1 = cos, G2 = -sin; odd lane (Im row): G1 = sin, G2 = cos
-          g1h[j] = odd ? psh : ch;      g1l[j] = odd ? psl : cl;
-          g2h[j] = odd ? pch : -sh;     g2l[j] = odd ? pcl : -sl;
-          g1h[4 + j] = odd ? sh : pch;  g1l[4 + j] = odd ? sl : pcl;
-          g2h[4 + j] = odd ? ch : -psh; g2l[4 + j] = odd ? cl : -psl;
-        }
-        uint32_t pk[4][4];  // packed bf16: G1_hi, G1_lo, G2_hi, G2_lo, 8 k -> 4 columns each
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          pk[0][j] = pack_bf16(g1h[2 * j], g1h[2 * j + 1]);
-          pk[1][j] = pack_bf16(g1l[2 * j], g1l[2 * j + 1]);
-          pk[2][j] = pack_bf16(g2h[2 * j], g2h[2 * j + 1]);
-          pk[3][j] = pack_bf16(g2l[2 * j], g2l[2 * j + 1]);
-        }
         mbar_wait(emptyG_bar(stage), phase ^ 1);
         tc_fence_after();
         const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS);
-        tmem_st8(g0 + ks * UMMA_K, g1h);        // tf32 G1_hi: columns [0,16)
-        tmem_st8(g0 + BK + ks * UMMA_K, g2h);   // tf32 G2_hi: columns [16,32)
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) tmem_st4u(g0 + GB_BASE + q4 * GB_COLS + ks * (UMMA_K / 2), pk[q4]);
+        for (int half = 0; half < 2; ++half) {   // 4 k at a time keeps the register footprint small
+          float g1h[4], g2h[4], g1l[4], g2l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float sn, cs;
+#ifdef DLUX_DEBUG_NOGEN
+            sn = xk[4 * half + e]; cs = u;
+#else
+            fast_sincos_mufu(phase_arg(p.sign2pi, xk[4 * half + e], u), qshift, &sn, &cs);
+#endif
+            g1h[e] = tf32_hi(cs);
+            g1l[e] = cs - g1h[e];
+            g2h[e] = tf32_hi(-sn);
+            g2l[e] = -sn - g2h[e];
+          }
+          const uint32_t kcol = ks * UMMA_K + 4 * half;
+          tmem_st4(g0 + kcol, g1h);        // tf32 G1_hi: columns [0,16)
+          tmem_st4(g0 + BK + kcol, g2h);   // tf32 G2_hi: columns [16,32)
+          const uint32_t bcol = g0 + GB_BASE + (kcol >> 1);  // packed bf16: 2 k per column
+          tmem_st2u(bcol + 0 * GB_COLS, pack_bf16(g1h[0], g1h[1]), pack_bf16(g1h[2], g1h[3]));
+          tmem_st2u(bcol + 1 * GB_COLS, pack_bf16(g1l[0], g1l[1]), pack_bf16(g1l[2], g1l[3]));
+          tmem_st2u(bcol + 2 * GB_COLS, pack_bf16(g2h[0], g2h[1]), pack_bf16(g2h[2], g2h[3]));
+          tmem_st2u(bcol + 3 * GB_COLS, pack_bf16(g2l[0], g2l[1]), pack_bf16(g2l[2], g2l[3]));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // next chunk's coordinates
+          const int k = (kc + 1) * BK + ks * UMMA_K + j;
+          xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
