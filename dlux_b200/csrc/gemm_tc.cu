@@ -30,6 +30,9 @@
 //   tile's epilogue warpgroup with tcgen05.ld and added, round-to-nearest, into fp32
 //   registers (Ootomo & Yokota's scheme for error-corrected TF32 GEMM).  Draining overlaps
 //   the MMAs of the other tile / next partial.
+// * CTA pairs (thread-block clusters of 2) work on the same data rows and neighbouring
+//   n-tiles: each CTA fetches one of the two data tiles of a stage and TMA-multicasts it to
+//   both, halving the L2 -> SM traffic that bounded the single-CTA version (ncu: 8.9 TB/s).
 // * Persistent CTAs, one per SM, 20 warps in 5 warpgroups: WG0 / WG1 = drain + fused
 //   epilogue of tile a / b (setmaxnreg.inc: 128 running totals per thread), WG2 = TMA
 //   producer + MMA issuer (setmaxnreg.dec), WG3 / WG4 = phasor generators (two warps per TMEM
@@ -77,6 +80,7 @@ constexpr int REGS_LAUNCH = 96;    // 65536 / 640 rounded down to a multiple of 
 constexpr int REGS_EPI = 152, REGS_CTRL = 40, REGS_GEN = 64;        // setmaxnreg budgets
 static_assert(256 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_GEN),
               "register budget");
+constexpr int CLUSTER = 2;         // CTAs sharing (multicasting) the data tiles
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 2560 /*epilogue staging*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
@@ -119,6 +123,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem]   (A: 128 lanes x 8 columns of tf32, K-major)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
                                              uint32_t idesc, uint32_t accumulate) {
@@ -157,8 +181,9 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
-__device__ __forceinline__ void tmem_st2u(uint32_t taddr, uint32_t v0, uint32_t v1) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(v0), "r"(v1) : "memory");
+__device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 // two floats -> packed bf16x2, `lo` in bits [0,16) (the lower k index), `hi` in bits [16,32)
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -340,7 +365,7 @@ __device__ __forceinline__ PartialSchedule partial_schedule(int kc, int k_chunks
 
 struct TcParams {
   GemmParams g;
-  int tiles_mp, tiles_n, n_units, k_chunks;  // tiles_mp: pairs of 128-row data tiles
+  int tiles_mp, tiles_np, n_units, k_chunks;  // pairs of 128-row data tiles, pairs of 64-column n-tiles
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -375,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   if (warp == WARP_MMA && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(fullA_bar(s), 1);   // TMA producer's arrive.expect_tx
-      mbar_init(emptyA_bar(s), 1);  // tcgen05.commit
+      mbar_init(emptyA_bar(s), CLUSTER);  // tcgen05.commit of every CTA of the cluster (multicast)
     }
     for (int s = 0; s < G_STAGES; ++s) {
       mbar_init(fullG_bar(s), NUM_GEN_WARPS);  // one arrive per generator warp
@@ -394,11 +419,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = cluster_ctarank();
+  const int cl_id = blockIdx.x / CLUSTER, n_cl = gridDim.x / CLUSTER;
 
-  // work unit = (item, n-tile, pair of m-tiles)
-  const int units_per_item = tp.tiles_mp * tp.tiles_n;
+  // cluster work unit = (item, pair of n-tiles, pair of m-tiles); CTA `crank` of the cluster
+  // takes n-tile 2 * np + crank (an n-tile beyond the matrix computes on zeros and stores
+  // nothing)
+  const int units_per_item = tp.tiles_mp * tp.tiles_np;
   const int n_partials = (tp.k_chunks + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS;
 
   // Register re-balancing between warpgroups: setmaxnreg is the first instruction of each
@@ -409,7 +439,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
+      for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
         const int item = unit / units_per_item;
         const int t = unit % units_per_item;
         const int m0 = (t % tp.tiles_mp) * (2 * BM);
@@ -420,16 +450,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             const uint32_t dst = smem_base + stage * A_BYTES;
             const uint32_t bar = fullA_bar(stage);
             mbar_arrive_expect_tx(bar, A_BYTES);
-#pragma unroll
-            for (int tb = 0; tb < 2; ++tb) {  // tile a, tile b (rows beyond the matrix are zero-filled)
-              const uint32_t t0 = dst + tb * TILE_BYTES;
-              const int mr = m0 + tb * BM;
-              tma_load_3d(t0 + 0 * PLANE_BYTES, &map0, bar, kc * BK, mr, d);   // tf32 hi: re, im
-              tma_load_3d(t0 + 1 * PLANE_BYTES, &map1, bar, kc * BK, mr, d);
-              tma_load_3d(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, bar, kc * BK, mr, d);  // bf16: re_hi, re_lo,
-              tma_load_3d(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, bar, kc * BK, mr, d);  //       im_hi, im_lo
-              tma_load_3d(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, bar, kc * BK, mr, d);
-              tma_load_3d(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, bar, kc * BK, mr, d);
+            {  // I fetch tile `crank` (a or b) of the stage and multicast it to both CTAs; the
+               // peer does the same with the other tile (rows beyond the matrix are zero-filled)
+              const uint32_t t0 = dst + crank * TILE_BYTES;
+              const int mr = m0 + (int)crank * BM;
+              constexpr uint16_t MASK = (1u << CLUSTER) - 1;
+              tma_load_3d_mc(t0 + 0 * PLANE_BYTES, &map0, bar, kc * BK, mr, d, MASK);   // tf32 hi: re, im
+              tma_load_3d_mc(t0 + 1 * PLANE_BYTES, &map1, bar, kc * BK, mr, d, MASK);
+              tma_load_3d_mc(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, bar, kc * BK, mr, d, MASK);  // bf16
+              tma_load_3d_mc(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, bar, kc * BK, mr, d, MASK);
+              tma_load_3d_mc(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, bar, kc * BK, mr, d, MASK);
+              tma_load_3d_mc(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, bar, kc * BK, mr, d, MASK);
             }
           }
           __syncwarp();
@@ -443,7 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       uint32_t pa = 0, pg = 0;
       uint32_t take = 0;         // running count of partial-accumulator acquisitions; buffer = take % 3
       uint32_t ta = 0, tb = 0;   // acquisition numbers of the open partials of tiles a and b
-      for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
+      for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           // Partials are FLUSH_CHUNKS long; tile b's boundaries are staggered by half a partial so
           // that the three TMEM buffers are re-acquired >= 2 chunks after they were handed to a
@@ -470,7 +501,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           if (elect_one()) {
             issue_tile_chunk(tmem_base + (tb % NUM_ACC) * ACC_COLS, g0, smem_base + sa * A_BYTES + TILE_BYTES,
                              ps.b_open);
-            umma_commit(emptyA_bar(sa));  // free the smem slot and the phasor stage when these MMAs retire
+            umma_commit_mc(emptyA_bar(sa), (1u << CLUSTER) - 1);  // smem slot: released in both CTAs
+            // ... and the phasor stage, when these MMAs retire
             umma_commit(emptyG_bar(sg));
             if (ps.b_close) umma_commit(tfull_bar(tb % NUM_ACC));  // tile b's partial complete -> WG1
           }
@@ -487,11 +519,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     const int which = warp >> 2;     // 0: tile a, 1: tile b
     uint32_t take = 0, ta = 0, tb = 0;  // mirrors the MMA issuer's acquisition counter
     float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256 + warp * STG_BYTES);
-    for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
+    for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
       const int item = unit / units_per_item;
       const int t = unit % units_per_item;
       const int m0 = (t % tp.tiles_mp) * (2 * BM) + which * BM;
-      const int nq0 = (t / tp.tiles_mp) * NB + q * 16;  // first output row of this warp's lane quarter
+      const int nq0 = ((t / tp.tiles_mp) * CLUSTER + (int)crank) * NB + q * 16;  // first output row of this warp's lane quarter
       float tot[BM];
 #pragma unroll
       for (int j = 0; j < BM; ++j) tot[j] = 0.0f;
@@ -541,49 +573,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int stage = 0;
     uint32_t phase = 0;
-    for (int unit = blockIdx.x; unit < tp.n_units; unit += gridDim.x) {
+    for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
       const int item = unit / units_per_item;
       const int t = unit % units_per_item;
-      const int n = (t / tp.tiles_mp) * NB + jcol;
+      const int n = ((t / tp.tiles_mp) * CLUSTER + (int)crank) * NB + jcol;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
       const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
       float xk[8];  // this chunk's k coordinates (warp-uniform), prefetched one chunk ahead
 #pragma unroll
       for (int j = 0; j < 8; ++j) xk[j] = (ks * UMMA_K + j < p.K) ? __ldg(kv + ks * UMMA_K + j) : 0.0f;
       for (int kc = 0; kc < tp.k_chunks; ++kc) {
-        mbar_wait(emptyG_bar(stage), phase ^ 1);
-        tc_fence_after();
-        const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS);
+        // Evaluate into registers first, THEN wait for the TMEM stage: with only two phasor
+        // stages the evaluation must overlap the MMAs that still read the stage.
+        float g1h[8], g2h[8];
+        uint32_t pk[4][4];  // packed bf16: G1_hi, G1_lo, G2_hi, G2_lo, 8 k -> 4 columns each
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {   // 4 k at a time keeps the register footprint small
-          float g1h[4], g2h[4], g1l[4], g2l[4];
+        for (int jj = 0; jj < 4; ++jj) {
+          float g1l2[2], g2l2[2];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * jj + e;
             float sn, cs;
 #ifdef DLUX_DEBUG_NOGEN
-            sn = xk[4 * half + e]; cs = u;
+            sn = xk[j]; cs = u;
 #else
-            fast_sincos_mufu(phase_arg(p.sign2pi, xk[4 * half + e], u), qshift, &sn, &cs);
+            fast_sincos_mufu(phase_arg(p.sign2pi, xk[j], u), qshift, &sn, &cs);
 #endif
-            g1h[e] = tf32_hi(cs);
-            g1l[e] = cs - g1h[e];
-            g2h[e] = tf32_hi(-sn);
-            g2l[e] = -sn - g2h[e];
+            g1h[j] = tf32_hi(cs);
+            g1l2[e] = cs - g1h[j];
+            g2h[j] = tf32_hi(-sn);
+            g2l2[e] = -sn - g2h[j];
           }
-          const uint32_t kcol = ks * UMMA_K + 4 * half;
-          tmem_st4(g0 + kcol, g1h);        // tf32 G1_hi: columns [0,16)
-          tmem_st4(g0 + BK + kcol, g2h);   // tf32 G2_hi: columns [16,32)
-          const uint32_t bcol = g0 + GB_BASE + (kcol >> 1);  // packed bf16: 2 k per column
-          tmem_st2u(bcol + 0 * GB_COLS, pack_bf16(g1h[0], g1h[1]), pack_bf16(g1h[2], g1h[3]));
-          tmem_st2u(bcol + 1 * GB_COLS, pack_bf16(g1l[0], g1l[1]), pack_bf16(g1l[2], g1l[3]));
-          tmem_st2u(bcol + 2 * GB_COLS, pack_bf16(g2h[0], g2h[1]), pack_bf16(g2h[2], g2h[3]));
-          tmem_st2u(bcol + 3 * GB_COLS, pack_bf16(g2l[0], g2l[1]), pack_bf16(g2l[2], g2l[3]));
+          pk[0][jj] = pack_bf16(g1h[2 * jj], g1h[2 * jj + 1]);
+          pk[1][jj] = pack_bf16(g1l2[0], g1l2[1]);
+          pk[2][jj] = pack_bf16(g2h[2 * jj], g2h[2 * jj + 1]);
+          pk[3][jj] = pack_bf16(g2l2[0], g2l2[1]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // next chunk's coordinates
+        for (int j = 0; j < 8; ++j) {  // next chunk's coordinates (latency hidden behind the wait)
           const int k = (kc + 1) * BK + ks * UMMA_K + j;
           xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
         }
+        mbar_wait(emptyG_bar(stage), phase ^ 1);
+        tc_fence_after();
+        const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS);
+        tmem_st8(g0 + ks * UMMA_K, g1h);        // tf32 G1_hi: columns [0,16)
+        tmem_st8(g0 + BK + ks * UMMA_K, g2h);   // tf32 G2_hi: columns [16,32)
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) tmem_st4u(g0 + GB_BASE + q4 * GB_COLS + ks * (UMMA_K / 2), pk[q4]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -595,6 +632,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // no CTA exits while its peer may still multicast into it
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
@@ -672,13 +710,30 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   TcParams tp;
   tp.g = p;
   tp.tiles_mp = (p.rows + 2 * BM - 1) / (2 * BM);
-  tp.tiles_n = (p.n_out + NB - 1) / NB;
-  const long long total = (long long)tp.tiles_mp * tp.tiles_n * p.n_items;
+  tp.tiles_np = (p.n_out + CLUSTER * NB - 1) / (CLUSTER * NB);
+  const long long total = (long long)tp.tiles_mp * tp.tiles_np * p.n_items;
   if (total > 2147483647LL) return DLUX_ERR_SHAPE;
   tp.n_units = (int)total;
   tp.k_chunks = (p.K + BK - 1) / BK;
-  const int grid = tp.n_units < s.num_sms ? tp.n_units : s.num_sms;
-  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], tp);
+  const int max_clusters = s.num_sms / CLUSTER;
+  const int n_clusters = tp.n_units < max_clusters ? tp.n_units : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_clusters * CLUSTER);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], tp);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
+    return DLUX_ERR_CUDA;
+  }
   note_launch();
   return check_launch("gemm_tc");
 }
