@@ -35,7 +35,7 @@
 //   both, halving the L2 -> SM traffic that bounded the single-CTA version (ncu: 8.9 TB/s).
 // * Persistent CTAs, one per SM, 20 warps in 5 warpgroups: WG0 / WG1 = drain + fused
 //   epilogue of tile a / b (setmaxnreg.inc: 128 running totals per thread), WG2 = TMA
-//   producer + MMA issuer (setmaxnreg.dec), WG3 / WG4 = phasor generators (two warps per TMEM
+//   producer + one MMA issuer warp per tile (setmaxnreg.dec), WG3 / WG4 = phasor generators (two warps per TMEM
 //   lane quarter, one per k-step of the chunk).
 // TMEM map (512 columns): [0,384) three partial accumulators, [384,512) two phasor stages
 // of 64 columns: G1_hi, G2_hi as tf32 (16 k -> 16 columns each) and G1_hi, G1_lo, G2_hi,
@@ -400,11 +400,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   if (warp == WARP_MMA && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(fullA_bar(s), 1);   // TMA producer's arrive.expect_tx
-      mbar_init(emptyA_bar(s), CLUSTER);  // tcgen05.commit of every CTA of the cluster (multicast)
+      mbar_init(emptyA_bar(s), 2 * CLUSTER);  // tcgen05.commit of both issuer warps of every CTA of the cluster
     }
     for (int s = 0; s < G_STAGES; ++s) {
       mbar_init(fullG_bar(s), NUM_GEN_WARPS);  // one arrive per generator warp
-      mbar_init(emptyG_bar(s), 1);             // tcgen05.commit
+      mbar_init(emptyG_bar(s), 2);             // tcgen05.commit of both issuer warps
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);     // tcgen05.commit closing a partial
@@ -467,44 +467,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == WARP_MMA) {
-      // ===================== MMA issuer =====================
-      // The whole warp walks the loop (uniform control flow); one elected lane issues.
+    } else if (warp == WARP_MMA || warp == WARP_MMA + 1) {
+      // ===================== MMA issuers: warp WARP_MMA -> tile a, WARP_MMA + 1 -> tile b =====================
+      // One issuing warp per tile halves the (scalar, latency-bound) instruction stream that
+      // sits between consecutive tcgen05.mma's.  The whole warp walks the loop (uniform control
+      // flow); one elected lane issues.  Both warps mirror the same acquisition sequence of the
+      // three TMEM partial buffers (order inside a chunk: a, then b).
+      const int which = warp - WARP_MMA;
       int sa = 0, sg = 0;
       uint32_t pa = 0, pg = 0;
-      uint32_t take = 0;         // running count of partial-accumulator acquisitions; buffer = take % 3
-      uint32_t ta = 0, tb = 0;   // acquisition numbers of the open partials of tiles a and b
+      uint32_t nbuf = 0, nphase = 0;      // next buffer to acquire and the parity of its use count
+      uint32_t mybuf = 0, myphase = 0;    // my open partial
       for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           // Partials are FLUSH_CHUNKS long; tile b's boundaries are staggered by half a partial so
           // that the three TMEM buffers are re-acquired >= 2 chunks after they were handed to a
           // drain warpgroup (see partial_schedule()).
           const PartialSchedule ps = partial_schedule(kc, tp.k_chunks);
+          bool opened = false;
+          if (ps.a_open) {
+            if (which == 0) { mybuf = nbuf; myphase = nphase; opened = true; }
+            if (++nbuf == NUM_ACC) { nbuf = 0; nphase ^= 1; }
+          }
+          if (ps.b_open) {
+            if (which == 1) { mybuf = nbuf; myphase = nphase; opened = true; }
+            if (++nbuf == NUM_ACC) { nbuf = 0; nphase ^= 1; }
+          }
           mbar_wait(fullG_bar(sg), pg);
           mbar_wait(fullA_bar(sa), pa);
-          if (ps.a_open) {
-            ta = take++;
-            mbar_wait(tempty_bar(ta % NUM_ACC), ((ta / NUM_ACC) & 1) ^ 1);
-          }
+          if (opened) mbar_wait(tempty_bar(mybuf), myphase ^ 1);  // my drain warpgroup released the buffer
           tc_fence_after();
-          const uint32_t g0 = tmem_base + (uint32_t)(G_BASE_COL + sg * G_COLS);
           if (elect_one()) {
-            issue_tile_chunk(tmem_base + (ta % NUM_ACC) * ACC_COLS, g0, smem_base + sa * A_BYTES, ps.a_open);
-            if (ps.a_close) umma_commit(tfull_bar(ta % NUM_ACC));  // tile a's partial complete -> WG0
-          }
-          __syncwarp();
-          if (ps.b_open) {
-            tb = take++;
-            mbar_wait(tempty_bar(tb % NUM_ACC), ((tb / NUM_ACC) & 1) ^ 1);
-            tc_fence_after();
-          }
-          if (elect_one()) {
-            issue_tile_chunk(tmem_base + (tb % NUM_ACC) * ACC_COLS, g0, smem_base + sa * A_BYTES + TILE_BYTES,
-                             ps.b_open);
-            umma_commit_mc(emptyA_bar(sa), (1u << CLUSTER) - 1);  // smem slot: released in both CTAs
-            // ... and the phasor stage, when these MMAs retire
+            issue_tile_chunk(tmem_base + mybuf * ACC_COLS, tmem_base + (uint32_t)(G_BASE_COL + sg * G_COLS),
+                             smem_base + sa * A_BYTES + which * TILE_BYTES, opened);
+            // when these MMAs retire: smem slot released in both CTAs, phasor stage released
+            // (each barrier also counts the other issuer warp's commit), partial handed over
+            umma_commit_mc(emptyA_bar(sa), (1u << CLUSTER) - 1);
             umma_commit(emptyG_bar(sg));
-            if (ps.b_close) umma_commit(tfull_bar(tb % NUM_ACC));  // tile b's partial complete -> WG1
+            if (which ? ps.b_close : ps.a_close) umma_commit(tfull_bar(mybuf));
           }
           __syncwarp();
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
@@ -517,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int which = warp >> 2;     // 0: tile a, 1: tile b
-    uint32_t take = 0, ta = 0, tb = 0;  // mirrors the MMA issuer's acquisition counter
+    uint32_t nbuf = 0, nphase = 0, mybuf = 0, myphase = 0;  // mirrors the MMA issuers' acquisition sequence
     float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256 + warp * STG_BYTES);
     for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
       const int item = unit / units_per_item;
@@ -529,12 +529,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       for (int j = 0; j < BM; ++j) tot[j] = 0.0f;
       for (int kc = 0; kc < tp.k_chunks; ++kc) {
         const PartialSchedule ps = partial_schedule(kc, tp.k_chunks);
-        if (ps.a_open) ta = take++;
-        if (ps.b_open) tb = take++;
+        if (ps.a_open) {
+          if (which == 0) { mybuf = nbuf; myphase = nphase; }
+          if (++nbuf == NUM_ACC) { nbuf = 0; nphase ^= 1; }
+        }
+        if (ps.b_open) {
+          if (which == 1) { mybuf = nbuf; myphase = nphase; }
+          if (++nbuf == NUM_ACC) { nbuf = 0; nphase ^= 1; }
+        }
         if (!(which ? ps.b_close : ps.a_close)) continue;
-        const uint32_t mine = which ? tb : ta;
-        const uint32_t buf = mine % NUM_ACC;
-        mbar_wait(tfull_bar(buf), (mine / NUM_ACC) & 1);
+        const uint32_t buf = mybuf;
+        mbar_wait(tfull_bar(buf), myphase);
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
 #pragma unroll
