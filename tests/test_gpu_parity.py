@@ -284,6 +284,31 @@ def test_point_sources_position_and_flux_gradients(dev, prec):
     assert rel_l2(pos.grad.cpu().numpy(), pos_r.grad.numpy()) < 5e-5   # position: float32 tilt scale 1e-7 rad
 
 
+def test_config4_like_large_pupil_many_sources(dev):
+    # BASELINE config 4 shape (scaled down in sources/wavelengths): 2048 px pupil with a binary
+    # 0/pi phase mask, several stars, MFT to 256x256
+    import dlux_b200 as dl
+    N, M = 2048, 256
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[:N, :N]
+    r = np.hypot(xx - (N - 1) / 2, yy - (N - 1) / 2) / (N / 2)
+    T = (r <= 1).astype(np.float32)
+    f = np.fft.fft2(rng.standard_normal((N, N)))
+    f[40:-40, :] = 0
+    f[:, 40:-40] = 0
+    phase = (np.pi * (np.fft.ifft2(f).real > 0)).astype(np.float32)
+    od = dict(wf_npixels=N, diameter=0.125, psf_npixels=M, psf_pixel_scale=0.7, oversample=1,
+              transmission=T, phase=phase, normalise=True)
+    wls = np.linspace(5.3e-7, 6.4e-7, 3).astype(np.float32)
+    pos = (rng.uniform(-0.35, 0.35, (3, 2)) * M * O.arcsec2rad(0.7)).astype(np.float32)
+    flux = np.array([1.0, 30.0, 500.0], np.float32)
+    layer = dl.Optic(T, None, phase, normalise=True, device=dev)
+    sys_ = dl.AngularOpticalSystem(N, 0.125, [("mask", layer)], M, 0.7, device=dev)
+    psf = sys_.model(dl.PointSources(wls, pos, flux))
+    ref = O.point_sources_model(od, wls, pos, flux)
+    assert rel_l2(psf.cpu().numpy(), ref) < TOL
+
+
 def test_multi_chunk_paths(dev):
     # force the item-chunk loops (DLUX_B200_CHUNK_MB is read once per process, so run a child)
     import subprocess, sys, os, textwrap
