@@ -204,12 +204,16 @@ def run_ours(args):
     grad_h = torch.empty(nz, dtype=torch.float32).pin_memory()
     from dlux_b200 import distributed as D
 
+    # the model is built once (as in a fitting loop); every step gets new coefficients and a new
+    # image-plane cotangent from the host
+    e2e_layer = dl.BasisOptic(basis_d, T_d, coeffs_d, "opd", normalise=True, device=dev)
+    optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("pupil", e2e_layer)], cfg["psf_npixels"],
+                                     cfg["psf_pixel_scale"], cfg["oversample"], device=dev)
+
     def step_e2e():
         c = coeffs_h.to(dev, non_blocking=True).requires_grad_(True)
         G = G_h.to(dev, non_blocking=True)
-        layer = dl.BasisOptic(basis_d, T_d, c, "opd", normalise=True, device=dev)
-        optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("pupil", layer)], cfg["psf_npixels"],
-                                         cfg["psf_pixel_scale"], cfg["oversample"], device=dev)
+        e2e_layer.coefficients = c
         # PointSources(world stars).model(optics), sources sharded one per rank + NCCL all-reduce
         psf = D.sharded_point_sources_model(optics, cfg["wavelengths"], all_positions, all_fluxes,
                                             cfg["weights"])

@@ -176,11 +176,23 @@ class _FocalSystem(LayeredOpticalSystem):
         return T, opd, phase, normalise
 
     def _geometry(self, wavelengths):
+        """Per-wavelength device operands (wavenumber, scale_out, norm, wavelengths), cached:
+        a fitting loop calls propagate with the same wavelength grid every step."""
         npix, ps, fl = self._focal_args()
-        ps_in = np.float32(self.diameter / np.float32(self.wf_npixels))
-        scale_out, norm = _prop.mft_geometry(wavelengths, self.wf_npixels, ps_in, npix, ps, fl)
-        k = (np.float32(2 * math.pi) / wavelengths).astype(np.float32)
-        return npix, scale_out.astype(np.float32), norm.astype(np.float32), k
+        key = (wavelengths.tobytes(), npix, float(ps), None if fl is None else float(fl),
+               float(self.diameter), self.wf_npixels, str(self.device))
+        cache = self.__dict__.setdefault("_geom_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            ps_in = np.float32(self.diameter / np.float32(self.wf_npixels))
+            scale_out, norm = _prop.mft_geometry(wavelengths, self.wf_npixels, ps_in, npix, ps, fl)
+            k = (np.float32(2 * math.pi) / wavelengths).astype(np.float32)
+            up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=self.device)
+            hit = (npix, up(scale_out), up(norm), up(k), up(wavelengths))
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = hit
+        return hit
 
     def fused_propagate(self, wavelengths, offsets, weights):
         """psf = sum_{s,l} weights[s,l] |E_sl|^2 in one fused call.
@@ -191,18 +203,18 @@ class _FocalSystem(LayeredOpticalSystem):
         T, opd, phase, normalise = parts
         dev = self.device
         wavelengths = np.atleast_1d(_np32(wavelengths))
-        npix, scale_out, norm, k = self._geometry(wavelengths)
+        npix, scale_out, norm, k, wl_dev = self._geometry(wavelengths)
         up = lambda a: torch.as_tensor(a, device=dev)
         offsets_t = offsets.to(dev, torch.float32) if torch.is_tensor(offsets) else up(_np32(offsets))
         offsets_t = offsets_t.reshape(-1, 2)
         # tilt (wavefronts.py:370-395) folded into the output coordinates:
         # delta = theta * D / lambda, in fringes
-        delta = (offsets_t[:, None, :] * self.diameter) / up(wavelengths)[None, :, None]
+        delta = (offsets_t[:, None, :] * self.diameter) / wl_dev[None, :, None]
         weights_t = weights.to(dev, torch.float32) if torch.is_tensor(weights) else up(_np32(weights))
         weights_t = weights_t.reshape(offsets_t.shape[0], len(wavelengths))
         cont = lambda t: None if t is None else t.contiguous()
         return ops.PolyPSFFunction.apply(cont(opd), cont(phase), weights_t.contiguous(), delta.contiguous(),
-                                         cont(T), up(k), up(scale_out), up(norm), self.wf_npixels,
+                                         cont(T), k, scale_out, norm, self.wf_npixels,
                                          npix, normalise, self.precision)
 
     def _propagate(self, wavelengths, offset, weights, return_wf):
