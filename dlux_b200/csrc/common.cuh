@@ -57,10 +57,11 @@ struct GemmParams {
   float2* out_c64;       // EPI_C64: [n_items][n_out][rows]
 };
 
+// round-to-nearest (ties away from zero) to tf32's 10 mantissa bits.  Equivalent to
+// cvt.rna.tf32.f32 for finite inputs; spelled with integer ops because sm_100a expands that
+// cvt into a ~5-instruction sequence and the hot loops do it twice per phasor / output.
 __device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // Reference phase argument: two float32 multiplies, no fused contraction.

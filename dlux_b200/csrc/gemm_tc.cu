@@ -81,6 +81,11 @@ constexpr int REGS_EPI = 152, REGS_CTRL = 40, REGS_GEN = 64;        // setmaxnre
 static_assert(256 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_GEN),
               "register budget");
 constexpr int CLUSTER = 2;         // CTAs sharing (multicasting) the data tiles
+#ifdef DLUX_NO_MULTICAST
+constexpr bool MULTICAST = false;  // A/B switch: every CTA loads both tiles itself
+#else
+constexpr bool MULTICAST = true;
+#endif
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 2560 /*epilogue staging*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
@@ -252,41 +257,49 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
                                               float (&tot)[BM], float* stg) {
   const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
   const int mmax = p.rows - m0;  // tile columns c < mmax are valid
+  if (p.mode == EPI_PLANES) {
+    // read-back mapping: lane -> staging rows r = lane/4 + 8*it (it = 0..3), 4 columns at
+    // 4*(lane%4).  r & 1 (real / imaginary row) does not depend on `it`; the output row
+    // advances by 4 per `it`: base pointers are formed once per tile.
+    const int cc = 4 * (lane & 3);
+    const int part = (lane >> 2) & 1;
+    const int n_first = nq0 + (lane >> 3);
+    const int p4 = pitch4(p.rows), p8 = pitch8(p.rows);
+    const size_t row0 = (size_t)item * p.n_out + n_first;
+    float* hp0 = p.out.hi[part] + row0 * p4 + m0 + cc;
+    __nv_bfloat16* hb0 = p.out.b[2 * part] + row0 * p8 + m0 + cc;
+    __nv_bfloat16* lb0 = p.out.b[2 * part + 1] + row0 * p8 + m0 + cc;
 #pragma unroll
-  for (int s = 0; s < BM / STG_COLS; ++s) {
-    const int c0 = s * STG_COLS;
+    for (int s = 0; s < BM / STG_COLS; ++s) {
+      const int c0 = s * STG_COLS;
 #pragma unroll
-    for (int v = 0; v < STG_COLS / 4; ++v)
-      *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * v) =
-          make_float4(tot[c0 + 4 * v] * sc, tot[c0 + 4 * v + 1] * sc, tot[c0 + 4 * v + 2] * sc,
-                      tot[c0 + 4 * v + 3] * sc);
-    __syncwarp();
-    if (c0 < mmax) {  // warp-uniform
-      if (p.mode == EPI_PLANES) {
-        // lane -> staging rows r = lane/4 + 8*it (it = 0..3), 4 columns at 4*(lane%4)
-        const int cc = 4 * (lane & 3);
+      for (int v = 0; v < STG_COLS / 4; ++v)
+        *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * v) =
+            make_float4(tot[c0 + 4 * v] * sc, tot[c0 + 4 * v + 1] * sc, tot[c0 + 4 * v + 2] * sc,
+                        tot[c0 + 4 * v + 3] * sc);
+      __syncwarp();
+      if (c0 < mmax) {  // warp-uniform
+        float4 v[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          v[it] = *reinterpret_cast<const float4*>(stg + ((lane >> 2) + 8 * it) * STG_PITCH + cc);
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int r = (lane >> 2) + 8 * it;
-          const int n = nq0 + (r >> 1);
-          const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + cc);
-          if (n < p.n_out) {
+          if (n_first + 4 * it < p.n_out) {
             float4 h;
-            h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-            const size_t row = (size_t)item * p.n_out + n;
-            const int col = m0 + c0 + cc;  // multiple of 4
-            float* hp = p.out.hi[r & 1] + row * pitch4(p.rows) + col;
-            __nv_bfloat16* hb = p.out.b[(r & 1) * 2] + row * pitch8(p.rows) + col;
-            __nv_bfloat16* lb = p.out.b[(r & 1) * 2 + 1] + row * pitch8(p.rows) + col;
-            if (c0 + cc + 4 <= mmax) {
+            h.x = tf32_hi(v[it].x); h.y = tf32_hi(v[it].y); h.z = tf32_hi(v[it].z); h.w = tf32_hi(v[it].w);
+            float* hp = hp0 + (size_t)(4 * it) * p4 + c0;
+            __nv_bfloat16* hb = hb0 + (size_t)(4 * it) * p8 + c0;
+            __nv_bfloat16* lb = lb0 + (size_t)(4 * it) * p8 + c0;
+            if (c0 + cc + 4 <= mmax) {  // pitches, m0, c0, cc are multiples of 4: aligned vector stores
               *reinterpret_cast<float4*>(hp) = h;
               uint2 wh, wl;
               wh.x = pack_bf16(h.x, h.y); wh.y = pack_bf16(h.z, h.w);
-              wl.x = pack_bf16(v.x - h.x, v.y - h.y); wl.y = pack_bf16(v.z - h.z, v.w - h.w);
+              wl.x = pack_bf16(v[it].x - h.x, v[it].y - h.y); wl.y = pack_bf16(v[it].z - h.z, v[it].w - h.w);
               *reinterpret_cast<uint2*>(hb) = wh;
               *reinterpret_cast<uint2*>(lb) = wl;
             } else {
-              const float hh[4] = {h.x, h.y, h.z, h.w}, vv[4] = {v.x, v.y, v.z, v.w};
+              const float hh[4] = {h.x, h.y, h.z, h.w}, vv[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 if (c0 + cc + e < mmax) {
@@ -297,28 +310,47 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
             }
           }
         }
-      } else {  // EPI_C64
-        // lane -> output row j = lane/8 + 4*it (it = 0..3), complex pair at columns 2*(lane%8)
-        const int cc = 2 * (lane & 7);
+      }
+      __syncwarp();
+    }
+  } else {  // EPI_C64
+    // lane -> output row j = lane/8 + 4*it (it = 0..3), complex pair at columns 2*(lane%8)
+    const int cc = 2 * (lane & 7);
+    const int j0 = lane >> 3;
+    const bool vec = (p.rows & 1) == 0;  // 16-byte alignment of (n * rows + even column) complex pairs
+    float2* out0 = p.out_c64 + ((size_t)item * p.n_out + nq0 + j0) * p.rows + m0 + cc;
+#pragma unroll
+    for (int s = 0; s < BM / STG_COLS; ++s) {
+      const int c0 = s * STG_COLS;
+#pragma unroll
+      for (int v = 0; v < STG_COLS / 4; ++v)
+        *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * v) =
+            make_float4(tot[c0 + 4 * v] * sc, tot[c0 + 4 * v + 1] * sc, tot[c0 + 4 * v + 2] * sc,
+                        tot[c0 + 4 * v + 3] * sc);
+      __syncwarp();
+      if (c0 < mmax) {  // warp-uniform
+        float2 re[4], im[4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int j = (lane >> 3) + 4 * it;
-          const int n = nq0 + j;
-          const float2 re = *reinterpret_cast<const float2*>(stg + (2 * j) * STG_PITCH + cc);
-          const float2 im = *reinterpret_cast<const float2*>(stg + (2 * j + 1) * STG_PITCH + cc);
-          if (n < p.n_out) {
-            float2* out = p.out_c64 + ((size_t)item * p.n_out + n) * p.rows + m0 + c0 + cc;
-            if (((p.rows & 1) == 0) && c0 + cc + 2 <= mmax) {
-              *reinterpret_cast<float4*>(out) = make_float4(re.x, im.x, re.y, im.y);
+          const int j = j0 + 4 * it;
+          re[it] = *reinterpret_cast<const float2*>(stg + (2 * j) * STG_PITCH + cc);
+          im[it] = *reinterpret_cast<const float2*>(stg + (2 * j + 1) * STG_PITCH + cc);
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          if (nq0 + j0 + 4 * it < p.n_out) {
+            float2* out = out0 + (size_t)(4 * it) * p.rows + c0;
+            if (vec && c0 + cc + 2 <= mmax) {
+              *reinterpret_cast<float4*>(out) = make_float4(re[it].x, im[it].x, re[it].y, im[it].y);
             } else {
-              if (c0 + cc < mmax) out[0] = make_float2(re.x, im.x);
-              if (c0 + cc + 1 < mmax) out[1] = make_float2(re.y, im.y);
+              if (c0 + cc < mmax) out[0] = make_float2(re[it].x, im[it].x);
+              if (c0 + cc + 1 < mmax) out[1] = make_float2(re[it].y, im[it].y);
             }
           }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -400,7 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   if (warp == WARP_MMA && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(fullA_bar(s), 1);   // TMA producer's arrive.expect_tx
-      mbar_init(emptyA_bar(s), 2 * CLUSTER);  // tcgen05.commit of both issuer warps of every CTA of the cluster
+      mbar_init(emptyA_bar(s), MULTICAST ? 2 * CLUSTER : 2);  // tcgen05.commit of both issuer warps (of every CTA of the cluster)
     }
     for (int s = 0; s < G_STAGES; ++s) {
       mbar_init(fullG_bar(s), NUM_GEN_WARPS);  // one arrive per generator warp
@@ -450,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             const uint32_t dst = smem_base + stage * A_BYTES;
             const uint32_t bar = fullA_bar(stage);
             mbar_arrive_expect_tx(bar, A_BYTES);
-            {  // I fetch tile `crank` (a or b) of the stage and multicast it to both CTAs; the
+            if (MULTICAST) {  // I fetch tile `crank` (a or b) of the stage and multicast it to both CTAs; the
                // peer does the same with the other tile (rows beyond the matrix are zero-filled)
               const uint32_t t0 = dst + crank * TILE_BYTES;
               const int mr = m0 + (int)crank * BM;
@@ -461,6 +493,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
               tma_load_3d_mc(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, bar, kc * BK, mr, d, MASK);
               tma_load_3d_mc(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, bar, kc * BK, mr, d, MASK);
               tma_load_3d_mc(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, bar, kc * BK, mr, d, MASK);
+            }
+            else {
+#pragma unroll
+              for (int tb2 = 0; tb2 < 2; ++tb2) {
+                const uint32_t t0 = dst + tb2 * TILE_BYTES;
+                const int mr = m0 + tb2 * BM;
+                tma_load_3d(t0 + 0 * PLANE_BYTES, &map0, bar, kc * BK, mr, d);
+                tma_load_3d(t0 + 1 * PLANE_BYTES, &map1, bar, kc * BK, mr, d);
+                tma_load_3d(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, bar, kc * BK, mr, d);
+                tma_load_3d(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, bar, kc * BK, mr, d);
+                tma_load_3d(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, bar, kc * BK, mr, d);
+                tma_load_3d(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, bar, kc * BK, mr, d);
+              }
             }
           }
           __syncwarp();
@@ -478,6 +523,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       uint32_t pa = 0, pg = 0;
       uint32_t nbuf = 0, nphase = 0;      // next buffer to acquire and the parity of its use count
       uint32_t mybuf = 0, myphase = 0;    // my open partial
+#ifdef DLUX_DEBUG_TIMING
+      long long dbg_g = 0, dbg_a = 0, dbg_t = 0;
+      const long long dbg_start = clock64();
+#endif
       for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           // Partials are FLUSH_CHUNKS long; tile b's boundaries are staggered by half a partial so
@@ -493,16 +542,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             if (which == 1) { mybuf = nbuf; myphase = nphase; opened = true; }
             if (++nbuf == NUM_ACC) { nbuf = 0; nphase ^= 1; }
           }
+#ifdef DLUX_DEBUG_TIMING
+          const long long t0_ = clock64();
+          mbar_wait(fullG_bar(sg), pg);
+          const long long t1_ = clock64();
+          mbar_wait(fullA_bar(sa), pa);
+          const long long t2_ = clock64();
+          if (opened) mbar_wait(tempty_bar(mybuf), myphase ^ 1);
+          const long long t3_ = clock64();
+          dbg_g += t1_ - t0_; dbg_a += t2_ - t1_; dbg_t += t3_ - t2_;
+#else
           mbar_wait(fullG_bar(sg), pg);
           mbar_wait(fullA_bar(sa), pa);
           if (opened) mbar_wait(tempty_bar(mybuf), myphase ^ 1);  // my drain warpgroup released the buffer
+#endif
           tc_fence_after();
           if (elect_one()) {
             issue_tile_chunk(tmem_base + mybuf * ACC_COLS, tmem_base + (uint32_t)(G_BASE_COL + sg * G_COLS),
                              smem_base + sa * A_BYTES + which * TILE_BYTES, opened);
             // when these MMAs retire: smem slot released in both CTAs, phasor stage released
             // (each barrier also counts the other issuer warp's commit), partial handed over
-            umma_commit_mc(emptyA_bar(sa), (1u << CLUSTER) - 1);
+            if (MULTICAST) umma_commit_mc(emptyA_bar(sa), (1u << CLUSTER) - 1);
+            else umma_commit(emptyA_bar(sa));
             umma_commit(emptyG_bar(sg));
             if (which ? ps.b_close : ps.a_close) umma_commit(tfull_bar(mybuf));
           }
@@ -511,6 +572,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           if (++sg == G_STAGES) { sg = 0; pg ^= 1; }
         }
       }
+#ifdef DLUX_DEBUG_TIMING
+      if (blockIdx.x == 0 && lane == 0)
+        printf("MMA%d K=%d rows=%d: total %lld  wait fullG %lld  fullA %lld  tempty %lld\n", which, p.K, p.rows,
+               clock64() - dbg_start, dbg_g, dbg_a, dbg_t);
+#endif
     }
   } else if (warp < NUM_EPI_WARPS) {
     // ===================== drain + epilogue (WG0: tile a, WG1: tile b) =====================
@@ -518,6 +584,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int which = warp >> 2;     // 0: tile a, 1: tile b
     uint32_t nbuf = 0, nphase = 0, mybuf = 0, myphase = 0;  // mirrors the MMA issuers' acquisition sequence
+#ifdef DLUX_DEBUG_TIMING
+    long long dbg_w = 0, dbg_e = 0, dbg_n = 0;
+    const long long dbg_start = clock64();
+#endif
     float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256 + warp * STG_BYTES);
     for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
       const int item = unit / units_per_item;
@@ -539,7 +609,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         }
         if (!(which ? ps.b_close : ps.a_close)) continue;
         const uint32_t buf = mybuf;
+#ifdef DLUX_DEBUG_TIMING
+        const long long tw0_ = clock64();
         mbar_wait(tfull_bar(buf), myphase);
+        dbg_w += clock64() - tw0_;
+#else
+        mbar_wait(tfull_bar(buf), myphase);
+#endif
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
 #pragma unroll
@@ -557,12 +633,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
       }
+#ifdef DLUX_DEBUG_TIMING
+      const long long te0_ = clock64();
+#endif
 #ifdef DLUX_DEBUG_NOEPI
       if (m0 < p.rows && tot[5] == 123.456f) tile_epilogue(p, item, nq0, m0, lane, tot, stg);
 #else
       if (m0 < p.rows) tile_epilogue(p, item, nq0, m0, lane, tot, stg);  // warp-uniform condition
 #endif
+#ifdef DLUX_DEBUG_TIMING
+      dbg_e += clock64() - te0_; ++dbg_n;
+#endif
     }
+#ifdef DLUX_DEBUG_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0)
+      printf("DRAIN%d: total %lld  wait tfull %lld  epilogue %lld  units %lld\n", which, clock64() - dbg_start, dbg_w,
+             dbg_e, dbg_n);
+#endif
   } else {
     // ===================== phasor generators =====================
     // Two warps per TMEM lane quarter: WG3 produces k-step 0 (k 0..7) of every chunk, WG4
