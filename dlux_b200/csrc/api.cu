@@ -439,8 +439,8 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
                      const float* phase, const float* wavenumber, const float* scale_out,
                      const float* norm, const float* weights, const float* delta_xy,
                      const void* field, const float* psf_bar, float* opd_bar, float* phase_bar,
-                     float* weights_bar, float* delta_bar, void* scratch, size_t scratch_bytes,
-                     void* cuda_stream) {
+                     float* weights_bar, float* delta_bar, float* transmission_bar, void* scratch,
+                     size_t scratch_bytes, void* cuda_stream) {
   int rc = check_poly_desc(d);
   if (rc != DLUX_OK) return rc;
   if (!wavenumber || !scale_out || !weights || !field || !psf_bar || !scratch) return DLUX_ERR_ARG;
@@ -457,7 +457,8 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   if (rc) return rc;
   if (weights_bar && (rc = launch_zero(weights_bar, (size_t)items, st))) return rc;
   if (delta_bar && (rc = launch_zero(delta_bar, (size_t)items * 2, st))) return rc;
-  const bool need_pupil_grad = opd_bar || phase_bar || delta_bar;
+  if (transmission_bar && !T) return DLUX_ERR_ARG;
+  const bool need_pupil_grad = opd_bar || phase_bar || delta_bar || transmission_bar;
   const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
   const int exact = d->precision == DLUX_PREC_FP32;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
@@ -487,9 +488,9 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     rc = run_gemm(h, d->precision, st);
     if (rc) return rc;
     const float a0 = 1.0f / (float)((long long)N * N);
-    if (opd_bar || phase_bar) {
+    if (opd_bar || phase_bar || transmission_bar) {
       rc = launch_grad_reduce((size_t)N * N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
-                              opd_bar, phase_bar, b0 > 0, st);
+                              opd_bar, phase_bar, transmission_bar, b0 > 0, st);
       if (rc) return rc;
     }
     if (delta_bar) {
@@ -497,6 +498,13 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
                            delta_bar + 2 * (size_t)b0, st);
       if (rc) return rc;
     }
+  }
+  if (transmission_bar && d->normalise) {
+    // amp_scale's scratch slot is followed by the 256-double work area of the power reduction
+    double* work = reinterpret_cast<double*>(reinterpret_cast<char*>(s.amp_scale) + 16);
+    rc = launch_tbar_finalize((size_t)N * N, T, s.amp_scale, 1.0f / (float)((long long)N * N),
+                              transmission_bar, work, st);
+    if (rc) return rc;
   }
   return DLUX_OK;
 }

@@ -394,14 +394,15 @@ __global__ void grad_reduce_kernel(size_t npix, int n_items, const float2* __res
                                    const float* __restrict__ opd, const float* __restrict__ phase,
                                    const float* __restrict__ amp_scale, float a0,
                                    float* __restrict__ opd_bar, float* __restrict__ phase_bar,
-                                   int accumulate) {
+                                   float* __restrict__ t_bar, int accumulate) {
   const float amp = a0 * amp_scale[0];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (size_t)gridDim.x * blockDim.x) {
     float ao = (accumulate && opd_bar) ? opd_bar[i] : 0.0f;
     float ap = (accumulate && phase_bar) ? phase_bar[i] : 0.0f;
+    float at = (accumulate && t_bar) ? t_bar[i] : 0.0f;
     const float t = T ? T[i] : 1.0f;
-    if (t != 0.0f) {
+    if (t != 0.0f || t_bar) {  // blocked pixels only matter for the transmission gradient
       const float a = amp * t;
       const float o = opd ? opd[i] : 0.0f;
       const float ph = phase ? phase[i] : 0.0f;
@@ -411,24 +412,68 @@ __global__ void grad_reduce_kernel(size_t npix, int n_items, const float2* __res
         const float kw = __ldg(k + it);
         float sn, cs;
         fast_sincos(__fmul_rn(kw, o) + ph, &sn, &cs);
-        const float g = a * (cs * v.y - sn * v.x);
+        const float g = a * (cs * v.y - sn * v.x);   // Im(conj(P) Q)
         ao = fmaf(kw, g, ao);
         ap += g;
+        at = fmaf(amp, cs * v.x + sn * v.y, at);     // Re(conj(Q) dP/dT), direct term
       }
     }
     if (opd_bar) opd_bar[i] = ao;
     if (phase_bar) phase_bar[i] = ap;
+    if (t_bar) t_bar[i] = at;
   }
 }
 
 int launch_grad_reduce(size_t npix, int n_items, const float2* q, const float* k, const float* T,
                        const float* opd, const float* phase, const float* amp_scale, float a0,
-                       float* opd_bar, float* phase_bar, int accumulate, cudaStream_t st) {
+                       float* opd_bar, float* phase_bar, float* t_bar, int accumulate, cudaStream_t st) {
   grad_reduce_kernel<<<grid_for(npix, 128, 148 * 16), 128, 0, st>>>(npix, n_items, q, k, T, opd, phase,
-                                                                    amp_scale, a0, opd_bar, phase_bar,
+                                                                    amp_scale, a0, opd_bar, phase_bar, t_bar,
                                                                     accumulate);
   note_launch();
   return check_launch("grad_reduce");
+}
+
+// Power normalisation (wavefronts.py:418-424) makes amp = (sum_j (a0 T_j)^2)^(-1/2) depend on
+// T: dL/dT_j gets  -(sum_i T_i Tbar_i) * amp^2 * a0^2 * T_j  on top of the direct term.
+__global__ void tbar_partial_kernel(size_t npix, const float* __restrict__ T, const float* __restrict__ t_bar,
+                                    double* __restrict__ partial) {
+  __shared__ double sm[256];
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (size_t)gridDim.x * blockDim.x)
+    acc += (double)T[i] * (double)t_bar[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+__global__ void tbar_apply_kernel(size_t npix, const float* __restrict__ T, const float* __restrict__ amp_scale,
+                                  float a0, const double* __restrict__ partial, float* __restrict__ t_bar) {
+  __shared__ double sm[256];
+  sm[threadIdx.x] = partial[threadIdx.x];   // every block re-sums the 256 partials in the same order
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  const float amp = amp_scale[0];
+  const float coef = (float)sm[0] * amp * amp * a0 * a0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (size_t)gridDim.x * blockDim.x)
+    t_bar[i] -= coef * T[i];
+}
+
+int launch_tbar_finalize(size_t npix, const float* T, const float* amp_scale, float a0, float* t_bar,
+                         double* work, cudaStream_t st) {
+  tbar_partial_kernel<<<256, 256, 0, st>>>(npix, T, t_bar, work);
+  tbar_apply_kernel<<<grid_for(npix, 256, 148 * 8), 256, 0, st>>>(npix, T, amp_scale, a0, work, t_bar);
+  note_launch(2);
+  return check_launch("tbar_finalize");
 }
 
 // VJP w.r.t. the source offset: the offset delta (fringes) shifts the output coordinates,

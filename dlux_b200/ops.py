@@ -180,7 +180,7 @@ def polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, 
 
 def polypsf_bwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,
                 psf_bar, n_pupil, n_psf, normalise=True, precision=None, want_opd=True,
-                want_phase=False, want_weights=False, want_delta=False):
+                want_phase=False, want_weights=False, want_delta=False, want_transmission=False):
     lib = _lib.load()
     dev = wavenumber.device
     L = wavenumber.numel()
@@ -194,25 +194,26 @@ def polypsf_bwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, 
     phase_bar = mk(n_pupil, n_pupil) if want_phase else None
     w_bar = mk(S, L) if want_weights else None
     d_bar = mk(S, L, 2) if want_delta else None
+    t_bar = mk(n_pupil, n_pupil) if want_transmission else None
     psf_bar = psf_bar.to(torch.float32).contiguous()
     with torch.cuda.device(dev):
         check(lib.dlux_polypsf_bwd(C.byref(desc), _ptr(transmission), _ptr(opd), _ptr(phase),
                                    _ptr(wavenumber), _ptr(scale_out), _ptr(norm), _ptr(weights),
                                    _ptr(delta_xy), _ptr(field), _ptr(psf_bar), _ptr(opd_bar),
-                                   _ptr(phase_bar), _ptr(w_bar), _ptr(d_bar), _ptr(scratch), scratch.numel(),
-                                   _stream(dev)), "dlux_polypsf_bwd")
-    return opd_bar, phase_bar, w_bar, d_bar
+                                   _ptr(phase_bar), _ptr(w_bar), _ptr(d_bar), _ptr(t_bar), _ptr(scratch),
+                                   scratch.numel(), _stream(dev)), "dlux_polypsf_bwd")
+    return opd_bar, phase_bar, w_bar, d_bar, t_bar
 
 
 class PolyPSFFunction(torch.autograd.Function):
     """psf = sum_{s,l} w_sl |MFT_l(amp T exp(i(k_l opd + phase)))|^2 with gradients w.r.t.
-    opd, phase, weights and the source offsets delta_xy (the fused primitive behind
+    opd, phase, weights, the source offsets delta_xy and the transmission (the fused primitive behind
     OpticalSystem.propagate / PointSources.model)."""
 
     @staticmethod
     def forward(ctx, opd, phase, weights, delta_xy, transmission, wavenumber, scale_out, norm,
                 n_pupil, n_psf, normalise, precision):
-        need = any(t is not None and t.requires_grad for t in (opd, phase, weights, delta_xy))
+        need = any(t is not None and t.requires_grad for t in (opd, phase, weights, delta_xy, transmission))
         psf, field = polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights,
                                  delta_xy, n_pupil, n_psf, normalise, precision, save_field=need)
         ctx.save_for_backward(*(t for t in (opd, phase, weights, transmission, wavenumber, scale_out,
@@ -229,16 +230,17 @@ class PolyPSFFunction(torch.autograd.Function):
             next(it) if p else None for p in ctx.present]
         n_pupil, n_psf, normalise, precision, wshape = ctx.cfg
         want = ctx.needs_input_grad
-        opd_bar, phase_bar, w_bar, d_bar = polypsf_bwd(
+        opd_bar, phase_bar, w_bar, d_bar, t_bar = polypsf_bwd(
             transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,
             psf_bar, n_pupil, n_psf, normalise, precision, want_opd=bool(want[0]),
             want_phase=bool(want[1]), want_weights=bool(want[2]),
-            want_delta=bool(want[3]) and delta_xy is not None)
+            want_delta=bool(want[3]) and delta_xy is not None,
+            want_transmission=bool(want[4]) and transmission is not None)
         if w_bar is not None:
             w_bar = w_bar.reshape(wshape)
         if d_bar is not None:
             d_bar = d_bar.reshape(delta_xy.shape)
-        return (opd_bar, phase_bar, w_bar, d_bar) + (None,) * 8
+        return (opd_bar, phase_bar, w_bar, d_bar, t_bar) + (None,) * 7
 
 
 # --------------------------------------------------------------------------- basis

@@ -148,7 +148,7 @@ DLUX_API int dlux_polypsf_fwd(const dlux_polypsf_desc* desc,
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
 /* VJP of dlux_polypsf_fwd w.r.t. opd (-> Zernike coefficients through
- * dlux_basis_reduce), phase, weights (-> flux, spectrum) and the source offsets delta_xy
+ * dlux_basis_reduce), phase, transmission, weights (-> flux, spectrum) and the source offsets delta_xy
  * (-> PointSources.position through delta = theta * D / lambda), given psf_bar = dL/dpsf and
  * the saved field.  Stands in for jax.grad through the same lines
  * (docs/phase_retrieval.md:269-287). */
@@ -162,6 +162,7 @@ DLUX_API int dlux_polypsf_bwd(const dlux_polypsf_desc* desc,
                      float* phase_bar,         /* [N, N] or NULL */
                      float* weights_bar,       /* [S, L] or NULL */
                      float* delta_bar,         /* [S, L, 2] or NULL */
+                     float* transmission_bar,  /* [N, N] or NULL (incl. the power-normalisation term) */
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------

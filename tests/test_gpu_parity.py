@@ -284,6 +284,40 @@ def test_point_sources_position_and_flux_gradients(dev, prec):
     assert rel_l2(pos.grad.cpu().numpy(), pos_r.grad.numpy()) < 5e-5   # position: float32 tilt scale 1e-7 rad
 
 
+@pytest.mark.parametrize("prec", PRECS)
+def test_transmission_and_phase_gradients(dev, prec):
+    # gradients w.r.t. the remaining pupil-plane leaves: transmission (through the power
+    # normalisation too) and an additive phase screen
+    import dlux_b200 as dl
+    from oracle import torch_twin
+    N, M = 64, 32
+    rng = np.random.default_rng(40)
+    yy, xx = np.mgrid[:N, :N]
+    r = np.hypot(xx - (N - 1) / 2, yy - (N - 1) / 2) / (N / 2)
+    T0 = ((r <= 1) * rng.uniform(0.5, 1.0, (N, N))).astype(np.float32)
+    opd0 = (rng.standard_normal((N, N)) * 3e-8).astype(np.float32)
+    wls = np.linspace(0.9e-6, 1.1e-6, 3).astype(np.float32)
+    w = np.array([0.2, 0.5, 0.3], np.float32)
+    off = np.array([1.0e-7, -3.0e-7], np.float32)
+    G = rng.standard_normal((M, M)).astype(np.float32)
+    for normalise in (True, False):
+        T = torch.as_tensor(T0, device=dev).requires_grad_(True)
+        opd = torch.as_tensor(opd0, device=dev).requires_grad_(True)
+        layer = dl.Optic(T, opd, None, normalise=normalise, device=dev)
+        sys_ = dl.AngularOpticalSystem(N, 1.0, [("optic", layer)], M, 0.05, device=dev, precision=prec)
+        psf = sys_.propagate(wls, off, w)
+        (psf * torch.as_tensor(G, device=dev)).sum().backward()
+        T_r = torch.tensor(T0, dtype=torch.float64, requires_grad=True)
+        o_r = torch.tensor(opd0, dtype=torch.float64, requires_grad=True)
+        ref = torch_twin.poly_psf(T_r, o_r, wls, w, diameter=1.0, psf_npixels=M,
+                                  pixel_scale_rad=O.arcsec2rad(0.05), offset=off, normalise=normalise,
+                                  dtype=np.float64)
+        (ref * torch.tensor(G, dtype=torch.float64)).sum().backward()
+        assert rel_l2(psf.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+        assert rel_l2(opd.grad.cpu().numpy(), o_r.grad.numpy()) < TOL, normalise
+        assert rel_l2(T.grad.cpu().numpy(), T_r.grad.numpy()) < 2e-5, (normalise, rel_l2(T.grad.cpu().numpy(), T_r.grad.numpy()))
+
+
 def test_config4_like_large_pupil_many_sources(dev):
     # BASELINE config 4 shape (scaled down in sources/wavelengths): 2048 px pupil with a binary
     # 0/pi phase mask, several stars, MFT to 256x256
