@@ -49,19 +49,28 @@ namespace dlux {
 
 namespace {
 
+#ifdef DLUX_NO_PAIR
+constexpr bool PAIR = false;       // fallback: cta_group::1 MMAs, data tiles TMA-multicast to both CTAs
+#else
+constexpr bool PAIR = true;        // cta_group::2 MMAs: each CTA of the pair holds half of every data tile
+#endif
 constexpr int BM = 128;            // data rows per tile  (UMMA N)
 constexpr int NB = 64;             // output coordinates per tile; 2*NB TMEM lanes (UMMA M = 128)
 constexpr int BK = 16;             // k per pipeline stage = one 64-byte swizzle row of fp32
 constexpr int UMMA_K = 8;          // kind::tf32
-constexpr int A_STAGES = 3;        // data ring (TMA), each stage holds both tiles
+constexpr int ROWS_CTA = PAIR ? BM / 2 : BM;   // rows of a data tile resident in this CTA's shared memory
+constexpr int A_STAGES = PAIR ? 6 : 3;        // data ring (TMA), each stage holds (this CTA's part of) both tiles
 constexpr int G_STAGES = 2;        // phasor ring (TMEM)
-constexpr int PLANE_BYTES = BM * BK * 4;            // 8 KiB: one fp32 (tf32) plane of a tile-chunk
-constexpr int BPLANE_BYTES = BM * BK * 2;           // 4 KiB: one bf16 plane
+constexpr int PLANE_BYTES = ROWS_CTA * BK * 4;      // one fp32 (tf32) plane of a tile-chunk
+constexpr int BPLANE_BYTES = ROWS_CTA * BK * 2;     // one bf16 plane
 constexpr int BPL_BASE = 2 * PLANE_BYTES;           // bf16 planes follow the two fp32 planes
-constexpr int TILE_BYTES = 2 * PLANE_BYTES + 4 * BPLANE_BYTES;  // 32 KiB per tile-chunk
-constexpr int A_BYTES = 2 * TILE_BYTES;             // 64 KiB: tiles a and b
+constexpr int TILE_BYTES = 2 * PLANE_BYTES + 4 * BPLANE_BYTES;  // 16 (pair) / 32 KiB per tile-chunk
+constexpr int A_BYTES = 2 * TILE_BYTES;             // 32 (pair) / 64 KiB: tiles a and b
 constexpr int RING_BYTES = A_STAGES * A_BYTES;      // 192 KiB
-constexpr int FLUSH_CHUNKS = 4;    // k-chunks accumulated in TMEM before draining to registers
+#ifndef DLUX_FLUSH_CHUNKS
+#define DLUX_FLUSH_CHUNKS 4
+#endif
+constexpr int FLUSH_CHUNKS = DLUX_FLUSH_CHUNKS;    // k-chunks accumulated in TMEM before draining to registers
 constexpr int NUM_ACC = 3;         // TMEM partial-accumulator buffers, used round-robin (a, b, a, b, ...)
 constexpr int ACC_COLS = BM;       // 128 fp32 columns per partial
 constexpr int G_COLS = 4 * BK;     // 64 columns per phasor stage
@@ -81,11 +90,6 @@ constexpr int REGS_EPI = 152, REGS_CTRL = 40, REGS_GEN = 64;        // setmaxnre
 static_assert(256 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_GEN),
               "register budget");
 constexpr int CLUSTER = 2;         // CTAs sharing (multicasting) the data tiles
-#ifdef DLUX_NO_MULTICAST
-constexpr bool MULTICAST = false;  // A/B switch: every CTA loads both tiles itself
-#else
-constexpr bool MULTICAST = true;
-#endif
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 2560 /*epilogue staging*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
@@ -113,6 +117,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
+// ---- cluster-scope forms (pair mode): barriers that live in the leader CTA of the pair
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#ifdef DLUX_ARRIVE_RELEASE
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  // relaxed: what the arrival publishes lives in tensor memory and is ordered by the
+  // tcgen05 fences around it, not by the generic-proxy release
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;"
+               ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+#ifdef DLUX_WAIT_PLAIN
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -135,6 +173,18 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
       " [%0], [%1, {%3, %4, %5}], [%2], %6;"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
 }
+// pair mode: destination in my own shared memory, completion bytes counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar,
+                                                int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc2(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask) : "memory");
@@ -156,6 +206,25 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// pair forms: M = 256 (128 TMEM lanes in each CTA), B = 64 rows from each CTA's shared memory
+__device__ __forceinline__ void umma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // same with bf16 operands: A 128 lanes x 8 columns (16 packed bf16), B K-major 16 x bf16
@@ -227,19 +296,20 @@ __device__ __forceinline__ bool elect_one() {
 constexpr uint64_t DESC_SW64_HI = ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
                                   ((uint64_t)4 << 61);
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
-  return DESC_SW64_HI | (uint64_t)(saddr >> 4);  // shared addresses are < 256 KiB: 14 bits after >> 4
+  return DESC_SW64_HI | (uint64_t)((saddr & 0x3FFFFu) >> 4);  // CTA-local offset (< 256 KiB): 14 bits after >> 4
 }
 
 // K-major SWIZZLE_32B descriptor for the bf16 planes (rows of 16 bf16 = 32 bytes; 8 rows = 256 B)
 constexpr uint64_t DESC_SW32_HI = ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
                                   ((uint64_t)6 << 61);
 __device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
-  return DESC_SW32_HI | (uint64_t)(saddr >> 4);
+  return DESC_SW32_HI | (uint64_t)((saddr & 0x3FFFFu) >> 4);
 }
 
 // instruction descriptors: D=f32, K-major both, M=128 (lanes), N=128 (data rows);
 // A=B=tf32 (format 2, kind::tf32) or A=B=bf16 (format 1, kind::f16)
-constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BM >> 3) << 17) | ((uint32_t)((2 * NB) >> 4) << 24);
+constexpr int UMMA_M = PAIR ? 4 * NB : 2 * NB;   // pair: 128 lanes in each of the two CTAs
+constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BM >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
 constexpr uint32_t IDESC = IDESC_SHAPE | (2u << 7) | (2u << 10);
 constexpr uint32_t IDESC_BF16 = IDESC_SHAPE | (1u << 7) | (1u << 10);
 
@@ -367,31 +437,52 @@ __device__ __forceinline__ void issue_tile_chunk(uint32_t d, uint32_t g0, uint32
   const uint64_t b_il = make_desc_sw32(tile_smem + BPL_BASE + 3 * BPLANE_BYTES);
   const uint32_t gb = g0 + GB_BASE;  // packed bf16: G1_hi, G1_lo, G2_hi, G2_lo
   // small terms first
-  umma_bf16_ts(d, gb + 1 * GB_COLS, b_rh, IDESC_BF16, fresh ? 0u : 1u);  // G1_lo * Re_hi
-  umma_bf16_ts(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);                // G1_hi * Re_lo
-  umma_bf16_ts(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);                // G2_lo * Im_hi
-  umma_bf16_ts(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);                // G2_hi * Im_lo
+  if constexpr (PAIR) {
+#ifndef DLUX_DEBUG_SKIP_BF16
+    umma_bf16_ts2(d, gb + 1 * GB_COLS, b_rh, IDESC_BF16, fresh ? 0u : 1u);  // G1_lo * Re_hi
+    umma_bf16_ts2(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);                // G1_hi * Re_lo
+    umma_bf16_ts2(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);                // G2_lo * Im_hi
+    umma_bf16_ts2(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);                // G2_hi * Im_lo
+#endif
+#ifndef DLUX_DEBUG_SKIP_TF32
 #pragma unroll
-  for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-    umma_tf32_ts(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);        // G1_hi * Re_hi
-    umma_tf32_ts(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);   // G2_hi * Im_hi
+    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+      umma_tf32_ts2(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);        // G1_hi * Re_hi
+      umma_tf32_ts2(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);   // G2_hi * Im_hi
+    }
+#endif
+  } else {
+    umma_bf16_ts(d, gb + 1 * GB_COLS, b_rh, IDESC_BF16, fresh ? 0u : 1u);
+    umma_bf16_ts(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);
+    umma_bf16_ts(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);
+    umma_bf16_ts(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);
+#pragma unroll
+    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+      umma_tf32_ts(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);
+      umma_tf32_ts(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);
+    }
   }
 }
 
 // Where the TMEM partial accumulators of the two tiles open and close along the k-chunks of
-// a unit.  Tile a: [0,4) [4,8) ...; tile b: [0,2) [2,6) [6,10) ... (staggered by half a
-// partial).  Both close at the last chunk.  Acquisition order inside a chunk: a, then b.
+// a unit.  The FIRST partial of a unit is twice as long: while the drain warpgroups are
+// still writing the previous unit's epilogue (~8 chunk-times, bounded by the SM's store port)
+// the issuers must not need a buffer that only those warpgroups can release.
+//   tile a: [0,8) [8,12) [12,16) ...      tile b: [0,6) [6,10) [10,14) ...
+// (steady state staggered by half a partial).  Both close at the last chunk.  Acquisition
+// order inside a chunk: a, then b.
 struct PartialSchedule {
   bool a_open, a_close, b_open, b_close;
 };
 __device__ __forceinline__ PartialSchedule partial_schedule(int kc, int k_chunks) {
+  constexpr int A0 = 2 * FLUSH_CHUNKS, B0 = 2 * FLUSH_CHUNKS - FLUSH_CHUNKS / 2;
   PartialSchedule ps;
-  const int r = kc % FLUSH_CHUNKS;
   const bool last = kc == k_chunks - 1;
-  ps.a_open = r == 0;
-  ps.a_close = (r == FLUSH_CHUNKS - 1) || last;
-  ps.b_open = (kc == 0) || (r == FLUSH_CHUNKS / 2);
-  ps.b_close = (r == FLUSH_CHUNKS / 2 - 1) || last;
+  const int ra = (kc - A0) % FLUSH_CHUNKS, rb = (kc - B0) % FLUSH_CHUNKS;  // used only for kc >= A0 / B0
+  ps.a_open = (kc == 0) || (kc >= A0 && ra == 0);
+  ps.a_close = last || (kc == A0 - 1) || (kc >= A0 && ra == FLUSH_CHUNKS - 1);
+  ps.b_open = (kc == 0) || (kc >= B0 && rb == 0);
+  ps.b_close = last || (kc == B0 - 1) || (kc >= B0 && rb == FLUSH_CHUNKS - 1);
   return ps;
 }
 
@@ -431,23 +522,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   }
   if (warp == WARP_MMA && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
-      mbar_init(fullA_bar(s), 1);   // TMA producer's arrive.expect_tx
-      mbar_init(emptyA_bar(s), MULTICAST ? 2 * CLUSTER : 2);  // tcgen05.commit of both issuer warps (of every CTA of the cluster)
+      mbar_init(fullA_bar(s), PAIR ? 2 : 1);   // TMA producer's arrive.expect_tx (pair: both CTAs', on the leader)
+      mbar_init(emptyA_bar(s), PAIR ? 2 : 2 * CLUSTER);  // multicast tcgen05.commit of the issuer warps
     }
     for (int s = 0; s < G_STAGES; ++s) {
-      mbar_init(fullG_bar(s), NUM_GEN_WARPS);  // one arrive per generator warp
+      mbar_init(fullG_bar(s), PAIR ? 2 * NUM_GEN_WARPS : NUM_GEN_WARPS);  // one arrive per generator warp (pair: of both CTAs)
       mbar_init(emptyG_bar(s), 2);             // tcgen05.commit of both issuer warps
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);     // tcgen05.commit closing a partial
-      mbar_init(tempty_bar(a), 128);  // every thread of the draining warpgroup
+      mbar_init(tempty_bar(a), PAIR ? 256 : 128);  // every thread of the draining warpgroup (pair: of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (PAIR) {  // the same warp of both CTAs: one allocation spanning the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -456,12 +553,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t crank = cluster_ctarank();
   const int cl_id = blockIdx.x / CLUSTER, n_cl = gridDim.x / CLUSTER;
+  // pair mode: fullA / fullG / tempty are the LEADER's (cluster rank 0); everyone addresses them
+  // through the cluster window, the leader's own threads included
+  const uint32_t lead_delta = PAIR ? mapa_rank(bar_base, 0) - bar_base : 0u;
 
   // cluster work unit = (item, pair of n-tiles, pair of m-tiles); CTA `crank` of the cluster
   // takes n-tile 2 * np + crank (an n-tile beyond the matrix computes on zeros and stores
   // nothing)
   const int units_per_item = tp.tiles_mp * tp.tiles_np;
-  const int n_partials = (tp.k_chunks + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS;
 
   // Register re-balancing between warpgroups: setmaxnreg is the first instruction of each
   // warpgroup's branch (all four warps of a warpgroup execute it).
@@ -481,9 +580,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           if (elect_one()) {
             const uint32_t dst = smem_base + stage * A_BYTES;
             const uint32_t bar = fullA_bar(stage);
-            mbar_arrive_expect_tx(bar, A_BYTES);
-            if (MULTICAST) {  // I fetch tile `crank` (a or b) of the stage and multicast it to both CTAs; the
+            if constexpr (PAIR) {  // my half (64 rows) of both tiles into my own slot; bytes counted by the leader
+              const uint32_t lbar = bar + lead_delta;
+              mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
+#pragma unroll
+              for (int tb2 = 0; tb2 < 2; ++tb2) {
+                const uint32_t t0 = dst + tb2 * TILE_BYTES;
+                const int mr = m0 + tb2 * BM + (int)crank * ROWS_CTA;
+                tma_load_3d_2sm(t0 + 0 * PLANE_BYTES, &map0, lbar, kc * BK, mr, d);
+                tma_load_3d_2sm(t0 + 1 * PLANE_BYTES, &map1, lbar, kc * BK, mr, d);
+                tma_load_3d_2sm(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, lbar, kc * BK, mr, d);
+                tma_load_3d_2sm(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, lbar, kc * BK, mr, d);
+                tma_load_3d_2sm(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, lbar, kc * BK, mr, d);
+                tma_load_3d_2sm(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, lbar, kc * BK, mr, d);
+              }
+            } else {  // I fetch tile `crank` (a or b) of the stage and multicast it to both CTAs; the
                // peer does the same with the other tile (rows beyond the matrix are zero-filled)
+              mbar_arrive_expect_tx(bar, A_BYTES);
               const uint32_t t0 = dst + crank * TILE_BYTES;
               const int mr = m0 + (int)crank * BM;
               constexpr uint16_t MASK = (1u << CLUSTER) - 1;
@@ -493,19 +606,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
               tma_load_3d_mc(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, bar, kc * BK, mr, d, MASK);
               tma_load_3d_mc(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, bar, kc * BK, mr, d, MASK);
               tma_load_3d_mc(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, bar, kc * BK, mr, d, MASK);
-            }
-            else {
-#pragma unroll
-              for (int tb2 = 0; tb2 < 2; ++tb2) {
-                const uint32_t t0 = dst + tb2 * TILE_BYTES;
-                const int mr = m0 + tb2 * BM;
-                tma_load_3d(t0 + 0 * PLANE_BYTES, &map0, bar, kc * BK, mr, d);
-                tma_load_3d(t0 + 1 * PLANE_BYTES, &map1, bar, kc * BK, mr, d);
-                tma_load_3d(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, bar, kc * BK, mr, d);
-                tma_load_3d(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, bar, kc * BK, mr, d);
-                tma_load_3d(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, bar, kc * BK, mr, d);
-                tma_load_3d(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, bar, kc * BK, mr, d);
-              }
             }
           }
           __syncwarp();
@@ -527,7 +627,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       long long dbg_g = 0, dbg_a = 0, dbg_t = 0;
       const long long dbg_start = clock64();
 #endif
-      for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
+      // pair mode: only the leader CTA issues; its MMAs drive the tensor cores of both SMs
+      for (int unit = (PAIR && crank != 0) ? tp.n_units : cl_id; unit < tp.n_units; unit += n_cl) {
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           // Partials are FLUSH_CHUNKS long; tile b's boundaries are staggered by half a partial so
           // that the three TMEM buffers are re-acquired >= 2 chunks after they were handed to a
@@ -544,17 +645,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           }
 #ifdef DLUX_DEBUG_TIMING
           const long long t0_ = clock64();
-          mbar_wait(fullG_bar(sg), pg);
+#ifndef DLUX_DEBUG_NOGWAIT
+          mbar_wait_cluster(fullG_bar(sg), pg);
+#endif
           const long long t1_ = clock64();
-          mbar_wait(fullA_bar(sa), pa);
+          mbar_wait_cluster(fullA_bar(sa), pa);
           const long long t2_ = clock64();
-          if (opened) mbar_wait(tempty_bar(mybuf), myphase ^ 1);
+          if (opened) mbar_wait_cluster(tempty_bar(mybuf), myphase ^ 1);
           const long long t3_ = clock64();
           dbg_g += t1_ - t0_; dbg_a += t2_ - t1_; dbg_t += t3_ - t2_;
 #else
-          mbar_wait(fullG_bar(sg), pg);
-          mbar_wait(fullA_bar(sa), pa);
-          if (opened) mbar_wait(tempty_bar(mybuf), myphase ^ 1);  // my drain warpgroup released the buffer
+          // (acquire at cluster scope: in pair mode the peer CTA's warps arrive on these too)
+          mbar_wait_cluster(fullG_bar(sg), pg);
+          mbar_wait_cluster(fullA_bar(sa), pa);
+          if (opened) mbar_wait_cluster(tempty_bar(mybuf), myphase ^ 1);  // the drain warpgroup(s) released the buffer
 #endif
           tc_fence_after();
           if (elect_one()) {
@@ -562,10 +666,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
                              smem_base + sa * A_BYTES + which * TILE_BYTES, opened);
             // when these MMAs retire: smem slot released in both CTAs, phasor stage released
             // (each barrier also counts the other issuer warp's commit), partial handed over
-            if (MULTICAST) umma_commit_mc(emptyA_bar(sa), (1u << CLUSTER) - 1);
-            else umma_commit(emptyA_bar(sa));
-            umma_commit(emptyG_bar(sg));
-            if (which ? ps.b_close : ps.a_close) umma_commit(tfull_bar(mybuf));
+            constexpr uint16_t BOTH = (1u << CLUSTER) - 1;
+            if constexpr (PAIR) {
+              umma_commit_mc2(emptyA_bar(sa), BOTH);
+              umma_commit_mc2(emptyG_bar(sg), BOTH);
+              if (which ? ps.b_close : ps.a_close) umma_commit_mc2(tfull_bar(mybuf), BOTH);
+            } else {
+              umma_commit_mc(emptyA_bar(sa), BOTH);
+              umma_commit(emptyG_bar(sg));
+              if (which ? ps.b_close : ps.a_close) umma_commit(tfull_bar(mybuf));
+            }
           }
           __syncwarp();
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
@@ -631,7 +741,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(buf));
+        if constexpr (PAIR) mbar_arrive_cluster(tempty_bar(buf) + lead_delta);
+        else mbar_arrive(tempty_bar(buf));
       }
 #ifdef DLUX_DEBUG_TIMING
       const long long te0_ = clock64();
@@ -716,7 +827,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(fullG_bar(stage));
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(fullG_bar(stage) + lead_delta);
+          else mbar_arrive(fullG_bar(stage));
+        }
         if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -726,7 +840,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   __syncthreads();
   cluster_sync_all();  // no CTA exits while its peer may still multicast into it
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -787,7 +904,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
     const cuuint64_t pitch = bf ? pitch8(p.K) : pitch4(p.K);  // row strides are multiples of 16 bytes
     cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.rows, n_data};
     cuuint64_t strides[2] = {pitch * esz, pitch * esz * (cuuint64_t)p.rows};
-    cuuint32_t box[3] = {BK, BM, 1};
+    cuuint32_t box[3] = {BK, ROWS_CTA, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     void* base = bf ? (void*)p.a.b[i - 2] : (void*)p.a.hi[i];
     CUresult r = s.encode(&maps[i], bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,

@@ -1,0 +1,6 @@
+for v in "$@"; do
+  cp dlux_b200/lib/var_$v.so dlux_b200/lib/libdlux_b200.so
+  echo "=== $v"
+  timeout 200 python bench.py --steps 50 --warmup 5 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['gemm_ms_per_step'], d['clocks'])"
+  timeout 100 python tools/accuracy.py 2>&1 | grep 3xtf32
+done
