@@ -49,23 +49,18 @@ namespace dlux {
 
 namespace {
 
-#ifdef DLUX_NO_PAIR
-constexpr bool PAIR = false;       // fallback: cta_group::1 MMAs, data tiles TMA-multicast to both CTAs
-#else
-constexpr bool PAIR = true;        // cta_group::2 MMAs: each CTA of the pair holds half of every data tile
-#endif
 constexpr int BM = 128;            // data rows per tile  (UMMA N)
 constexpr int NB = 64;             // output coordinates per tile; 2*NB TMEM lanes (UMMA M = 128)
 constexpr int BK = 16;             // k per pipeline stage = one 64-byte swizzle row of fp32
 constexpr int UMMA_K = 8;          // kind::tf32
-constexpr int ROWS_CTA = PAIR ? BM / 2 : BM;   // rows of a data tile resident in this CTA's shared memory
-constexpr int A_STAGES = PAIR ? 6 : 3;        // data ring (TMA), each stage holds (this CTA's part of) both tiles
+constexpr int ROWS_CTA = BM / 2;   // rows of a data tile resident in this CTA's shared memory (the peer holds the rest)
+constexpr int A_STAGES = 6;        // data ring (TMA), each stage holds this CTA's half of both tiles
 constexpr int G_STAGES = 2;        // phasor ring (TMEM)
 constexpr int PLANE_BYTES = ROWS_CTA * BK * 4;      // one fp32 (tf32) plane of a tile-chunk
 constexpr int BPLANE_BYTES = ROWS_CTA * BK * 2;     // one bf16 plane
 constexpr int BPL_BASE = 2 * PLANE_BYTES;           // bf16 planes follow the two fp32 planes
-constexpr int TILE_BYTES = 2 * PLANE_BYTES + 4 * BPLANE_BYTES;  // 16 (pair) / 32 KiB per tile-chunk
-constexpr int A_BYTES = 2 * TILE_BYTES;             // 32 (pair) / 64 KiB: tiles a and b
+constexpr int TILE_BYTES = 2 * PLANE_BYTES + 4 * BPLANE_BYTES;  // 16 KiB: my half of a tile-chunk
+constexpr int A_BYTES = 2 * TILE_BYTES;             // 32 KiB: tiles a and b
 constexpr int RING_BYTES = A_STAGES * A_BYTES;      // 192 KiB
 #ifndef DLUX_FLUSH_CHUNKS
 #define DLUX_FLUSH_CHUNKS 4
@@ -99,12 +94,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -160,19 +149,6 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                               int c2, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
-}
 // pair mode: destination in my own shared memory, completion bytes counted on the LEADER's barrier
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar,
                                                 int c0, int c1, int c2) {
@@ -185,10 +161,6 @@ __device__ __forceinline__ void umma_commit_mc2(uint32_t bar, uint16_t cta_mask)
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask) : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(cta_mask) : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -198,17 +170,8 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem]   (A: 128 lanes x 8 columns of tf32, K-major)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// pair forms: M = 256 (128 TMEM lanes in each CTA), B = 64 rows from each CTA's shared memory
+// D[tmem] (+)= A[tmem] * B[smem] over the CTA pair: M = 256 (128 TMEM lanes in each CTA; A: 8
+// columns of tf32 or of packed bf16 per lane, K-major), B = 64 rows from each CTA's shared memory
 __device__ __forceinline__ void umma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
                                               uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -226,19 +189,6 @@ __device__ __forceinline__ void umma_bf16_ts2(uint32_t d_tmem, uint32_t a_tmem, 
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// same with bf16 operands: A 128 lanes x 8 columns (16 packed bf16), B K-major 16 x bf16
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -308,7 +258,7 @@ __device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
 
 // instruction descriptors: D=f32, K-major both, M=128 (lanes), N=128 (data rows);
 // A=B=tf32 (format 2, kind::tf32) or A=B=bf16 (format 1, kind::f16)
-constexpr int UMMA_M = PAIR ? 4 * NB : 2 * NB;   // pair: 128 lanes in each of the two CTAs
+constexpr int UMMA_M = 4 * NB;     // 256: 128 lanes in each of the two CTAs
 constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BM >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
 constexpr uint32_t IDESC = IDESC_SHAPE | (2u << 7) | (2u << 10);
 constexpr uint32_t IDESC_BF16 = IDESC_SHAPE | (1u << 7) | (1u << 10);
@@ -437,45 +387,31 @@ __device__ __forceinline__ void issue_tile_chunk(uint32_t d, uint32_t g0, uint32
   const uint64_t b_il = make_desc_sw32(tile_smem + BPL_BASE + 3 * BPLANE_BYTES);
   const uint32_t gb = g0 + GB_BASE;  // packed bf16: G1_hi, G1_lo, G2_hi, G2_lo
   // small terms first
-  if constexpr (PAIR) {
-#ifndef DLUX_DEBUG_SKIP_BF16
-    umma_bf16_ts2(d, gb + 1 * GB_COLS, b_rh, IDESC_BF16, fresh ? 0u : 1u);  // G1_lo * Re_hi
-    umma_bf16_ts2(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);                // G1_hi * Re_lo
-    umma_bf16_ts2(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);                // G2_lo * Im_hi
-    umma_bf16_ts2(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);                // G2_hi * Im_lo
-#endif
-#ifndef DLUX_DEBUG_SKIP_TF32
+  umma_bf16_ts2(d, gb + 1 * GB_COLS, b_rh, IDESC_BF16, fresh ? 0u : 1u);  // G1_lo * Re_hi
+  umma_bf16_ts2(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);                // G1_hi * Re_lo
+  umma_bf16_ts2(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);                // G2_lo * Im_hi
+  umma_bf16_ts2(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);                // G2_hi * Im_lo
 #pragma unroll
-    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-      umma_tf32_ts2(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);        // G1_hi * Re_hi
-      umma_tf32_ts2(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);   // G2_hi * Im_hi
-    }
-#endif
-  } else {
-    umma_bf16_ts(d, gb + 1 * GB_COLS, b_rh, IDESC_BF16, fresh ? 0u : 1u);
-    umma_bf16_ts(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);
-    umma_bf16_ts(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);
-    umma_bf16_ts(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);
-#pragma unroll
-    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-      umma_tf32_ts(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);
-      umma_tf32_ts(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);
-    }
+  for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+    umma_tf32_ts2(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);        // G1_hi * Re_hi
+    umma_tf32_ts2(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);   // G2_hi * Im_hi
   }
 }
 
 // Where the TMEM partial accumulators of the two tiles open and close along the k-chunks of
-// a unit.  The FIRST partial of a unit is twice as long: while the drain warpgroups are
-// still writing the previous unit's epilogue (~8 chunk-times, bounded by the SM's store port)
-// the issuers must not need a buffer that only those warpgroups can release.
-//   tile a: [0,8) [8,12) [12,16) ...      tile b: [0,6) [6,10) [10,14) ...
+// a unit.  The FIRST partial of a unit is two (three for K >= 768) flush periods long: while
+// the drain warpgroups are still writing the previous unit's epilogue (8-12 chunk-times,
+// bounded by the SM's store port) the issuers must not need a buffer that only those
+// warpgroups can release.
+//   tile a: [0,12) [12,16) [16,20) ...      tile b: [0,10) [10,14) [14,18) ...
 // (steady state staggered by half a partial).  Both close at the last chunk.  Acquisition
 // order inside a chunk: a, then b.
 struct PartialSchedule {
   bool a_open, a_close, b_open, b_close;
 };
 __device__ __forceinline__ PartialSchedule partial_schedule(int kc, int k_chunks) {
-  constexpr int A0 = 2 * FLUSH_CHUNKS, B0 = 2 * FLUSH_CHUNKS - FLUSH_CHUNKS / 2;
+  // first partial: 3 (long K) or 2 flush periods for tile a, half a period less for tile b
+  const int A0 = (k_chunks >= 12 * FLUSH_CHUNKS ? 3 : 2) * FLUSH_CHUNKS, B0 = A0 - FLUSH_CHUNKS / 2;
   PartialSchedule ps;
   const bool last = kc == k_chunks - 1;
   const int ra = (kc - A0) % FLUSH_CHUNKS, rb = (kc - B0) % FLUSH_CHUNKS;  // used only for kc >= A0 / B0
@@ -522,29 +458,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   }
   if (warp == WARP_MMA && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
-      mbar_init(fullA_bar(s), PAIR ? 2 : 1);   // TMA producer's arrive.expect_tx (pair: both CTAs', on the leader)
-      mbar_init(emptyA_bar(s), PAIR ? 2 : 2 * CLUSTER);  // multicast tcgen05.commit of the issuer warps
+      mbar_init(fullA_bar(s), 2);   // [leader's] arrive.expect_tx of both CTAs' TMA producers
+      mbar_init(emptyA_bar(s), 2);  // multicast tcgen05.commit of the two issuer warps
     }
     for (int s = 0; s < G_STAGES; ++s) {
-      mbar_init(fullG_bar(s), PAIR ? 2 * NUM_GEN_WARPS : NUM_GEN_WARPS);  // one arrive per generator warp (pair: of both CTAs)
-      mbar_init(emptyG_bar(s), 2);             // tcgen05.commit of both issuer warps
+      mbar_init(fullG_bar(s), 2 * NUM_GEN_WARPS);  // [leader's] one arrive per generator warp of both CTAs
+      mbar_init(emptyG_bar(s), 2);                 // multicast tcgen05.commit of the two issuer warps
     }
     for (int a = 0; a < NUM_ACC; ++a) {
-      mbar_init(tfull_bar(a), 1);     // tcgen05.commit closing a partial
-      mbar_init(tempty_bar(a), PAIR ? 256 : 128);  // every thread of the draining warpgroup (pair: of both CTAs)
+      mbar_init(tfull_bar(a), 1);     // multicast tcgen05.commit closing a partial
+      mbar_init(tempty_bar(a), 256);  // [leader's] every thread of the draining warpgroup of both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 0) {
-    if constexpr (PAIR) {  // the same warp of both CTAs: one allocation spanning the pair
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                   "n"(TMEM_COLS));
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                   "n"(TMEM_COLS));
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
+    // the same warp of both CTAs: one allocation spanning the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
@@ -553,9 +484,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t crank = cluster_ctarank();
   const int cl_id = blockIdx.x / CLUSTER, n_cl = gridDim.x / CLUSTER;
-  // pair mode: fullA / fullG / tempty are the LEADER's (cluster rank 0); everyone addresses them
-  // through the cluster window, the leader's own threads included
-  const uint32_t lead_delta = PAIR ? mapa_rank(bar_base, 0) - bar_base : 0u;
+  // fullA / fullG / tempty are the LEADER's (cluster rank 0); everyone addresses them through
+  // the cluster window, the leader's own threads included
+  const uint32_t lead_delta = mapa_rank(bar_base, 0) - bar_base;
 
   // cluster work unit = (item, pair of n-tiles, pair of m-tiles); CTA `crank` of the cluster
   // takes n-tile 2 * np + crank (an n-tile beyond the matrix computes on zeros and stores
@@ -580,32 +511,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           if (elect_one()) {
             const uint32_t dst = smem_base + stage * A_BYTES;
             const uint32_t bar = fullA_bar(stage);
-            if constexpr (PAIR) {  // my half (64 rows) of both tiles into my own slot; bytes counted by the leader
-              const uint32_t lbar = bar + lead_delta;
-              mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
+            // my half (64 rows) of both tiles into my own slot; the bytes are counted by the
+            // leader's barrier (rows beyond the matrix are zero-filled)
+            const uint32_t lbar = bar + lead_delta;
+            mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
 #pragma unroll
-              for (int tb2 = 0; tb2 < 2; ++tb2) {
-                const uint32_t t0 = dst + tb2 * TILE_BYTES;
-                const int mr = m0 + tb2 * BM + (int)crank * ROWS_CTA;
-                tma_load_3d_2sm(t0 + 0 * PLANE_BYTES, &map0, lbar, kc * BK, mr, d);
-                tma_load_3d_2sm(t0 + 1 * PLANE_BYTES, &map1, lbar, kc * BK, mr, d);
-                tma_load_3d_2sm(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, lbar, kc * BK, mr, d);
-                tma_load_3d_2sm(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, lbar, kc * BK, mr, d);
-                tma_load_3d_2sm(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, lbar, kc * BK, mr, d);
-                tma_load_3d_2sm(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, lbar, kc * BK, mr, d);
-              }
-            } else {  // I fetch tile `crank` (a or b) of the stage and multicast it to both CTAs; the
-               // peer does the same with the other tile (rows beyond the matrix are zero-filled)
-              mbar_arrive_expect_tx(bar, A_BYTES);
-              const uint32_t t0 = dst + crank * TILE_BYTES;
-              const int mr = m0 + (int)crank * BM;
-              constexpr uint16_t MASK = (1u << CLUSTER) - 1;
-              tma_load_3d_mc(t0 + 0 * PLANE_BYTES, &map0, bar, kc * BK, mr, d, MASK);   // tf32 hi: re, im
-              tma_load_3d_mc(t0 + 1 * PLANE_BYTES, &map1, bar, kc * BK, mr, d, MASK);
-              tma_load_3d_mc(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, bar, kc * BK, mr, d, MASK);  // bf16
-              tma_load_3d_mc(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, bar, kc * BK, mr, d, MASK);
-              tma_load_3d_mc(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, bar, kc * BK, mr, d, MASK);
-              tma_load_3d_mc(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, bar, kc * BK, mr, d, MASK);
+            for (int tb2 = 0; tb2 < 2; ++tb2) {
+              const uint32_t t0 = dst + tb2 * TILE_BYTES;
+              const int mr = m0 + tb2 * BM + (int)crank * ROWS_CTA;
+              tma_load_3d_2sm(t0 + 0 * PLANE_BYTES, &map0, lbar, kc * BK, mr, d);   // tf32 hi: re, im
+              tma_load_3d_2sm(t0 + 1 * PLANE_BYTES, &map1, lbar, kc * BK, mr, d);
+              tma_load_3d_2sm(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, lbar, kc * BK, mr, d);  // bf16
+              tma_load_3d_2sm(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, lbar, kc * BK, mr, d);
+              tma_load_3d_2sm(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, lbar, kc * BK, mr, d);
+              tma_load_3d_2sm(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, lbar, kc * BK, mr, d);
             }
           }
           __syncwarp();
@@ -628,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       const long long dbg_start = clock64();
 #endif
       // pair mode: only the leader CTA issues; its MMAs drive the tensor cores of both SMs
-      for (int unit = (PAIR && crank != 0) ? tp.n_units : cl_id; unit < tp.n_units; unit += n_cl) {
+      for (int unit = (crank != 0) ? tp.n_units : cl_id; unit < tp.n_units; unit += n_cl) {
         for (int kc = 0; kc < tp.k_chunks; ++kc) {
           // Partials are FLUSH_CHUNKS long; tile b's boundaries are staggered by half a partial so
           // that the three TMEM buffers are re-acquired >= 2 chunks after they were handed to a
@@ -655,7 +574,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           const long long t3_ = clock64();
           dbg_g += t1_ - t0_; dbg_a += t2_ - t1_; dbg_t += t3_ - t2_;
 #else
-          // (acquire at cluster scope: in pair mode the peer CTA's warps arrive on these too)
+          // (acquire at cluster scope: the peer CTA's warps arrive on these too)
           mbar_wait_cluster(fullG_bar(sg), pg);
           mbar_wait_cluster(fullA_bar(sa), pa);
           if (opened) mbar_wait_cluster(tempty_bar(mybuf), myphase ^ 1);  // the drain warpgroup(s) released the buffer
@@ -667,15 +586,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             // when these MMAs retire: smem slot released in both CTAs, phasor stage released
             // (each barrier also counts the other issuer warp's commit), partial handed over
             constexpr uint16_t BOTH = (1u << CLUSTER) - 1;
-            if constexpr (PAIR) {
-              umma_commit_mc2(emptyA_bar(sa), BOTH);
-              umma_commit_mc2(emptyG_bar(sg), BOTH);
-              if (which ? ps.b_close : ps.a_close) umma_commit_mc2(tfull_bar(mybuf), BOTH);
-            } else {
-              umma_commit_mc(emptyA_bar(sa), BOTH);
-              umma_commit(emptyG_bar(sg));
-              if (which ? ps.b_close : ps.a_close) umma_commit(tfull_bar(mybuf));
-            }
+            umma_commit_mc2(emptyA_bar(sa), BOTH);
+            umma_commit_mc2(emptyG_bar(sg), BOTH);
+            if (which ? ps.b_close : ps.a_close) umma_commit_mc2(tfull_bar(mybuf), BOTH);
           }
           __syncwarp();
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
@@ -741,8 +654,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           }
         }
         tc_fence_before();
-        if constexpr (PAIR) mbar_arrive_cluster(tempty_bar(buf) + lead_delta);
-        else mbar_arrive(tempty_bar(buf));
+        mbar_arrive_cluster(tempty_bar(buf) + lead_delta);
       }
 #ifdef DLUX_DEBUG_TIMING
       const long long te0_ = clock64();
@@ -765,9 +677,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     // ===================== phasor generators =====================
     // Two warps per TMEM lane quarter: WG3 produces k-step 0 (k 0..7) of every chunk, WG4
     // k-step 1.  Lane 2j (Re row of phasor column j) needs (G1, G2) = (cos, -sin), lane 2j+1
-    // (Im row) needs (sin, cos) = (cos, -sin) of the angle minus a quarter turn: every lane
-    // evaluates its own 8 phasors with an exact quadrant shift and stores (c, -s) -- no
-    // shuffles, no selects.
+    // (Im row) needs (sin, cos) = (cos, -sin) of the angle minus a quarter turn (an exact
+    // quadrant shift inside the sincos).
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GEN));
     const int q = warp & 3;                          // TMEM lane quarter
     const int ks = (warp - FIRST_GEN_WARP) >> 2;     // which k-step of the chunk
@@ -776,18 +687,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int stage = 0;
     uint32_t phase = 0;
+#ifdef DLUX_DEBUG_TIMING
+    long long dbg_gw = 0;
+    const long long dbg_gstart = clock64();
+#endif
     for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
       const int item = unit / units_per_item;
       const int t = unit % units_per_item;
       const int n = ((t / tp.tiles_mp) * CLUSTER + (int)crank) * NB + jcol;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
       const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
-      float xk[8];  // this chunk's k coordinates (warp-uniform), prefetched one chunk ahead
+      // The two lanes of a pair (2j, 2j+1) need the same 8 phasors in different roles: each
+      // evaluates 4 of them (even lane k 0..3 of the k-step, odd lane k 4..7) and passes the
+      // other lane what it needs with one shuffle per value.
+      const int half = lane & 1;
+      const uint32_t sgn = (uint32_t)half << 31;
+      float xk[4];  // my four k coordinates of this chunk, prefetched one chunk ahead
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xk[j] = (ks * UMMA_K + j < p.K) ? __ldg(kv + ks * UMMA_K + j) : 0.0f;
+      for (int j = 0; j < 4; ++j) {
+        const int k = ks * UMMA_K + half * 4 + j;
+        xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
+      }
       for (int kc = 0; kc < tp.k_chunks; ++kc) {
         // Evaluate into registers first, THEN wait for the TMEM stage: with only two phasor
         // stages the evaluation must overlap the MMAs that still read the stage.
+        float g1[8], g2[8];  // (G1, G2) of my row for the 8 k of the k-step
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float sn, cs;
+#ifdef DLUX_DEBUG_NOGEN
+          sn = xk[j]; cs = u;
+#else
+          fast_sincos_mufu(phase_arg(p.sign2pi, xk[j], u), qshift, &sn, &cs);
+#endif
+          // mine: (G1, G2) = (cs, -sn).  The other lane's: even -> odd (sin, cos) = (sn, cs);
+          // odd -> even (cos, -sin) = (-sn, -cs) in terms of my quarter-turn-shifted values.
+          const float r1 = __shfl_xor_sync(0xFFFFFFFFu, __uint_as_float(__float_as_uint(sn) ^ sgn), 1);
+          const float r2 = __shfl_xor_sync(0xFFFFFFFFu, __uint_as_float(__float_as_uint(cs) ^ sgn), 1);
+          g1[j] = half ? r1 : cs;
+          g1[4 + j] = half ? cs : r1;
+          g2[j] = half ? r2 : -sn;
+          g2[4 + j] = half ? -sn : r2;
+        }
         float g1h[8], g2h[8];
         uint32_t pk[4][4];  // packed bf16: G1_hi, G1_lo, G2_hi, G2_lo, 8 k -> 4 columns each
 #pragma unroll
@@ -796,16 +737,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int j = 2 * jj + e;
-            float sn, cs;
-#ifdef DLUX_DEBUG_NOGEN
-            sn = xk[j]; cs = u;
-#else
-            fast_sincos_mufu(phase_arg(p.sign2pi, xk[j], u), qshift, &sn, &cs);
-#endif
-            g1h[j] = tf32_hi(cs);
-            g1l2[e] = cs - g1h[j];
-            g2h[j] = tf32_hi(-sn);
-            g2l2[e] = -sn - g2h[j];
+            g1h[j] = tf32_hi(g1[j]);
+            g1l2[e] = g1[j] - g1h[j];
+            g2h[j] = tf32_hi(g2[j]);
+            g2l2[e] = g2[j] - g2h[j];
           }
           pk[0][jj] = pack_bf16(g1h[2 * jj], g1h[2 * jj + 1]);
           pk[1][jj] = pack_bf16(g1l2[0], g1l2[1]);
@@ -813,11 +748,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           pk[3][jj] = pack_bf16(g2l2[0], g2l2[1]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // next chunk's coordinates (latency hidden behind the wait)
-          const int k = (kc + 1) * BK + ks * UMMA_K + j;
+        for (int j = 0; j < 4; ++j) {  // next chunk's coordinates (latency hidden behind the wait)
+          const int k = (kc + 1) * BK + ks * UMMA_K + half * 4 + j;
           xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
         }
+#ifdef DLUX_DEBUG_TIMING
+        const long long tg1_ = clock64();
         mbar_wait(emptyG_bar(stage), phase ^ 1);
+        dbg_gw += clock64() - tg1_;
+#else
+        mbar_wait(emptyG_bar(stage), phase ^ 1);
+#endif
         tc_fence_after();
         const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS);
         tmem_st8(g0 + ks * UMMA_K, g1h);        // tf32 G1_hi: columns [0,16)
@@ -827,23 +768,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          if constexpr (PAIR) mbar_arrive_cluster(fullG_bar(stage) + lead_delta);
-          else mbar_arrive(fullG_bar(stage));
-        }
+        if (lane == 0) mbar_arrive_cluster(fullG_bar(stage) + lead_delta);
         if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
     }
+#ifdef DLUX_DEBUG_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == FIRST_GEN_WARP || warp == FIRST_GEN_WARP + 5))
+      printf("GEN%d: total %lld  wait emptyG %lld\n", warp, clock64() - dbg_gstart, dbg_gw);
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // no CTA exits while its peer may still multicast into it
   if (warp == 0) {
-    if constexpr (PAIR)
-      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
-    else
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
