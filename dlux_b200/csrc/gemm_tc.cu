@@ -284,11 +284,20 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
     const int cc = 4 * (lane & 3);
     const int part = (lane >> 2) & 1;
     const int n_first = nq0 + (lane >> 3);
+#ifdef DLUX_DEBUG_NOSTG  // timing experiment: all the epilogue's work, its stores redirected to shared memory
+    const bool real = tot[5] == 123.456f;
+    const int p4 = real ? pitch4(p.rows) : 0, p8 = real ? pitch8(p.rows) : 0;
+    const size_t row0 = (size_t)item * p.n_out + n_first;
+    float* hp0 = real ? p.out.hi[part] + row0 * p4 + m0 + cc : stg + cc;
+    __nv_bfloat16* hb0 = real ? p.out.b[2 * part] + row0 * p8 + m0 + cc : reinterpret_cast<__nv_bfloat16*>(stg) + cc;
+    __nv_bfloat16* lb0 = real ? p.out.b[2 * part + 1] + row0 * p8 + m0 + cc : reinterpret_cast<__nv_bfloat16*>(stg) + cc;
+#else
     const int p4 = pitch4(p.rows), p8 = pitch8(p.rows);
     const size_t row0 = (size_t)item * p.n_out + n_first;
     float* hp0 = p.out.hi[part] + row0 * p4 + m0 + cc;
     __nv_bfloat16* hb0 = p.out.b[2 * part] + row0 * p8 + m0 + cc;
     __nv_bfloat16* lb0 = p.out.b[2 * part + 1] + row0 * p8 + m0 + cc;
+#endif
 #pragma unroll
     for (int s = 0; s < BM / STG_COLS; ++s) {
       const int c0 = s * STG_COLS;
@@ -338,7 +347,15 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
     const int cc = 2 * (lane & 7);
     const int j0 = lane >> 3;
     const bool vec = (p.rows & 1) == 0;  // 16-byte alignment of (n * rows + even column) complex pairs
+#ifdef DLUX_DEBUG_NOSTG
+    const bool real = tot[5] == 123.456f;
+    const int prow = real ? p.rows : 0;
+    float2* out0 = real ? p.out_c64 + ((size_t)item * p.n_out + nq0 + j0) * p.rows + m0 + cc
+                        : reinterpret_cast<float2*>(stg) + cc;
+#else
+    const int prow = p.rows;
     float2* out0 = p.out_c64 + ((size_t)item * p.n_out + nq0 + j0) * p.rows + m0 + cc;
+#endif
 #pragma unroll
     for (int s = 0; s < BM / STG_COLS; ++s) {
       const int c0 = s * STG_COLS;
@@ -359,7 +376,7 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           if (nq0 + j0 + 4 * it < p.n_out) {
-            float2* out = out0 + (size_t)(4 * it) * p.rows + c0;
+            float2* out = out0 + (size_t)(4 * it) * prow + c0;
             if (vec && c0 + cc + 2 <= mmax) {
               *reinterpret_cast<float4*>(out) = make_float4(re[it].x, im[it].x, re[it].y, im[it].y);
             } else {
@@ -750,7 +767,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // next chunk's coordinates (latency hidden behind the wait)
           const int k = (kc + 1) * BK + ks * UMMA_K + half * 4 + j;
+#ifdef DLUX_DEBUG_NOXLD
+          xk[j] = (float)k * 1e-3f;
+#else
           xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
+#endif
         }
 #ifdef DLUX_DEBUG_TIMING
         const long long tg1_ = clock64();
