@@ -2,24 +2,24 @@
 //
 //   Out[n][m] = sum_k G[n][k] * Data[m][k],   G[n][k] = exp(i * fl(sign2pi * fl(kvec[k]*nvec[n])))
 //
-// One work unit = 64 output coordinates n x 256 data rows m, computed as TWO 64 x 128 tiles
-// (a, b) that share every generated phasor -- generation, not the tensor pipe, is the
-// scarce resource, so each phasor is used for 256 data rows.  The MMA is issued in its
-// "TS" form:
+// A CTA pair (cluster of 2, tcgen05.mma.cta_group::2) works on one unit = 128 output coordinates
+// n (64 per CTA) x 256 data rows m, computed as TWO tiles (a, b) of 128 data rows that share
+// every generated phasor -- generation, not the tensor pipe, is the scarce resource, so each
+// phasor is used for 256 data rows.  The MMA is issued in its "TS" form, M = 256 over the pair:
 //
-// * A operand = the DFT phasors, in TENSOR MEMORY.  They are never materialised in HBM nor
-//   in shared memory: generator warps evaluate the reference's float32 phase argument, a
-//   Cody-Waite/minimax sincos, split hi/lo (tf32) and write the operand tiles straight
-//   from registers with tcgen05.st.  TMEM lane 2j holds the "real" row of phasor column
-//   j and lane 2j+1 its "imaginary" row, in two arrangements
+// * A operand = the DFT phasors, in TENSOR MEMORY (128 lanes in each CTA).  They are never
+//   materialised in HBM nor in shared memory: generator warps evaluate the reference's float32
+//   phase argument, an exact Cody-Waite reduction + MUFU sincos, split hi/lo (tf32) and write
+//   the operand tiles straight from registers with tcgen05.st.  TMEM lane 2j holds the "real"
+//   row of phasor column j and lane 2j+1 its "imaginary" row, in two arrangements
 //       G1 = (cos | sin),   G2 = (-sin | cos)        (row 2j | row 2j+1)
 //   so that  D = G1 * Re(Data)^T + G2 * Im(Data)^T  has Re(Out[j][:]) in lane 2j and
-//   Im(Out[j][:]) in lane 2j+1: one M128 x N128 MMA yields both complex parts.
+//   Im(Out[j][:]) in lane 2j+1: one MMA yields both complex parts.
 // * B operand = the data (PlaneSet, common.cuh): tf32 "hi" planes in float32 plus bf16 copies
-//   of hi and of the residual lo, streamed by TMA (cp.async.bulk.tensor, K-major, SWIZZLE_64B
-//   for the 64-byte fp32 rows and SWIZZLE_32B for the 32-byte bf16 rows) into a 3-deep
-//   shared-memory ring of 64 KiB stages (both tiles).  Shared memory carries only this
-//   operand.
+//   of hi and of the residual lo, streamed by TMA (cp.async.bulk.tensor.cta_group::2, K-major,
+//   SWIZZLE_64B for the 64-byte fp32 rows and SWIZZLE_32B for the 32-byte bf16 rows).  Each CTA
+//   holds 64 of the 128 rows of a tile: 32 KiB stages (both tiles), a 6-deep ring, completion
+//   bytes counted on the leader CTA's mbarrier.  Shared memory carries only this operand.
 // * Split precision ("TF32 + 2xBF16"): per 16-k chunk and tile, 4 tcgen05.mma kind::tf32
 //   (hi*hi, K=8) + 4 kind::f16 bf16 MMAs (hi*lo and lo*hi, K=16) accumulate into the same
 //   fp32 TMEM accumulator -- 8 MMA slots instead of the 12 of 3xTF32; lo*lo is dropped.
@@ -30,13 +30,15 @@
 //   tile's epilogue warpgroup with tcgen05.ld and added, round-to-nearest, into fp32
 //   registers (Ootomo & Yokota's scheme for error-corrected TF32 GEMM).  Draining overlaps
 //   the MMAs of the other tile / next partial.
-// * CTA pairs (thread-block clusters of 2) work on the same data rows and neighbouring
-//   n-tiles: each CTA fetches one of the two data tiles of a stage and TMA-multicasts it to
-//   both, halving the L2 -> SM traffic that bounded the single-CTA version (ncu: 8.9 TB/s).
+// * Barriers: the "full" side of every ring lives in the LEADER CTA (rank 0), which alone
+//   issues MMAs: fullA (both CTAs' TMA producers), fullG (both CTAs' generator warps), tempty
+//   (both CTAs' drain warpgroups) -- remote arrivals are mbarrier.arrive.relaxed.cluster.  The
+//   "empty" side is local to each CTA and signalled by tcgen05.commit ... multicast::cluster:
+//   emptyA, emptyG, tfull.
 // * Persistent CTAs, one per SM, 20 warps in 5 warpgroups: WG0 / WG1 = drain + fused
 //   epilogue of tile a / b (setmaxnreg.inc: 128 running totals per thread), WG2 = TMA
-//   producer + one MMA issuer warp per tile (setmaxnreg.dec), WG3 / WG4 = phasor generators (two warps per TMEM
-//   lane quarter, one per k-step of the chunk).
+//   producer + one MMA issuer warp per tile (setmaxnreg.dec), WG3 / WG4 = phasor generators
+//   (two warps per TMEM lane quarter, one per k-step of the chunk).
 // TMEM map (512 columns): [0,384) three partial accumulators, [384,512) two phasor stages
 // of 64 columns: G1_hi, G2_hi as tf32 (16 k -> 16 columns each) and G1_hi, G1_lo, G2_hi,
 // G2_lo as packed bf16 (16 k -> 8 columns each).
@@ -84,7 +86,7 @@ constexpr int REGS_LAUNCH = 96;    // 65536 / 640 rounded down to a multiple of 
 constexpr int REGS_EPI = 152, REGS_CTRL = 40, REGS_GEN = 64;        // setmaxnreg budgets
 static_assert(256 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_GEN),
               "register budget");
-constexpr int CLUSTER = 2;         // CTAs sharing (multicasting) the data tiles
+constexpr int CLUSTER = 2;         // the CTA pair of a cta_group::2 MMA
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 2560 /*epilogue staging*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
