@@ -439,8 +439,8 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
                      const float* phase, const float* wavenumber, const float* scale_out,
                      const float* norm, const float* weights, const float* delta_xy,
                      const void* field, const float* psf_bar, float* opd_bar, float* phase_bar,
-                     float* weights_bar, float* delta_bar, float* transmission_bar, void* scratch,
-                     size_t scratch_bytes, void* cuda_stream) {
+                     float* weights_bar, float* delta_bar, float* transmission_bar, float* scale_bar,
+                     void* scratch, size_t scratch_bytes, void* cuda_stream) {
   int rc = check_poly_desc(d);
   if (rc != DLUX_OK) return rc;
   if (!wavenumber || !scale_out || !weights || !field || !psf_bar || !scratch) return DLUX_ERR_ARG;
@@ -457,46 +457,63 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   if (rc) return rc;
   if (weights_bar && (rc = launch_zero(weights_bar, (size_t)items, st))) return rc;
   if (delta_bar && (rc = launch_zero(delta_bar, (size_t)items * 2, st))) return rc;
+  if (scale_bar && (rc = launch_zero(scale_bar, (size_t)items, st))) return rc;
   if (transmission_bar && !T) return DLUX_ERR_ARG;
-  const bool need_pupil_grad = opd_bar || phase_bar || delta_bar || transmission_bar;
+  const bool need_pupil_grad = opd_bar || phase_bar || delta_bar || transmission_bar || scale_bar;
   const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
   const int exact = d->precision == DLUX_PREC_FP32;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
-    rc = launch_cotangent(M, c, (const float2*)field + (size_t)b0 * M * M, psf_bar, weights + b0,
-                          s.ebar_pl, exact, weights_bar ? weights_bar + b0 : nullptr, st);
-    if (rc) return rc;
-    if (!need_pupil_grad) continue;
-    rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
-                       1, s.xin, s.uout, st);
-    if (rc) return rc;
-    GemmParams g{};
-    fill_stage(g, true, 0, N, M, c, s.xin, s.uout, sign2pi);
-    g.a = s.ebar_pl;
-    g.out = s.mid_pl;
-    g.exact = exact;
-    g.mode = EPI_PLANES;
-    rc = run_gemm(g, d->precision, st);
-    if (rc) return rc;
-    GemmParams h{};
-    fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
-    h.a = s.mid_pl;
-    h.exact = exact;
-    h.mode = EPI_C64;
-    h.scale = s.norm_item + b0;
-    h.out_c64 = s.qbuf;
-    rc = run_gemm(h, d->precision, st);
-    if (rc) return rc;
-    const float a0 = 1.0f / (float)((long long)N * N);
-    if (opd_bar || phase_bar || transmission_bar) {
-      rc = launch_grad_reduce((size_t)N * N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
-                              opd_bar, phase_bar, transmission_bar, b0 > 0, st);
+    // pass 0: Q = adjoint(Ebar) -> opd / phase / transmission / offset gradients.  Passes 1, 2
+    // (scale_bar only): the output coordinate is u_a = scale_out (a - (M-1)/2) - delta, so
+    // d/d scale_out weighs Ebar with the pixel index along x, then along y, and reduces the
+    // adjoint like the offset gradient (opposite sign).
+    const int n_pass = scale_bar ? 3 : 1;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      rc = launch_cotangent(M, c, (const float2*)field + (size_t)b0 * M * M, psf_bar, weights + b0,
+                            s.ebar_pl, exact, (pass == 0 && weights_bar) ? weights_bar + b0 : nullptr,
+                            pass - 1, st);
       if (rc) return rc;
-    }
-    if (delta_bar) {
-      rc = launch_pos_grad(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
-                           delta_bar + 2 * (size_t)b0, st);
+      if (!need_pupil_grad) continue;
+      if (pass == 0) {
+        rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
+                           1, s.xin, s.uout, st);
+        if (rc) return rc;
+      }
+      GemmParams g{};
+      fill_stage(g, true, 0, N, M, c, s.xin, s.uout, sign2pi);
+      g.a = s.ebar_pl;
+      g.out = s.mid_pl;
+      g.exact = exact;
+      g.mode = EPI_PLANES;
+      rc = run_gemm(g, d->precision, st);
       if (rc) return rc;
+      GemmParams h{};
+      fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
+      h.a = s.mid_pl;
+      h.exact = exact;
+      h.mode = EPI_C64;
+      h.scale = s.norm_item + b0;
+      h.out_c64 = s.qbuf;
+      rc = run_gemm(h, d->precision, st);
+      if (rc) return rc;
+      const float a0 = 1.0f / (float)((long long)N * N);
+      if (pass > 0) {
+        rc = launch_pos_grad(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0, scale_bar + b0,
+                             pass, st);
+        if (rc) return rc;
+        continue;
+      }
+      if (opd_bar || phase_bar || transmission_bar) {
+        rc = launch_grad_reduce((size_t)N * N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
+                                opd_bar, phase_bar, transmission_bar, b0 > 0, st);
+        if (rc) return rc;
+      }
+      if (delta_bar) {
+        rc = launch_pos_grad(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
+                             delta_bar + 2 * (size_t)b0, 0, st);
+        if (rc) return rc;
+      }
     }
   }
   if (transmission_bar && d->normalise) {

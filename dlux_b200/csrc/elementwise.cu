@@ -230,19 +230,23 @@ int launch_pupil(int N, int L, const float* T, const float* opd, const float* ph
 // cotangent of the field: Ebar = 2 w psf_bar .* E (planes), w_bar[item] = sum psf_bar |E|^2
 __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
                                  const float* __restrict__ psf_bar, const float* __restrict__ w,
-                                 PlaneSet out, int exact, float* __restrict__ w_bar) {
+                                 PlaneSet out, int exact, float* __restrict__ w_bar, int weight_axis) {
   __shared__ float sm[256];
   const size_t n = (size_t)M * M;
   const int item = blockIdx.y;
   const float w2 = 2.0f * w[item];
+  const float half = 0.5f * (float)(M - 1);
   float acc = 0.0f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
     const float2 e = field[(size_t)item * n + i];
     const float g = psf_bar[i];
     acc += g * (e.x * e.x + e.y * e.y);
-    const float re = w2 * g * e.x, im = w2 * g * e.y;
     const size_t r = i / M;
+    float wg = w2 * g;
+    if (weight_axis == 0) wg *= (float)(i - r * M) - half;
+    else if (weight_axis == 1) wg *= (float)r - half;
+    const float re = wg * e.x, im = wg * e.y;
     const size_t row = (size_t)item * M + r;
     plane_store(out, row * pitch4(M) + (i - r * M), row * pitch8(M) + (i - r * M), re, im, exact);
   }
@@ -258,7 +262,7 @@ __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
 }
 
 int launch_cotangent(int M, int n_items, const float2* field, const float* psf_bar, const float* w,
-                     const PlaneSet& out, int exact, float* w_bar, cudaStream_t st) {
+                     const PlaneSet& out, int exact, float* w_bar, int weight_axis, cudaStream_t st) {
   for (int b0 = 0; b0 < n_items; b0 += 65535) {
     int nb = n_items - b0 < 65535 ? n_items - b0 : 65535;
     const size_t off = (size_t)b0 * M * M;
@@ -267,7 +271,7 @@ int launch_cotangent(int M, int n_items, const float2* field, const float* psf_b
     for (int i = 0; i < 4; ++i) if (o.b[i]) o.b[i] += (size_t)b0 * M * pitch8(M);
     dim3 grid(grid_for((size_t)M * M, 256, 64), nb);
     cotangent_kernel<<<grid, 256, 0, st>>>(M, field + off, psf_bar, w + b0, o, exact,
-                                            w_bar ? w_bar + b0 : nullptr);
+                                            w_bar ? w_bar + b0 : nullptr, weight_axis);
     note_launch();
   }
   return check_launch("cotangent");
@@ -484,7 +488,7 @@ int launch_tbar_finalize(size_t npix, const float* T, const float* amp_scale, fl
 __global__ void pos_grad_kernel(int N, const float2* __restrict__ q, const float* __restrict__ k,
                                 const float* __restrict__ T, const float* __restrict__ opd,
                                 const float* __restrict__ phase, const float* __restrict__ amp_scale,
-                                float a0, float* __restrict__ delta_bar) {
+                                float a0, float* __restrict__ out, int sel) {
   __shared__ float smx[8], smy[8];
   const int item = blockIdx.y;
   const size_t npix = (size_t)N * N;
@@ -515,18 +519,22 @@ __global__ void pos_grad_kernel(int N, const float2* __restrict__ q, const float
     float sx = 0.0f, sy = 0.0f;
     for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) { sx += smx[wv]; sy += smy[wv]; }
     const float two_pi = 6.283185307179586f;
-    atomicAdd(delta_bar + 2 * item, two_pi * sx);
-    atomicAdd(delta_bar + 2 * item + 1, two_pi * sy);
+    if (sel == 0) {
+      atomicAdd(out + 2 * item, two_pi * sx);
+      atomicAdd(out + 2 * item + 1, two_pi * sy);
+    } else {
+      atomicAdd(out + item, -two_pi * (sel == 1 ? sx : sy));
+    }
   }
 }
 
 int launch_pos_grad(int N, int n_items, const float2* q, const float* k, const float* T, const float* opd,
-                    const float* phase, const float* amp_scale, float a0, float* delta_bar, cudaStream_t st) {
+                    const float* phase, const float* amp_scale, float a0, float* out, int sel, cudaStream_t st) {
   for (int b0 = 0; b0 < n_items; b0 += 65535) {
     const int nb = n_items - b0 < 65535 ? n_items - b0 : 65535;
     dim3 grid(grid_for((size_t)N * N, 256, 32), nb);
     pos_grad_kernel<<<grid, 256, 0, st>>>(N, q + (size_t)b0 * N * N, k + b0, T, opd, phase, amp_scale, a0,
-                                          delta_bar + 2 * (size_t)b0);
+                                          out + (sel == 0 ? 2 : 1) * (size_t)b0, sel);
     note_launch();
   }
   return check_launch("pos_grad");

@@ -119,7 +119,9 @@ class _FocalSystem(LayeredOpticalSystem):
         super().__init__(wf_npixels, diameter, layers, **kw)
         self.psf_npixels = int(psf_npixels)
         self.oversample = int(oversample)
-        self.psf_pixel_scale = np.float32(psf_pixel_scale)
+        # a torch scalar (requires_grad) makes the pixel scale a fitted parameter of the fused route
+        self.psf_pixel_scale = (psf_pixel_scale if torch.is_tensor(psf_pixel_scale)
+                                else np.float32(psf_pixel_scale))
 
     # -- units --------------------------------------------------------------------
     def _focal_args(self):  # pragma: no cover - abstract
@@ -179,6 +181,13 @@ class _FocalSystem(LayeredOpticalSystem):
         """Per-wavelength device operands (wavenumber, scale_out, norm, wavelengths), cached:
         a fitting loop calls propagate with the same wavelength grid every step."""
         npix, ps, fl = self._focal_args()
+        if torch.is_tensor(ps):   # differentiable pixel scale: no cache, geometry through autograd
+            ps_in = np.float32(self.diameter / np.float32(self.wf_npixels))
+            wl_dev = torch.as_tensor(wavelengths, device=self.device)
+            scale_out, norm = _prop.mft_geometry(wl_dev, self.wf_npixels, ps_in, npix,
+                                                 ps.to(self.device, torch.float32), fl)
+            k = np.float32(2 * math.pi) / wl_dev
+            return npix, scale_out, norm, k, wl_dev
         key = (wavelengths.tobytes(), npix, float(ps), None if fl is None else float(fl),
                float(self.diameter), self.wf_npixels, str(self.device))
         cache = self.__dict__.setdefault("_geom_cache", {})
@@ -228,6 +237,9 @@ class AngularOpticalSystem(_FocalSystem):
     """optical_systems.py:597-680: psf_pixel_scale in arcseconds."""
 
     def _focal_args(self):                              # :676-680
+        if torch.is_tensor(self.psf_pixel_scale):
+            p = self.psf_pixel_scale.to(self.device, torch.float32)
+            return (self.psf_npixels * self.oversample, _prop.arcsec2rad(p / np.float32(self.oversample)), None)
         true_pixel_scale = np.float32(self.psf_pixel_scale / np.float32(self.oversample))
         return (self.psf_npixels * self.oversample, np.float32(_prop.arcsec2rad(true_pixel_scale)),
                 None)
@@ -244,5 +256,8 @@ class CartesianOpticalSystem(_FocalSystem):
         self.focal_length = np.float32(focal_length)
 
     def _focal_args(self):                              # :771-775
+        if torch.is_tensor(self.psf_pixel_scale):
+            p = self.psf_pixel_scale.to(self.device, torch.float32)
+            return (self.psf_npixels * self.oversample, p * np.float32(1e-6 / self.oversample), None)
         true_pixel_scale = np.float32(self.psf_pixel_scale / np.float32(self.oversample))
         return (self.psf_npixels * self.oversample, np.float32(1e-6 * true_pixel_scale), None)

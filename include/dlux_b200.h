@@ -163,6 +163,7 @@ DLUX_API int dlux_polypsf_bwd(const dlux_polypsf_desc* desc,
                      float* weights_bar,       /* [S, L] or NULL */
                      float* delta_bar,         /* [S, L, 2] or NULL */
                      float* transmission_bar,  /* [N, N] or NULL (incl. the power-normalisation term) */
+                     float* scale_bar,         /* [S, L] or NULL: d/d scale_out (two extra adjoint MFTs) */
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------
