@@ -203,6 +203,20 @@ class _FocalSystem(LayeredOpticalSystem):
             cache[key] = hit
         return hit
 
+    def _upload(self, a):
+        """Device copy of a small host array, cached by content: a fitting loop passes the same
+        positions / weights every step, and a pageable host->device copy would serialise the
+        host with the stream each time."""
+        a = np.ascontiguousarray(_np32(a))
+        key = (a.shape, a.tobytes())
+        cache = self.__dict__.setdefault("_upload_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) > 32:
+                cache.clear()
+            hit = cache[key] = torch.as_tensor(a, device=self.device)
+        return hit
+
     def fused_propagate(self, wavelengths, offsets, weights):
         """psf = sum_{s,l} weights[s,l] |E_sl|^2 in one fused call.
         wavelengths [L] (host), offsets [S,2] rad (host or device), weights [S,L]."""
@@ -213,13 +227,13 @@ class _FocalSystem(LayeredOpticalSystem):
         dev = self.device
         wavelengths = np.atleast_1d(_np32(wavelengths))
         npix, scale_out, norm, k, wl_dev = self._geometry(wavelengths)
-        up = lambda a: torch.as_tensor(a, device=dev)
-        offsets_t = offsets.to(dev, torch.float32) if torch.is_tensor(offsets) else up(_np32(offsets))
+        up = self._upload
+        offsets_t = offsets.to(dev, torch.float32) if torch.is_tensor(offsets) else up(offsets)
         offsets_t = offsets_t.reshape(-1, 2)
         # tilt (wavefronts.py:370-395) folded into the output coordinates:
         # delta = theta * D / lambda, in fringes
         delta = (offsets_t[:, None, :] * self.diameter) / wl_dev[None, :, None]
-        weights_t = weights.to(dev, torch.float32) if torch.is_tensor(weights) else up(_np32(weights))
+        weights_t = weights.to(dev, torch.float32) if torch.is_tensor(weights) else up(weights)
         weights_t = weights_t.reshape(offsets_t.shape[0], len(wavelengths))
         cont = lambda t: None if t is None else t.contiguous()
         return ops.PolyPSFFunction.apply(cont(opd), cont(phase), weights_t.contiguous(), delta.contiguous(),
