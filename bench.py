@@ -194,8 +194,8 @@ def run_ours(args):
         psf, field = ops.polypsf_fwd(T_d, opd, None, k_d, s_d, nrm_d, w_d, delta_d, N, M, True, None, True)
         if world > 1:
             dist.all_reduce(psf)
-        opd_bar, _, _, _, _, _ = ops.polypsf_bwd(T_d, opd, None, k_d, s_d, nrm_d, w_d, delta_d, field, G_d, N, M,
-                                        True, None, True, False, False)
+        opd_bar = ops.polypsf_bwd(T_d, opd, None, k_d, s_d, nrm_d, w_d, delta_d, field, G_d, N, M,
+                                        True, None, True, False, False)[0]
         cbar = ops.basis_reduce(basis_d, opd_bar, coeffs_d.shape)
         if world > 1:
             dist.all_reduce(cbar)

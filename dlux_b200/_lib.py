@@ -43,7 +43,7 @@ SIGNATURES = {
     "dlux_mft_coords": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "dlux_polypsf_scratch_bytes": (C.c_size_t, [C.POINTER(PolyPsfDesc)]),
     "dlux_polypsf_fwd": (C.c_int, [C.POINTER(PolyPsfDesc)] + [_P] * 10 + [_P, C.c_size_t, _P]),
-    "dlux_polypsf_bwd": (C.c_int, [C.POINTER(PolyPsfDesc)] + [_P] * 16 + [_P, C.c_size_t, _P]),
+    "dlux_polypsf_bwd": (C.c_int, [C.POINTER(PolyPsfDesc)] + [_P] * 17 + [_P, C.c_size_t, _P]),
     "dlux_basis_eval": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, _P, _P]),
     "dlux_basis_reduce": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, _P]),
 }

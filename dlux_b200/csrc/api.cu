@@ -440,7 +440,7 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
                      const float* norm, const float* weights, const float* delta_xy,
                      const void* field, const float* psf_bar, float* opd_bar, float* phase_bar,
                      float* weights_bar, float* delta_bar, float* transmission_bar, float* scale_bar,
-                     void* scratch, size_t scratch_bytes, void* cuda_stream) {
+                     float* wavenumber_bar, void* scratch, size_t scratch_bytes, void* cuda_stream) {
   int rc = check_poly_desc(d);
   if (rc != DLUX_OK) return rc;
   if (!wavenumber || !scale_out || !weights || !field || !psf_bar || !scratch) return DLUX_ERR_ARG;
@@ -458,8 +458,10 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   if (weights_bar && (rc = launch_zero(weights_bar, (size_t)items, st))) return rc;
   if (delta_bar && (rc = launch_zero(delta_bar, (size_t)items * 2, st))) return rc;
   if (scale_bar && (rc = launch_zero(scale_bar, (size_t)items, st))) return rc;
+  if (wavenumber_bar && (rc = launch_zero(wavenumber_bar, (size_t)items, st))) return rc;
   if (transmission_bar && !T) return DLUX_ERR_ARG;
-  const bool need_pupil_grad = opd_bar || phase_bar || delta_bar || transmission_bar || scale_bar;
+  const bool need_pupil_grad =
+      opd_bar || phase_bar || delta_bar || transmission_bar || scale_bar || wavenumber_bar;
   const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
   const int exact = d->precision == DLUX_PREC_FP32;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
@@ -512,6 +514,11 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
       if (delta_bar) {
         rc = launch_pos_grad(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
                              delta_bar + 2 * (size_t)b0, 0, st);
+        if (rc) return rc;
+      }
+      if (wavenumber_bar && opd) {
+        rc = launch_pos_grad(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
+                             wavenumber_bar + b0, 3, st);
         if (rc) return rc;
       }
     }

@@ -185,7 +185,8 @@ int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* o
                         float* coeff_bar, cudaStream_t st);
 int launch_zero(float* p, size_t n, cudaStream_t st);
 // delta_bar[item][axis] = 2 pi sum_ij x_axis(i or j) * Im(conj(P_ij) Q_ij[item])  (source-offset VJP)
-// sel 0: delta_bar[item][2] += 2 pi (sum x g, sum y g); sel 1 / 2: out[item] -= 2 pi sum x g / sum y g
+// sel 0: delta_bar[item][2] += 2 pi (sum x g, sum y g); sel 1 / 2: out[item] -= 2 pi sum x g / sum y g;
+// sel 3: out[item] += sum opd g   (g = Im(conj(P) Q))
 int launch_pos_grad(int N, int n_items, const float2* q, const float* k, const float* T, const float* opd,
                     const float* phase, const float* amp_scale, float a0, float* out, int sel, cudaStream_t st);
 // psf[i] (+)= sum_item w[item] |field[item][i]|^2

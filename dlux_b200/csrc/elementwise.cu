@@ -505,8 +505,12 @@ __global__ void pos_grad_kernel(int N, const float2* __restrict__ q, const float
       fast_sincos(__fmul_rn(kw, opd ? opd[i] : 0.0f) + (phase ? phase[i] : 0.0f), &sn, &cs);
       const float g = amp * t * (cs * v.y - sn * v.x);
       const int r = (int)(i / N), c = (int)(i - (size_t)r * N);
-      ax = fmaf(((float)c - half) * inv, g, ax);
-      ay = fmaf(((float)r - half) * inv, g, ay);
+      if (sel == 3) {
+        ax = fmaf(opd ? opd[i] : 0.0f, g, ax);   // d phase / d k = opd
+      } else {
+        ax = fmaf(((float)c - half) * inv, g, ax);
+        ay = fmaf(((float)r - half) * inv, g, ay);
+      }
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -522,6 +526,8 @@ __global__ void pos_grad_kernel(int N, const float2* __restrict__ q, const float
     if (sel == 0) {
       atomicAdd(out + 2 * item, two_pi * sx);
       atomicAdd(out + 2 * item + 1, two_pi * sy);
+    } else if (sel == 3) {
+      atomicAdd(out + item, sx);
     } else {
       atomicAdd(out + item, -two_pi * (sel == 1 ? sx : sy));
     }

@@ -181,7 +181,7 @@ def polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, 
 def polypsf_bwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,
                 psf_bar, n_pupil, n_psf, normalise=True, precision=None, want_opd=True,
                 want_phase=False, want_weights=False, want_delta=False, want_transmission=False,
-                want_scale=False):
+                want_scale=False, want_wavenumber=False):
     lib = _lib.load()
     dev = wavenumber.device
     L = wavenumber.numel()
@@ -197,27 +197,29 @@ def polypsf_bwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, 
     d_bar = mk(S, L, 2) if want_delta else None
     t_bar = mk(n_pupil, n_pupil) if want_transmission else None
     s_bar = mk(S, L) if want_scale else None
+    k_bar = mk(S, L) if want_wavenumber else None
     psf_bar = psf_bar.to(torch.float32).contiguous()
     with torch.cuda.device(dev):
         check(lib.dlux_polypsf_bwd(C.byref(desc), _ptr(transmission), _ptr(opd), _ptr(phase),
                                    _ptr(wavenumber), _ptr(scale_out), _ptr(norm), _ptr(weights),
                                    _ptr(delta_xy), _ptr(field), _ptr(psf_bar), _ptr(opd_bar),
                                    _ptr(phase_bar), _ptr(w_bar), _ptr(d_bar), _ptr(t_bar), _ptr(s_bar),
-                                   _ptr(scratch), scratch.numel(), _stream(dev)), "dlux_polypsf_bwd")
-    return opd_bar, phase_bar, w_bar, d_bar, t_bar, s_bar
+                                   _ptr(k_bar), _ptr(scratch), scratch.numel(), _stream(dev)),
+              "dlux_polypsf_bwd")
+    return opd_bar, phase_bar, w_bar, d_bar, t_bar, s_bar, k_bar
 
 
 class PolyPSFFunction(torch.autograd.Function):
     """psf = sum_{s,l} w_sl |MFT_l(amp T exp(i(k_l opd + phase)))|^2 with gradients w.r.t.
-    opd, phase, weights, the source offsets delta_xy, the transmission and the geometry scalars
-    scale_out / norm (-> psf_pixel_scale) (the fused primitive behind OpticalSystem.propagate /
+    opd, phase, weights, the source offsets delta_xy, the transmission, the wavenumbers and the
+    geometry scalars scale_out / norm (-> psf_pixel_scale, wavelengths) (the fused primitive behind OpticalSystem.propagate /
     PointSources.model).  scale_out and norm are [L] (shared by the sources)."""
 
     @staticmethod
     def forward(ctx, opd, phase, weights, delta_xy, transmission, wavenumber, scale_out, norm,
                 n_pupil, n_psf, normalise, precision):
         need = any(t is not None and t.requires_grad
-                   for t in (opd, phase, weights, delta_xy, transmission, scale_out, norm))
+                   for t in (opd, phase, weights, delta_xy, transmission, wavenumber, scale_out, norm))
         psf, field = polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights,
                                  delta_xy, n_pupil, n_psf, normalise, precision, save_field=need)
         ctx.save_for_backward(*(t for t in (opd, phase, weights, transmission, wavenumber, scale_out,
@@ -235,25 +237,28 @@ class PolyPSFFunction(torch.autograd.Function):
         n_pupil, n_psf, normalise, precision, wshape = ctx.cfg
         want = ctx.needs_input_grad
         want_norm = bool(want[7])
-        opd_bar, phase_bar, w_bar, d_bar, t_bar, s_bar = polypsf_bwd(
+        opd_bar, phase_bar, w_bar, d_bar, t_bar, s_bar, k_bar = polypsf_bwd(
             transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,
             psf_bar, n_pupil, n_psf, normalise, precision, want_opd=bool(want[0]),
             want_phase=bool(want[1]), want_weights=bool(want[2]) or want_norm,
             want_delta=bool(want[3]) and delta_xy is not None,
-            want_transmission=bool(want[4]) and transmission is not None, want_scale=bool(want[6]))
+            want_transmission=bool(want[4]) and transmission is not None, want_scale=bool(want[6]),
+            want_wavenumber=bool(want[5]) and opd is not None)
         L = wavenumber.numel()
         n_bar = None
         if want_norm:   # psf is quadratic in norm: d/d norm_l = 2 sum_s w_sl <G, |E_sl|^2> / norm_l
             n_bar = (2.0 * (weights.reshape(-1, L) * w_bar.reshape(-1, L)).sum(0) / norm).reshape(norm.shape)
         if s_bar is not None:
             s_bar = s_bar.reshape(-1, L).sum(0).reshape(scale_out.shape)
+        if k_bar is not None:
+            k_bar = k_bar.reshape(-1, L).sum(0).reshape(wavenumber.shape)
         if not want[2]:
             w_bar = None
         if w_bar is not None:
             w_bar = w_bar.reshape(wshape)
         if d_bar is not None:
             d_bar = d_bar.reshape(delta_xy.shape)
-        return (opd_bar, phase_bar, w_bar, d_bar, t_bar, None, s_bar, n_bar) + (None,) * 4
+        return (opd_bar, phase_bar, w_bar, d_bar, t_bar, k_bar, s_bar, n_bar) + (None,) * 4
 
 
 # --------------------------------------------------------------------------- basis

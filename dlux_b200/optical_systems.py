@@ -43,6 +43,9 @@ class BaseOpticalSystem:
             raise ValueError(
                 "Cannot return both Wavefront and PSF objects. Choose one: "
                 "return_wf=True for Wavefront, or return_psf=True for PSF.")
+        wl_t = None
+        if torch.is_tensor(wavelengths) and wavelengths.is_cuda and wavelengths.requires_grad:
+            wl_t = torch.atleast_1d(wavelengths)       # differentiable leaf of the fused route
         wavelengths = np.atleast_1d(_np32(wavelengths))
         if weights is None:
             weights = np.ones_like(wavelengths) / np.float32(len(wavelengths))
@@ -61,6 +64,12 @@ class BaseOpticalSystem:
                 f"offset must be [x, y] array of shape (2,), "
                 f"got shape {tuple(offset.shape)}. "
                 "Pass offset as [on_axis_x, on_axis_y] angles in radians.")
+        if wl_t is not None:
+            if return_wf or not (getattr(self, "fused", False) and hasattr(self, "fused_propagate")
+                                 and self._fusable() is not None):
+                raise ValueError("differentiable wavelengths need the fused route (pupil-only layer stack)")
+            off = offset if torch.is_tensor(offset) else _np32(offset)
+            return self.fused_propagate(wl_t, off.reshape(1, 2), weights.reshape(1, -1))
         return self._propagate(wavelengths, offset, weights, return_wf)
 
     def _propagate(self, wavelengths, offset, weights, return_wf):
@@ -181,11 +190,13 @@ class _FocalSystem(LayeredOpticalSystem):
         """Per-wavelength device operands (wavenumber, scale_out, norm, wavelengths), cached:
         a fitting loop calls propagate with the same wavelength grid every step."""
         npix, ps, fl = self._focal_args()
-        if torch.is_tensor(ps):   # differentiable pixel scale: no cache, geometry through autograd
+        if torch.is_tensor(ps) or torch.is_tensor(wavelengths):
+            # differentiable pixel scale / wavelengths: no cache, geometry through autograd
             ps_in = np.float32(self.diameter / np.float32(self.wf_npixels))
-            wl_dev = torch.as_tensor(wavelengths, device=self.device)
-            scale_out, norm = _prop.mft_geometry(wl_dev, self.wf_npixels, ps_in, npix,
-                                                 ps.to(self.device, torch.float32), fl)
+            wl_dev = (wavelengths.to(self.device, torch.float32) if torch.is_tensor(wavelengths)
+                      else torch.as_tensor(wavelengths, device=self.device))
+            ps = ps.to(self.device, torch.float32) if torch.is_tensor(ps) else ps
+            scale_out, norm = _prop.mft_geometry(wl_dev, self.wf_npixels, ps_in, npix, ps, fl)
             k = np.float32(2 * math.pi) / wl_dev
             return npix, scale_out, norm, k, wl_dev
         key = (wavelengths.tobytes(), npix, float(ps), None if fl is None else float(fl),
@@ -225,7 +236,8 @@ class _FocalSystem(LayeredOpticalSystem):
             raise ValueError("layer stack is not pupil-only; use fused=False")
         T, opd, phase, normalise = parts
         dev = self.device
-        wavelengths = np.atleast_1d(_np32(wavelengths))
+        if not (torch.is_tensor(wavelengths) and wavelengths.requires_grad):
+            wavelengths = np.atleast_1d(_np32(wavelengths))
         npix, scale_out, norm, k, wl_dev = self._geometry(wavelengths)
         up = self._upload
         offsets_t = offsets.to(dev, torch.float32) if torch.is_tensor(offsets) else up(offsets)

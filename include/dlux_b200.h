@@ -164,6 +164,7 @@ DLUX_API int dlux_polypsf_bwd(const dlux_polypsf_desc* desc,
                      float* delta_bar,         /* [S, L, 2] or NULL */
                      float* transmission_bar,  /* [N, N] or NULL (incl. the power-normalisation term) */
                      float* scale_bar,         /* [S, L] or NULL: d/d scale_out (two extra adjoint MFTs) */
+                     float* wavenumber_bar,    /* [S, L] or NULL: d/d wavenumber through exp(i k opd) only */
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------

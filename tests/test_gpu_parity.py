@@ -351,6 +351,42 @@ def test_pixel_scale_gradient(dev):
         assert abs(got - fd) <= 2e-4 * abs(fd), (prec, got, fd)
 
 
+def test_wavelength_gradient(dev):
+    # d/d wavelength_l: through the wavenumber (exp(i k opd), wavenumber_bar), the fringe size
+    # (scale_out, norm) and the tilt (delta) -- all chained by autograd from dlux_polypsf_bwd's
+    # outputs; against central differences of the float64 oracle
+    import dlux_b200 as dl
+    from oracle import torch_twin
+    N, M = 64, 32
+    rng = np.random.default_rng(42)
+    od = _optics_dict(N, M, 4, 5)
+    G = rng.standard_normal((M, M))
+    wls0 = np.array([0.9e-6, 1.0e-6, 1.1e-6])
+    w = np.array([0.3, 0.3, 0.4], np.float32)
+    off = np.array([2.0e-7, -1.0e-7], np.float32)
+
+    def loss64(wls):
+        psf = torch_twin.poly_psf(od["transmission"], None, wls, w, diameter=1.0, psf_npixels=M,
+                                  pixel_scale_rad=0.05 * np.pi / 648000.0, offset=off, basis=od["basis"],
+                                  coefficients=od["coefficients"], dtype=np.float64)
+        return float((psf.numpy() * G).sum())
+
+    fd = np.zeros(3)
+    for l in range(3):
+        h = 1e-5 * wls0[l]
+        up_, dn_ = wls0.copy(), wls0.copy()
+        up_[l] += h
+        dn_[l] -= h
+        fd[l] = (loss64(up_) - loss64(dn_)) / (2 * h)
+    wl = torch.tensor(wls0, dtype=torch.float32, device=dev, requires_grad=True)
+    layer = dl.BasisOptic(od["basis"], od["transmission"], od["coefficients"], "opd", normalise=True, device=dev)
+    sys_ = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, 0.05, device=dev)
+    psf = sys_.propagate(wl, off, w)
+    (psf * torch.as_tensor(G.astype(np.float32), device=dev)).sum().backward()
+    got = wl.grad.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(got - fd) <= 3e-4 * np.abs(fd).max()), (got, fd)
+
+
 def test_config4_like_large_pupil_many_sources(dev):
     # BASELINE config 4 shape (scaled down in sources/wavelengths): 2048 px pupil with a binary
     # 0/pi phase mask, several stars, MFT to 256x256
