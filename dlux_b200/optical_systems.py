@@ -72,12 +72,24 @@ class BaseOpticalSystem:
             return self.fused_propagate(wl_t, off.reshape(1, 2), weights.reshape(1, -1))
         return self._propagate(wavelengths, offset, weights, return_wf)
 
+    def _batchable(self):
+        """True when every layer is one of this package's elementwise / MFT layers, which
+        broadcast over a leading wavelength axis (user layers and FFT keep the per-wavelength
+        loop)."""
+        return False
+
     def _propagate(self, wavelengths, offset, weights, return_wf):
-        fields = []
-        for wl, w in zip(wavelengths, weights):
-            wf = self.propagate_mono(wl, offset, return_wf=True)
-            fields.append(wf.phasor * (w ** 0.5))
-        fields = torch.stack(fields)
+        if self._batchable() and len(wavelengths) > 1:
+            # the reference vmaps propagate_mono over (wavelength, weight): one batched wavefront
+            wf = self.propagate_mono(wavelengths, offset, return_wf=True)
+            w = weights if torch.is_tensor(weights) else torch.as_tensor(weights, device=wf.phasor.device)
+            fields = wf.phasor * (w.to(torch.float32) ** 0.5)[:, None, None]
+        else:
+            fields = []
+            for wl, w in zip(wavelengths, weights):
+                wf = self.propagate_mono(wl, offset, return_wf=True)
+                fields.append(wf.phasor * (w ** 0.5))
+            fields = torch.stack(fields)
         if return_wf:
             return fields
         return (fields.real ** 2 + fields.imag ** 2).sum(0)
@@ -108,6 +120,11 @@ class LayeredOpticalSystem(BaseOpticalSystem):
         if key in layers:
             return layers[key]
         raise AttributeError(key)
+
+    def _batchable(self):
+        from .layers import MFT as _MFTLayer, Tilt as _Tilt
+        ok = (TransmissiveLayer, AberratedLayer, BasisLayer, Optic, BasisOptic, Normalise, _MFTLayer, _Tilt)
+        return all(type(l) in ok for l in self.layers.values())
 
     def initialise_wavefront(self, wavelength, offset=None):      # optical_systems.py:363-389
         wf = Wavefront(wavelength, self.wf_npixels, self.diameter, device=self.device)

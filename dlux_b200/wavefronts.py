@@ -50,10 +50,13 @@ class Wavefront:
                 "wavefront sampling.")
         device = torch.device("cuda" if device is None else device)
         f = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float32), device=device)
+        # a 1-d `wavelength` makes a batched wavefront, phasor [L, N, N]: what the reference gets
+        # from vmapping propagate_mono over the wavelengths (optical_systems.py:213-216)
         self.wavelength = f(wavelength)
         self.pixel_scale = f(np.float32(diameter) / np.float32(npixels)) if diameter is not None \
             else f(pixel_scale)
-        amp = torch.full((npixels, npixels), 1.0 / npixels ** 2, dtype=torch.float32, device=device)
+        amp = torch.full(tuple(self.wavelength.shape) + (npixels, npixels), 1.0 / npixels ** 2,
+                         dtype=torch.float32, device=device)
         self.phasor = torch.complex(amp, torch.zeros_like(amp))
         if center is not None:
             self.center = f(center)
@@ -101,8 +104,8 @@ class Wavefront:
         return np.float32(2 * math.pi) / self.wavelength
 
     @property
-    def power(self):                                   # wavefronts.py:330
-        return self.psf.sum()
+    def power(self):                                   # wavefronts.py:330 (per wavelength when batched)
+        return self.psf.sum((-2, -1))
 
     @property
     def xs(self):                                      # coordinates.py:129
@@ -126,7 +129,8 @@ class Wavefront:
         if opd is None:
             return self
         opd = torch.as_tensor(opd, dtype=torch.float32, device=self.phasor.device)
-        return self.add_phase(self.wavenumber * opd)
+        k = self.wavenumber
+        return self.add_phase((k[..., None, None] if k.dim() else k) * opd)
 
     def tilt(self, angles, unit: str = "rad"):         # wavefronts.py:370-395
         angles = torch.as_tensor(np.asarray(angles, dtype=np.float32) if not torch.is_tensor(angles)
@@ -142,10 +146,10 @@ class Wavefront:
         if mode == "power":
             scale = torch.sqrt(np.float32(value) / self.power)
         elif mode == "peak":
-            scale = torch.sqrt(np.float32(value) / self.psf.max())
+            scale = torch.sqrt(np.float32(value) / self.psf.amax((-2, -1)))
         else:
             raise ValueError("mode must be 'power' or 'peak'")
-        return self.multiply("phasor", scale)
+        return self.multiply("phasor", scale[..., None, None] if scale.dim() else scale)
 
     # ------------------------------------------------------------------ propagation
     def propagate(self, npixels: int, pixel_scale, focal_length=None, inverse: bool = False,
