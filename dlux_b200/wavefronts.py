@@ -75,8 +75,54 @@ class Wavefront:
     def multiply(self, name, value):
         return self.set(**{name: getattr(self, name) * value})
 
+    def add(self, name, value):
+        return self.set(**{name: getattr(self, name) + value})
+
+    @classmethod
+    def from_phasor(cls, phasor, wavelength, pixel_scale=None, diameter=None, center=None, device=None):
+        """wavefronts.py:124-167: a wavefront around an existing complex field."""
+        if not torch.is_tensor(phasor):
+            phasor = torch.as_tensor(np.asarray(phasor, dtype=np.complex64),
+                                     device=torch.device("cuda" if device is None else device))
+        wf = cls(wavelength, phasor.shape[-1], diameter, pixel_scale, center, device=phasor.device)
+        return wf.set(phasor=phasor.to(torch.complex64))
+
+    def _magic(self, other, op):                       # wavefronts.py:834-878
+        if other is None:
+            return self
+        if isinstance(other, Wavefront):
+            other = other.phasor
+        elif not (torch.is_tensor(other) or isinstance(other, (np.ndarray, np.generic, float, int, complex))):
+            raise TypeError(f"Unsupported type for {op}: {type(other)}. Must be an array, "
+                            "Wavefront, or None.")
+        if isinstance(other, np.ndarray):
+            other = torch.as_tensor(other, device=self.phasor.device)
+        if op == "add":
+            return self.add("phasor", other)
+        if op == "subtract":
+            return self.add("phasor", -other)
+        if op == "multiply":
+            return self.multiply("phasor", other)
+        return self.multiply("phasor", 1 / other)
+
+    def __add__(self, other):
+        return self._magic(other, "add")
+
+    def __sub__(self, other):
+        return self._magic(other, "subtract")
+
     def __mul__(self, other):
-        return self.multiply("phasor", other)
+        return self._magic(other, "multiply")
+
+    def __truediv__(self, other):
+        return self._magic(other, "divide")
+
+    __iadd__, __isub__, __imul__, __itruediv__ = __add__, __sub__, __mul__, __truediv__
+
+    def flip(self, axis):                              # wavefronts.py:426-440 (0 = y, 1 = x)
+        axes = (axis,) if isinstance(axis, int) else tuple(axis)
+        nd = self.phasor.dim()
+        return self.set(phasor=torch.flip(self.phasor, [a + nd - 2 if a >= 0 else a for a in axes]))
 
     # ------------------------------------------------------------------ properties
     @property
@@ -86,6 +132,26 @@ class Wavefront:
     @property
     def diameter(self):
         return self.npixels * self.pixel_scale
+
+    @property
+    def real(self):
+        return self.phasor.real
+
+    @property
+    def imaginary(self):
+        return self.phasor.imag
+
+    @property
+    def complex(self):                                 # wavefronts.py:244-254: [real, imaginary]
+        return torch.stack([self.phasor.real, self.phasor.imag])
+
+    @property
+    def polar(self):                                   # wavefronts.py:256-266: [amplitude, phase]
+        return torch.stack([self.amplitude, self.phase])
+
+    @property
+    def ndim(self):
+        return self.pixel_scale.dim()
 
     @property
     def amplitude(self):

@@ -355,6 +355,32 @@ def test_layered_system_with_mft_layers_batched_route(dev):
     assert rel_l2(first.detach().cpu().numpy(), want) < TOL
 
 
+def test_wavefront_container_api(dev):
+    # the rest of the Wavefront surface next to the path (wavefronts.py:124-167, 196-266, 426-440,
+    # 834-920): from_phasor, real/imaginary/complex/polar, flip, + - * / between wavefronts / arrays
+    import dlux_b200 as dl
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal((8, 8)) + 1j * rng.standard_normal((8, 8))).astype(np.complex64)
+    wf = dl.Wavefront.from_phasor(x, 1e-6, diameter=1.0, device=dev)
+    assert wf.npixels == 8 and abs(float(wf.pixel_scale) - 0.125) < 1e-7 and wf.ndim == 0
+    np.testing.assert_array_equal(wf.real.cpu().numpy(), x.real)
+    np.testing.assert_array_equal(wf.complex.cpu().numpy(), np.stack([x.real, x.imag]))
+    np.testing.assert_allclose(wf.polar.cpu().numpy(), np.stack([np.abs(x), np.angle(x)]), rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(wf.flip(0).phasor.cpu().numpy(), np.flip(x, 0))
+    np.testing.assert_array_equal(wf.flip((0, 1)).phasor.cpu().numpy(), np.flip(x, (0, 1)))
+    np.testing.assert_allclose((wf + wf).phasor.cpu().numpy(), 2 * x, rtol=1e-6)
+    np.testing.assert_allclose((wf - x).phasor.cpu().numpy(), 0 * x, atol=1e-7)
+    np.testing.assert_allclose((wf / 2.0).phasor.cpu().numpy(), x / 2, rtol=1e-6)
+    assert (wf * None) is wf and (wf + None) is wf
+    with pytest.raises(TypeError):
+        wf + "a"
+    with pytest.raises(ValueError):
+        dl.Wavefront.from_phasor(x, 1e-6, device=dev)
+    # a propagated from_phasor wavefront equals the functional MFT
+    out = wf.propagate(6, np.float32(2e-7)).phasor.cpu().numpy()
+    assert rel_l2(out, O.MFT(x, 1e-6, np.float32(0.125), 6, np.float32(2e-7))) < TOL
+
+
 def test_pixel_scale_gradient(dev):
     # d/d psf_pixel_scale (SURVEY 8f NEXT-1): two index-weighted adjoint MFTs inside
     # dlux_polypsf_bwd + the norm term, against central differences of the float64 oracle

@@ -118,3 +118,27 @@ def test_fusable_logic_and_validation():
     assert np.allclose(src.normalised_weights(), [0.25, 0.75])
     npix, ps, fl = s1._focal_args()
     assert npix == 4 and fl is None and ps == O.arcsec2rad(np.float32(0.1))
+
+
+def test_downsample_matches_reference_reduction_order():
+    # dlu.downsample (utils/array_ops.py:124-161): block mean / sum, columns first
+    import torch
+    from dlux_b200.utils import downsample
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((12, 12)).astype(np.float32)
+
+    def ref(array, n, mean):
+        method = np.mean if mean else np.sum
+        size_in, size_out = array.shape[0], array.shape[0] // n
+        array = method(array.reshape((size_in * size_out, n)), 1).reshape(size_in, size_out).T
+        return method(array.reshape((size_out * size_out, n)), 1).reshape(size_out, size_out).T
+
+    for n in (2, 3, 4):
+        for mean in (True, False):
+            got = downsample(torch.as_tensor(a), n, mean).numpy()
+            np.testing.assert_allclose(got, ref(a, n, mean), rtol=1e-6, atol=1e-7)
+    assert downsample(torch.as_tensor(np.stack([a, 2 * a])), 4, False).shape == (2, 3, 3)
+    with pytest.raises(ValueError):
+        downsample(torch.zeros(10, 10), 3)
+    with pytest.raises(ValueError):
+        downsample(torch.zeros(10, 8), 2)
