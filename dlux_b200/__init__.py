@@ -5,6 +5,8 @@ propagator layer, ``Wavefront.propagate`` and ``OpticalSystem.propagate/model``.
 Importing the package does not need a GPU; calling any operator does, and there is no
 CPU fallback (the native library is loaded lazily and its absence is an error)."""
 from . import utils
+from .apertures import (CircularAperture, CompoundAperture, CoordTransform, MultiAperture,
+                        RectangularAperture, RegPolyAperture, Spider, SquareAperture)
 from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, MFT, Normalise, Optic, OpticalLayer,
                      Tilt, TransmissiveLayer)
 from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, CartesianOpticalSystem,
@@ -16,4 +18,5 @@ __version__ = "0.1.0"
 __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer",
            "Tilt", "Normalise", "Optic", "BasisOptic", "MFT", "FFT", "CoordSpec", "BaseOpticalSystem",
            "LayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
-           "PointSources"]
+           "PointSources", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
+           "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture"]

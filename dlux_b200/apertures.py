@@ -1,0 +1,173 @@
+"""Dynamic (parametrised, soft-edged) aperture layers -- SURVEY 8f NEXT-3.  Mirrors the shape
+layers of /root/reference/src/dLux/layers/apertures.py (CircularAperture :240-311,
+SquareAperture :314-387, RectangularAperture :390-472, RegPolyAperture :475-555, Spider
+:558-640, CompoundAperture :1005-1069, MultiAperture :1072-1117) and ``CoordTransform``
+(coordinates.py:230-316).  They PRODUCE the transmission array the MFT path consumes: the
+arithmetic is differentiable torch (dlux_b200/utils/geometry.py), and in the fused route the
+transmission cotangent of ``dlux_polypsf_bwd`` flows back through it, so radii, widths,
+translations, rotations ... given as CUDA tensors with requires_grad are fitted parameters.
+Not mirrored: AberratedAperture (Zernike generation is a setup-time producer, SURVEY 8 OUT)."""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .layers import OpticalLayer
+from .utils import geometry as G
+
+__all__ = ["CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
+           "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture"]
+
+
+def _param(v, shape, name):
+    if v is None:
+        return None
+    if not torch.is_tensor(v):
+        v = np.asarray(v, dtype=np.float32)
+    if tuple(v.shape) != shape:
+        raise ValueError(f"{name} must have shape {shape}.")
+    return v
+
+
+class CoordTransform:
+    """coordinates.py:230-316: translation, shear, compression, rotation, applied in that order."""
+
+    def __init__(self, translation=None, rotation=None, compression=None, shear=None):
+        self.translation = _param(translation, (2,), "translation")
+        self.rotation = _param(rotation, (), "rotation")
+        self.compression = _param(compression, (2,), "compression")
+        self.shear = _param(shear, (2,), "shear")
+
+    def __call__(self, coords):
+        if self.translation is not None:
+            coords = G.translate_coords(coords, self.translation)
+        if self.shear is not None:
+            coords = G.shear_coords(coords, self.shear)
+        if self.compression is not None:
+            coords = G.compress_coords(coords, self.compression)
+        if self.rotation is not None:
+            coords = G.rotate_coords(coords, self.rotation)
+        return coords
+
+    apply = __call__
+
+
+class _DynamicAperture(OpticalLayer):
+    def __init__(self, transformation=None, occulting: bool = False, softening=1.0, normalise: bool = False):
+        if transformation is not None and not isinstance(transformation, CoordTransform):
+            raise TypeError("transformation must be a BaseCoordTransform instance, "
+                            f"got {type(transformation).__name__}.")
+        self.transformation = transformation
+        self.occulting = bool(occulting)
+        self.softness = softening if torch.is_tensor(softening) else np.float32(softening)
+        if float(self.softness) <= 0:
+            raise ValueError("softening must be greater than 0.")
+        self.normalise = bool(normalise)
+
+    def _shape(self, coords, clip):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def transmission(self, coords, pixel_scale):
+        """apertures.py:299-303 and siblings: edges softened over `softening` pixels."""
+        if self.transformation is not None:
+            coords = self.transformation(coords)
+        return self._shape(coords, pixel_scale * self.softness / 2)
+
+    def __call__(self, wavefront):                     # apertures.py:134-152
+        wavefront = wavefront * self.transmission(wavefront.coordinates(), wavefront.pixel_scale)
+        return wavefront.normalise() if self.normalise else wavefront
+
+
+class CircularAperture(_DynamicAperture):
+    def __init__(self, radius, transformation=None, occulting=False, softening=1.0, normalise=False):
+        super().__init__(transformation, occulting, softening, normalise)
+        self.radius = _param(radius, (), "radius")
+
+    def _shape(self, coords, clip):
+        return G.soft_circle(coords, self.radius, clip, self.occulting)
+
+
+class SquareAperture(_DynamicAperture):
+    def __init__(self, width, transformation=None, occulting=False, softening=1.0, normalise=False):
+        super().__init__(transformation, occulting, softening, normalise)
+        self.width = _param(width, (), "width")
+
+    def _shape(self, coords, clip):
+        return G.soft_square(coords, self.width, clip, self.occulting)
+
+
+class RectangularAperture(_DynamicAperture):
+    def __init__(self, height, width, transformation=None, occulting=False, softening=1.0, normalise=False):
+        super().__init__(transformation, occulting, softening, normalise)
+        self.height = _param(height, (), "height")
+        self.width = _param(width, (), "width")
+
+    def _shape(self, coords, clip):
+        return G.soft_rectangle(coords, self.width, self.height, clip, self.occulting)
+
+
+class RegPolyAperture(_DynamicAperture):
+    def __init__(self, nsides: int, rmax, transformation=None, occulting=False, softening=1.0,
+                 normalise=False):
+        super().__init__(transformation, occulting, softening, normalise)
+        self.nsides = int(nsides)
+        self.rmax = _param(rmax, (), "rmax")
+
+    def _shape(self, coords, clip):
+        return G.soft_reg_polygon(coords, self.rmax, self.nsides, clip, self.occulting)
+
+
+class Spider(_DynamicAperture):
+    def __init__(self, width, angles, transformation=None, occulting=False, softening=1.0, normalise=False):
+        super().__init__(transformation, occulting, softening, normalise)
+        self.width = _param(width, (), "width")
+        self.angles = angles if torch.is_tensor(angles) else np.atleast_1d(np.asarray(angles, np.float32))
+
+    def _shape(self, coords, clip):
+        return G.soft_spider(coords, self.width, self.angles, clip, self.occulting)
+
+
+class _Composite(_DynamicAperture):
+    def __init__(self, apertures, transformation=None, normalise=False):
+        super().__init__(transformation, False, 1.0, normalise)
+        if isinstance(apertures, (list, tuple)):
+            od = OrderedDict()
+            for i, a in enumerate(apertures):
+                key, ap = a if isinstance(a, tuple) else (f"{type(a).__name__}_{i}", a)
+                od[key] = ap
+            apertures = od
+        for ap in apertures.values():
+            if not isinstance(ap, _DynamicAperture):
+                raise TypeError("apertures must be dynamic aperture layers")
+        self.apertures = OrderedDict(apertures)
+
+    def __getattr__(self, key):
+        aps = self.__dict__.get("apertures", {})
+        if key in aps:
+            return aps[key]
+        raise AttributeError(key)
+
+    def transmissions(self, coords, pixel_scale):      # apertures.py:950-969
+        return torch.stack([ap.transmission(coords, pixel_scale) for ap in self.apertures.values()])
+
+    def transmission(self, coords, pixel_scale):
+        if self.transformation is not None:
+            coords = self.transformation(coords)
+        return self._join(self.transmissions(coords, pixel_scale))
+
+
+class CompoundAperture(_Composite):
+    """Overlapping shapes multiplied together (apertures.py:1005-1069), e.g. primary x secondary
+    obstruction x spiders."""
+
+    def _join(self, ts):
+        return ts.prod(0)
+
+
+class MultiAperture(_Composite):
+    """Separate sub-apertures summed (apertures.py:1072-1117), e.g. the holes of an NRM."""
+
+    def _join(self, ts):
+        return ts.sum(0)

@@ -433,7 +433,11 @@ __device__ __forceinline__ PartialSchedule partial_schedule(int kc, int k_chunks
 #ifndef DLUX_LONG_FIRST_MIN
 #define DLUX_LONG_FIRST_MIN (12 * FLUSH_CHUNKS)
 #endif
-  const int A0 = (k_chunks >= DLUX_LONG_FIRST_MIN ? 3 : 2) * FLUSH_CHUNKS, B0 = A0 - FLUSH_CHUNKS / 2;
+#ifndef DLUX_LONG_FIRST_FACTOR
+#define DLUX_LONG_FIRST_FACTOR 3
+#endif
+  const int A0 = (k_chunks >= DLUX_LONG_FIRST_MIN ? DLUX_LONG_FIRST_FACTOR : 2) * FLUSH_CHUNKS,
+            B0 = A0 - FLUSH_CHUNKS / 2;
   PartialSchedule ps;
   const bool last = kc == k_chunks - 1;
   const int ra = (kc - A0) % FLUSH_CHUNKS, rb = (kc - B0) % FLUSH_CHUNKS;  // used only for kc >= A0 / B0

@@ -123,8 +123,9 @@ class LayeredOpticalSystem(BaseOpticalSystem):
 
     def _batchable(self):
         from .layers import MFT as _MFTLayer, Tilt as _Tilt
+        from .apertures import _DynamicAperture
         ok = (TransmissiveLayer, AberratedLayer, BasisLayer, Optic, BasisOptic, Normalise, _MFTLayer, _Tilt)
-        return all(type(l) in ok for l in self.layers.values())
+        return all(type(l) in ok or isinstance(l, _DynamicAperture) for l in self.layers.values())
 
     def initialise_wavefront(self, wavelength, offset=None):      # optical_systems.py:363-389
         wf = Wavefront(wavelength, self.wf_npixels, self.diameter, device=self.device)
@@ -175,7 +176,23 @@ class _FocalSystem(LayeredOpticalSystem):
         def add(a, b):
             return b if a is None else (a if b is None else a + b)
 
+        from .apertures import _DynamicAperture
         for layer in self.layers.values():
+            if isinstance(layer, _DynamicAperture):
+                # a dynamic aperture evaluates its transmission on the pupil grid (torch, autograd)
+                coords = self.__dict__.get("_pupil_coords")
+                if coords is None:
+                    from .utils.geometry import pixel_coords
+                    coords = self.__dict__["_pupil_coords"] = pixel_coords(
+                        self.wf_npixels, float(self.diameter), device=self.device)
+                ps = torch.as_tensor(np.float32(self.diameter / np.float32(self.wf_npixels)), device=self.device)
+                t = layer.transmission(coords, ps)
+                if normalise:
+                    t_after_norm = True
+                T = mul(T, t)
+                if layer.normalise:
+                    normalise = True
+                continue
             if type(layer) not in (TransmissiveLayer, AberratedLayer, BasisLayer, Optic, BasisOptic,
                                    Normalise):
                 return None

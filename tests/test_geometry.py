@@ -1,0 +1,79 @@
+"""dlux_b200.utils.geometry (torch) against what the reference's own utils/geometry.py and
+utils/coordinates.py return (tests/golden/reference_geometry.npz, made by executing those files:
+tests/golden/make_golden_geometry.py).  CPU tests: the functions are device-agnostic torch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dlux_b200.utils import geometry as G
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "reference_geometry.npz"))
+
+
+def _close(a, b, atol=2e-6):
+    np.testing.assert_allclose(a.numpy() if torch.is_tensor(a) else a, b, rtol=0, atol=atol)
+
+
+def test_coordinate_transforms(gold):
+    c = G.pixel_coords(48, 2.0)
+    _close(c, gold["coords"], 1e-7)
+    tr = G.translate_coords(c, [0.11, -0.07])
+    sh = G.shear_coords(tr, [0.05, -0.02])
+    cm = G.compress_coords(sh, [1.1, 0.9])
+    ro = G.rotate_coords(cm, 0.3)
+    for got, key in ((tr, "translated"), (sh, "sheared"), (cm, "compressed"), (ro, "rotated")):
+        _close(got, gold[key], 1e-6)
+    _close(G.cart2polar(c), gold["polar"], 1e-6)
+
+
+@pytest.mark.parametrize("inv", [False, True])
+@pytest.mark.parametrize("cname", ["plain", "xf"])
+def test_shapes_match_reference(gold, inv, cname):
+    c = torch.as_tensor(gold["coords"] if cname == "plain" else gold["rotated"])
+    clip = np.float32(2.0 / 48 * 1.5 / 2)
+    fns = {
+        "soft_circle": lambda: G.soft_circle(c, 0.7, clip, inv),
+        "soft_square": lambda: G.soft_square(c, 1.1, clip, inv),
+        "soft_rectangle": lambda: G.soft_rectangle(c, 1.3, 0.6, clip, inv),
+        "soft_hexagon": lambda: G.soft_reg_polygon(c, 0.8, 6, clip, inv),
+        "soft_pentagon": lambda: G.soft_reg_polygon(c, 0.75, 5, clip, inv),
+        "soft_spider": lambda: G.soft_spider(c, 0.08, [0.0, 120.0, 240.0], clip, inv),
+        "circle": lambda: G.circle(c, 0.7, inv),
+        "square": lambda: G.square(c, 1.1, inv),
+        "rectangle": lambda: G.rectangle(c, 1.3, 0.6, inv),
+        "hexagon": lambda: G.reg_polygon(c, 0.8, 6, inv),
+    }
+    for name, fn in fns.items():
+        want = gold[f"{name}_{int(inv)}_{cname}"]
+        got = fn().numpy()
+        if name.startswith("soft"):
+            # soft edges: float32 rounding of the distance moves a value by ~1e-5 of the ramp
+            np.testing.assert_allclose(got, want, rtol=0, atol=2e-4, err_msg=name)
+        else:
+            # hard edges: identical except for pixels whose centre sits on the edge to rounding
+            assert (got != want).mean() < 2e-3, name
+
+
+def test_soften_constant_support(gold):
+    _close(G.soften(torch.full((4, 4), 2.0), 0.5), gold["soften_constant"])
+
+
+def test_shape_parameters_are_differentiable():
+    c = G.pixel_coords(32, 2.0, dtype=torch.float64)
+    r = torch.tensor(0.7, dtype=torch.float64, requires_grad=True)
+    t = torch.tensor([0.05, -0.02], dtype=torch.float64, requires_grad=True)
+    T = G.soft_circle(G.translate_coords(c, t), r, 0.05)
+    T.sum().backward()
+    # area grows with the radius: d(sum T)/dr ~ circumference / pixel area
+    assert float(r.grad) > 0 and torch.isfinite(t.grad).all()
+    eps = 1e-6
+    f = lambda rr: float(G.soft_circle(G.translate_coords(c, t.detach()), rr, 0.05).sum())
+    fd = (f(0.7 + eps) - f(0.7 - eps)) / (2 * eps)
+    assert abs(float(r.grad) - fd) < 1e-4 * abs(fd)
