@@ -136,20 +136,23 @@ def mft_c64(phasor: torch.Tensor, scale_out, n_out_or_in: int, shift_xy=None, de
 
 class MFTFunction(torch.autograd.Function):
     """Linear in the phasor; the VJP is the adjoint kernel (what ``jax.custom_vjp`` /
-    the primitive's transpose rule would call)."""
+    the primitive's transpose rule would call).  The backward is itself an ``MFTFunction``
+    (adjoint flag flipped), so the operator is closed under differentiation: Hessians /
+    Hessian-vector products of a loss through the layer-by-layer route work by double backward
+    (SURVEY 8f NEXT-1, second order)."""
 
     @staticmethod
-    def forward(ctx, phasor, scale_out, n_out, shift_xy, delta_xy, norm, inverse, precision):
-        ctx.n_in = phasor.shape[-1]
-        ctx.args = (scale_out, shift_xy, delta_xy, norm, inverse, precision)
-        return mft_c64(phasor, scale_out, n_out, shift_xy, delta_xy, norm, inverse, False, precision)
+    def forward(ctx, phasor, scale_out, n_other, shift_xy, delta_xy, norm, inverse, precision, adjoint=False):
+        ctx.n_self = phasor.shape[-1]
+        ctx.args = (scale_out, shift_xy, delta_xy, norm, inverse, precision, bool(adjoint))
+        return mft_c64(phasor, scale_out, n_other, shift_xy, delta_xy, norm, inverse, bool(adjoint), precision)
 
     @staticmethod
     def backward(ctx, grad_out):
-        scale_out, shift_xy, delta_xy, norm, inverse, precision = ctx.args
-        g = mft_c64(grad_out.contiguous(), scale_out, ctx.n_in, shift_xy, delta_xy, norm, inverse, True,
-                    precision)
-        return g, None, None, None, None, None, None, None
+        scale_out, shift_xy, delta_xy, norm, inverse, precision, adjoint = ctx.args
+        g = MFTFunction.apply(grad_out.contiguous(), scale_out, ctx.n_self, shift_xy, delta_xy, norm,
+                              inverse, precision, not adjoint)
+        return g, None, None, None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------- poly-PSF
@@ -230,6 +233,7 @@ class PolyPSFFunction(torch.autograd.Function):
         return psf
 
     @staticmethod
+    @torch.autograd.function.once_differentiable   # second order: use the layer-by-layer route (fused=False)
     def backward(ctx, psf_bar):
         it = iter(ctx.saved_tensors)
         opd, phase, weights, transmission, wavenumber, scale_out, norm, delta_xy, field = [
@@ -300,5 +304,19 @@ class BasisEvalFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, out_bar):
         (basis,) = ctx.saved_tensors
-        cb = basis_reduce(basis, out_bar, ctx.cshape) if ctx.needs_input_grad[0] else None
+        cb = BasisReduceFunction.apply(out_bar, basis, ctx.cshape) if ctx.needs_input_grad[0] else None
         return cb, None, (out_bar if ctx.has_base and ctx.needs_input_grad[2] else None)
+
+
+class BasisReduceFunction(torch.autograd.Function):
+    """The transpose of eval_basis, with eval_basis as ITS transpose (second-order support)."""
+
+    @staticmethod
+    def forward(ctx, out_bar, basis, cshape):
+        ctx.save_for_backward(basis)
+        return basis_reduce(basis, out_bar, cshape)
+
+    @staticmethod
+    def backward(ctx, cb_bar):
+        (basis,) = ctx.saved_tensors
+        return BasisEvalFunction.apply(cb_bar.contiguous(), basis, None), None, None

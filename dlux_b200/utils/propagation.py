@@ -118,7 +118,7 @@ def MFT(phasor, wavelength, pixel_scale_in, npixels_out, pixel_scale_out, focal_
     scale_out = _to_dev(scale_out, dev)
     norm = _to_dev(norm, dev)
     return ops.MFTFunction.apply(phasor, scale_out, npixels_out, shift, None, norm, bool(inverse),
-                                 precision)
+                                 precision, False)
 
 
 def FFT(phasor, wavelength, pixel_scale, focal_length=None, pad: int = 2, inverse: bool = False,
@@ -151,7 +151,7 @@ def FFT(phasor, wavelength, pixel_scale, focal_length=None, pad: int = 2, invers
     f = lambda v, w: torch.full((batch, w), float(v), dtype=torch.float32, device=dev)
     out = ops.MFTFunction.apply(phasor, f(s, 1).reshape(batch), n_out, f(sh_in, 2),
                                 f((sh_out - sh_in) * s, 2), f(np.float32(1.0) / np.float32(n_out), 1),
-                                bool(inverse), precision)
+                                bool(inverse), precision, False)
     return out, new_pixel_scale
 
 

@@ -425,6 +425,41 @@ def test_dynamic_apertures_fused_and_differentiable(dev):
         assert abs(float(rot.grad) - float(q64.grad)) <= 2e-3 * abs(float(q64.grad)) + 1e-9, (fused, rot.grad, q64.grad)
 
 
+def test_second_order_through_layer_route(dev):
+    # NEXT-1, second order: MFTFunction / BasisEvalFunction are closed under differentiation
+    # (each backward is the other linear operator as an autograd Function), so the Hessian of a
+    # loss w.r.t. the basis coefficients comes out of double backward on the layer-by-layer
+    # route (what zdx.hessian / a Fisher matrix needs).  Against the float64 Hessian of the twin.
+    import dlux_b200 as dl
+    from oracle import torch_twin
+    N, M, nz = 48, 24, 3
+    od = _optics_dict(N, M, nz, 21)
+    od["basis"] = od["basis"] * np.float32(4.0)       # stronger curvature
+    wls = np.array([0.95e-6, 1.05e-6], np.float32)
+    w = np.array([0.5, 0.5], np.float32)
+    rng = np.random.default_rng(22)
+    target = rng.uniform(0.5, 1.5, (M, M))
+    basis_d = torch.as_tensor(od["basis"], device=dev)
+
+    def loss_gpu(c):
+        layer = dl.BasisOptic(basis_d, od["transmission"], c, "opd", normalise=True, device=dev)
+        sys_ = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, 0.05, device=dev, fused=False)
+        psf = sys_.propagate(wls, None, w)
+        return ((psf * 1e3 - torch.as_tensor(target.astype(np.float32), device=dev)) ** 2).sum()
+
+    def loss_ref(c):
+        psf = torch_twin.poly_psf(od["transmission"], None, wls, w, diameter=1.0, psf_npixels=M,
+                                  pixel_scale_rad=O.arcsec2rad(0.05), basis=od["basis"], coefficients=c,
+                                  dtype=np.float64)
+        return ((psf * 1e3 - torch.tensor(target)) ** 2).sum()
+
+    c0 = od["coefficients"]
+    H = torch.autograd.functional.hessian(loss_gpu, torch.as_tensor(c0, device=dev)).cpu().numpy().astype(np.float64)
+    Href = torch.autograd.functional.hessian(loss_ref, torch.tensor(c0, dtype=torch.float64)).numpy()
+    assert np.allclose(H, H.T, rtol=1e-3, atol=1e-4 * np.abs(Href).max())
+    assert rel_l2(H, Href) < 1e-3, (H, Href)
+
+
 def test_pixel_scale_gradient(dev):
     # d/d psf_pixel_scale (SURVEY 8f NEXT-1): two index-weighted adjoint MFTs inside
     # dlux_polypsf_bwd + the norm term, against central differences of the float64 oracle
