@@ -11,12 +11,12 @@ from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, MFT, Normalise
                      Tilt, TransmissiveLayer)
 from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, CartesianOpticalSystem,
                               LayeredOpticalSystem)
-from .sources import PointSource, PointSources
+from .sources import BinarySource, PointSource, PointSources
 from .wavefronts import CoordSpec, Wavefront
 
 __version__ = "0.1.0"
 __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer",
            "Tilt", "Normalise", "Optic", "BasisOptic", "MFT", "FFT", "CoordSpec", "BaseOpticalSystem",
            "LayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
-           "PointSources", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
+           "PointSources", "BinarySource", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture"]

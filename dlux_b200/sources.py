@@ -1,11 +1,12 @@
-"""Mirror of ``PointSource`` / ``PointSources`` (/root/reference/src/dLux/sources.py:
-316-327, 392-411) and the spectrum normalisation they rely on (spectra.py:84-117)."""
+"""Mirror of ``PointSource`` / ``PointSources`` / ``BinarySource`` (/root/reference/src/dLux/
+sources.py:316-327, 392-411, 524-635) and the spectrum normalisation they rely on
+(spectra.py:84-117)."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-__all__ = ["PointSource", "PointSources"]
+__all__ = ["PointSource", "PointSources", "BinarySource"]
 
 
 def _np32(x):
@@ -20,11 +21,18 @@ class _Source:
         if weights is None:
             weights = np.ones(self.wavelengths.shape, np.float32) / np.float32(self.wavelengths.shape[-1])
         weights = _np32(weights)
-        self.weights = (weights / weights.sum()).astype(np.float32)      # spectra.py:88-92
-        if self.weights.shape != self.wavelengths.shape:
-            raise ValueError("wavelengths and weights must have the same shape.")
+        if weights.ndim == 2:                                            # spectra.py:88-92: per-source rows
+            self.weights = (weights / weights.sum(-1)[:, None]).astype(np.float32)
+            if self.weights.shape[-1:] != self.wavelengths.shape:
+                raise ValueError("wavelengths and weights must have the same trailing shape.")
+        else:
+            self.weights = (weights / weights.sum()).astype(np.float32)
+            if self.weights.shape != self.wavelengths.shape:
+                raise ValueError("wavelengths and weights must have the same shape.")
 
     def normalised_weights(self):                                         # spectra.py:113-117
+        if self.weights.ndim == 2:
+            return (self.weights / self.weights.sum(-1)[:, None]).astype(np.float32)
         return (self.weights / self.weights.sum()).astype(np.float32)
 
 
@@ -79,5 +87,51 @@ class PointSources(_Source):
         out = None
         for s in range(len(self.position)):
             psf = optics.propagate(self.wavelengths, self.position[s], weights[s])
+            out = psf if out is None else out + psf
+        return out
+
+
+class BinarySource(_Source):
+    """sources.py:524-635: two point sources parametrised by mean position, separation,
+    position angle, mean flux and contrast (utils/source.py:10-52); ``weights`` may be [2, L]
+    (one spectrum per component).  Any parameter given as a CUDA tensor with requires_grad is
+    differentiable: it reaches the fused kernels as source offsets / spectral weights."""
+
+    def __init__(self, wavelengths=None, position=None, mean_flux=1.0, separation=0.0,
+                 position_angle=np.pi / 2, contrast=1.0, weights=None):
+        wl = np.atleast_1d(_np32(wavelengths))
+        if weights is None:
+            weights = np.ones((2, len(wl)), np.float32)
+        position = np.zeros(2, np.float32) if position is None else position
+        keep = lambda v: v if torch.is_tensor(v) else _np32(v)
+        self.position = keep(position)
+        if tuple(self.position.shape) != (2,):
+            raise ValueError("position must be a 1d array of shape (2,).")
+        self.mean_flux, self.separation = keep(mean_flux), keep(separation)
+        self.position_angle, self.contrast = keep(position_angle), keep(contrast)
+        super().__init__(wl, weights)
+
+    def _device(self, optics):
+        return getattr(optics, "device", torch.device("cuda"))
+
+    def model(self, optics, return_wf=False, return_psf=False):
+        _validate_return_mode(return_wf, return_psf)
+        dev = self._device(optics)
+        t = lambda v: v.to(dev, torch.float32) if torch.is_tensor(v) else torch.as_tensor(v, device=dev)
+        pos, sep, pa = t(self.position), t(self.separation), t(self.position_angle)
+        mean_flux, contrast = t(self.mean_flux), t(self.contrast)
+        sep_vec = torch.stack([sep / 2 * torch.sin(pa), sep / 2 * torch.cos(pa)])     # utils/source.py:50-52
+        positions = torch.stack([pos + sep_vec, pos - sep_vec])
+        flux = 2 * torch.stack([contrast * mean_flux, mean_flux]) / (1 + contrast)    # utils/source.py:26
+        w = t(self.normalised_weights())
+        if w.dim() == 1:
+            w = w[None, :].expand(2, -1)
+        weights = w * flux[:, None]
+        if getattr(optics, "fused", False) and not return_wf and hasattr(optics, "fused_propagate") \
+                and optics._fusable() is not None:
+            return optics.fused_propagate(self.wavelengths, positions, weights)
+        out = None
+        for s in range(2):
+            psf = optics.propagate(self.wavelengths, positions[s], weights[s], return_wf, return_psf)
             out = psf if out is None else out + psf
         return out

@@ -460,6 +460,43 @@ def test_second_order_through_layer_route(dev):
     assert rel_l2(H, Href) < 1e-3, (H, Href)
 
 
+def test_binary_source(dev):
+    # BinarySource (sources.py:524-635) = two point sources from (position, separation, position
+    # angle, mean flux, contrast); forward vs the oracle's PointSources, gradient w.r.t. the
+    # separation and contrast vs float64 autograd of the twin
+    import dlux_b200 as dl
+    from oracle import torch_twin
+    N, M = 64, 32
+    od = _optics_dict(N, M, 3, 31)
+    wls = np.linspace(0.9e-6, 1.1e-6, 3).astype(np.float32)
+    w2 = np.array([[1.0, 2.0, 1.0], [3.0, 1.0, 1.0]], np.float32)
+    pos0, sep0, pa0, mf0, con0 = np.array([1e-7, -1e-7], np.float32), 6e-7, 0.7, 2.0, 3.0
+    G = np.random.default_rng(32).standard_normal((M, M))
+    sep = torch.tensor(sep0, device=dev, requires_grad=True)
+    con = torch.tensor(con0, device=dev, requires_grad=True)
+    src = dl.BinarySource(wls, pos0, mf0, sep, pa0, con, weights=w2)
+    sys_ = _system(od, dev)
+    psf = src.model(sys_)
+    (psf * torch.as_tensor(G.astype(np.float32), device=dev)).sum().backward()
+    # oracle: the same two stars as PointSources with per-star spectra
+    wn = w2 / w2.sum(-1)[:, None]
+    s64 = torch.tensor(sep0, dtype=torch.float64, requires_grad=True)
+    c64 = torch.tensor(con0, dtype=torch.float64, requires_grad=True)
+    vec = torch.stack([s64 / 2 * np.sin(pa0), s64 / 2 * np.cos(pa0)])
+    positions = torch.stack([torch.tensor(pos0, dtype=torch.float64) + vec, torch.tensor(pos0, dtype=torch.float64) - vec])
+    flux = 2 * torch.stack([c64 * mf0, torch.tensor(mf0, dtype=torch.float64)]) / (1 + c64)
+    ref = 0
+    for s in range(2):
+        ref = ref + torch_twin.poly_psf(od["transmission"], None, wls, torch.tensor(wn[s], dtype=torch.float64) * flux[s],
+                                        diameter=1.0, psf_npixels=M, pixel_scale_rad=O.arcsec2rad(0.05),
+                                        offset=positions[s], basis=od["basis"], coefficients=od["coefficients"],
+                                        dtype=np.float64)
+    (ref * torch.tensor(G)).sum().backward()
+    assert rel_l2(psf.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    assert abs(float(sep.grad) - float(s64.grad)) <= 1e-3 * abs(float(s64.grad))
+    assert abs(float(con.grad) - float(c64.grad)) <= 1e-3 * abs(float(c64.grad))
+
+
 def test_pixel_scale_gradient(dev):
     # d/d psf_pixel_scale (SURVEY 8f NEXT-1): two index-weighted adjoint MFTs inside
     # dlux_polypsf_bwd + the norm term, against central differences of the float64 oracle
