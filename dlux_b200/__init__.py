@@ -11,12 +11,13 @@ from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, MFT, Normalise
                      Tilt, TransmissiveLayer)
 from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, CartesianOpticalSystem,
                               LayeredOpticalSystem)
-from .sources import BinarySource, PointSource, PointSources
+from .sources import (BinarySource, PointResolvedSource, PointSource, PointSources, ResolvedSource,
+                      Scene)
 from .wavefronts import CoordSpec, Wavefront
 
 __version__ = "0.1.0"
 __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer",
            "Tilt", "Normalise", "Optic", "BasisOptic", "MFT", "FFT", "CoordSpec", "BaseOpticalSystem",
            "LayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
-           "PointSources", "BinarySource", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
+           "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture"]

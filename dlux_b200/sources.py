@@ -1,12 +1,14 @@
 """Mirror of ``PointSource`` / ``PointSources`` / ``BinarySource`` (/root/reference/src/dLux/
-sources.py:316-327, 392-411, 524-635) and the spectrum normalisation they rely on
-(spectra.py:84-117)."""
+sources.py:316-327, 392-411, 524-635), the image-plane sources built on them (``ResolvedSource``
+:414-521, ``PointResolvedSource`` :638-748, ``Scene`` :751-850) and the spectrum normalisation they
+rely on (spectra.py:84-117)."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-__all__ = ["PointSource", "PointSources", "BinarySource"]
+__all__ = ["PointSource", "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource",
+           "Scene", "convolve_same"]
 
 
 def _np32(x):
@@ -133,5 +135,106 @@ class BinarySource(_Source):
         out = None
         for s in range(2):
             psf = optics.propagate(self.wavelengths, positions[s], weights[s], return_wf, return_psf)
+            out = psf if out is None else out + psf
+        return out
+
+
+def convolve_same(image: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
+    """``jax.scipy.signal.convolve(image, kernel, mode="same")`` for 2-d arrays: the full linear
+    convolution cropped to the shape of ``image`` around its centre."""
+    kh, kw = kernel.shape
+    full = torch.nn.functional.conv2d(image[None, None], torch.flip(kernel, (0, 1))[None, None].to(image.dtype),
+                                      padding=(kh - 1, kw - 1))[0, 0]
+    y0, x0 = (kh - 1) // 2, (kw - 1) // 2
+    return full[y0:y0 + image.shape[0], x0:x0 + image.shape[1]]
+
+
+def _wavefront_not_supported():
+    raise NotImplementedError(
+        "Wavefront information cannot be preserved through convolution. "
+        "Convolution can only operate on PSFs (incoherent light). "
+        "Please use return_wf=False to get the PSF array or return_psf=True "
+        "to get a PSF object.")
+
+
+class ResolvedSource(PointSource):
+    """sources.py:414-521: a point-source PSF convolved with a (normalised, floored) intensity
+    distribution -- the convolution is image-plane work after the fused PSF."""
+
+    def __init__(self, wavelengths=None, position=None, flux=1.0, distribution=None, weights=None):
+        d = np.ones((3, 3), np.float32) if distribution is None else distribution
+        d = d if torch.is_tensor(d) else _np32(d)
+        if d.ndim != 2:
+            raise ValueError("distribution must be a 2d array.")
+        self.distribution = d / d.sum()
+        super().__init__(wavelengths, position, flux, weights)
+
+    def _distribution(self, device):
+        d = self.distribution if torch.is_tensor(self.distribution) else torch.as_tensor(self.distribution, device=device)
+        d = torch.clamp(d.to(device, torch.float32), min=0.0)                       # sources.py:470-474
+        return d / d.sum()
+
+    def model(self, optics, return_wf=False, return_psf=False):
+        _validate_return_mode(return_wf, return_psf)
+        if return_wf:
+            _wavefront_not_supported()
+        psf = PointSource.model(self, optics)
+        return convolve_same(psf, self._distribution(psf.device))
+
+
+class PointResolvedSource(ResolvedSource):
+    """sources.py:638-748: an unresolved star plus a resolved component sharing its spectrum
+    shape, fluxes set by the mean flux and the contrast; ``weights`` may be [2, L]."""
+
+    def __init__(self, wavelengths=None, position=None, flux=1.0, distribution=None, contrast=1.0,
+                 weights=None):
+        wl = np.atleast_1d(_np32(wavelengths))
+        if weights is None:
+            weights = np.ones((2, len(wl)), np.float32)
+        self.contrast = contrast if torch.is_tensor(contrast) else np.float32(contrast)
+        super().__init__(wl, position, flux, distribution, weights)
+
+    def model(self, optics, return_wf=False, return_psf=False):
+        _validate_return_mode(return_wf, return_psf)
+        if return_wf:
+            _wavefront_not_supported()
+        dev = getattr(optics, "device", torch.device("cuda"))
+        t = lambda v: v.to(dev, torch.float32) if torch.is_tensor(v) else torch.as_tensor(v, device=dev)
+        flux, contrast = t(self.flux), t(self.contrast)
+        fluxes = 2 * torch.stack([contrast * flux, flux]) / (1 + contrast)          # utils/source.py:26
+        w = t(self.normalised_weights())
+        if w.dim() == 1:
+            w = w[None, :].expand(2, -1)
+        weights = w * fluxes[:, None]
+        point = optics.propagate(self.wavelengths, self.position, weights[0])
+        resolved = optics.propagate(self.wavelengths, self.position, weights[1])
+        return point + convolve_same(resolved, self._distribution(point.device))
+
+
+class Scene:
+    """sources.py:751-850: several sources modelled through the same optics and summed."""
+
+    def __init__(self, sources):
+        if isinstance(sources, dict):
+            self.sources = dict(sources)
+        else:
+            self.sources = {}
+            for i, s in enumerate(sources):
+                key, src = s if isinstance(s, tuple) else (f"{type(s).__name__}_{i}", s)
+                self.sources[key] = src
+
+    def __getattr__(self, key):
+        srcs = self.__dict__.get("sources", {})
+        if key in srcs:
+            return srcs[key]
+        raise AttributeError(key)
+
+    def model(self, optics, return_wf=False, return_psf=False):
+        _validate_return_mode(return_wf, return_psf)
+        if return_wf:
+            raise NotImplementedError("Scene.model returns the summed PSF array")
+        out = None
+        for src in self.sources.values():
+            psf = src.model(optics)
             out = psf if out is None else out + psf
         return out

@@ -497,6 +497,34 @@ def test_binary_source(dev):
     assert abs(float(con.grad) - float(c64.grad)) <= 1e-3 * abs(float(c64.grad))
 
 
+def test_resolved_sources_and_scene(dev):
+    # image-plane sources (sources.py:414-521, 638-748, 751-850): PSF (*) distribution after the
+    # fused PSF; against the oracle PSF convolved with scipy
+    import dlux_b200 as dl
+    from scipy.signal import convolve
+    N, M = 64, 32
+    od = _optics_dict(N, M, 3, 41)
+    wls = np.linspace(0.9e-6, 1.1e-6, 3).astype(np.float32)
+    pos = np.array([1e-7, -2e-7], np.float32)
+    dist = np.random.default_rng(42).uniform(0, 1, (5, 5)).astype(np.float32)
+    dist[0, 0] = -1.0                                   # floored by normalise (sources.py:470-474)
+    sys_ = _system(od, dev)
+    base = O.point_source_model(od, wls, pos, 2.0).astype(np.float64)
+    dn = dist / dist.sum()
+    dn = np.maximum(dn, 0)
+    dn = dn / dn.sum()
+    res = dl.ResolvedSource(wls, pos, 2.0, dist).model(sys_).cpu().numpy()
+    assert rel_l2(res, convolve(base, dn, mode="same")) < TOL
+    pr = dl.PointResolvedSource(wls, pos, 2.0, dist, contrast=3.0).model(sys_).cpu().numpy()
+    f = 2 * np.array([3.0 * 2.0, 2.0]) / 4.0
+    want = base / 2.0 * f[0] + convolve(base / 2.0 * f[1], dn, mode="same")
+    assert rel_l2(pr, want) < TOL
+    scene = dl.Scene([("star", dl.PointSource(wls, pos, 2.0)), ("disk", dl.ResolvedSource(wls, pos, 2.0, dist))])
+    assert rel_l2(scene.model(sys_).cpu().numpy(), base + convolve(base, dn, mode="same")) < TOL
+    with pytest.raises(NotImplementedError):
+        dl.ResolvedSource(wls, pos, 2.0, dist).model(sys_, return_wf=True)
+
+
 def test_pixel_scale_gradient(dev):
     # d/d psf_pixel_scale (SURVEY 8f NEXT-1): two index-weighted adjoint MFTs inside
     # dlux_polypsf_bwd + the norm term, against central differences of the float64 oracle

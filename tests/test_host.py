@@ -142,3 +142,16 @@ def test_downsample_matches_reference_reduction_order():
         downsample(torch.zeros(10, 10), 3)
     with pytest.raises(ValueError):
         downsample(torch.zeros(10, 8), 2)
+
+
+def test_convolve_same_matches_scipy():
+    # jax.scipy.signal.convolve(mode="same") semantics used by ResolvedSource (sources.py:516)
+    import torch
+    from scipy.signal import convolve
+    from dlux_b200.sources import convolve_same
+    rng = np.random.default_rng(8)
+    img = rng.standard_normal((17, 17))
+    for shape in ((3, 3), (4, 4), (5, 2), (1, 1)):
+        k = rng.uniform(0, 1, shape)
+        got = convolve_same(torch.as_tensor(img), torch.as_tensor(k)).numpy()
+        np.testing.assert_allclose(got, convolve(img, k, mode="same"), rtol=1e-10, atol=1e-12)
