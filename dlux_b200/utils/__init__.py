@@ -1,8 +1,8 @@
 """Mirror of the slice of ``dLux.utils`` that sits on the diffraction hot path."""
-from . import geometry, propagation
+from . import geometry, propagation, zernikes
 from .array_ops import downsample
 from .propagation import (MFT, FFT, calc_nfringes, mft_geometry, arcsec2rad, eval_basis, fft_spec,
                           fft_phase_ramp)
 
-__all__ = ["propagation", "geometry", "MFT", "FFT", "calc_nfringes", "mft_geometry", "arcsec2rad", "eval_basis",
+__all__ = ["propagation", "geometry", "zernikes", "MFT", "FFT", "calc_nfringes", "mft_geometry", "arcsec2rad", "eval_basis",
            "fft_spec", "fft_phase_ramp", "downsample"]

@@ -1,0 +1,48 @@
+"""Zernike polynomials on a pupil grid (Noll order, unit-rms normalisation): the OPD basis the
+BASELINE configurations C1 / C2 put behind ``BasisOptic``.  A setup-time producer, evaluated once
+in float64 and stored as float32; mirrors ``zernike_basis`` of /root/reference/src/dLux/utils/
+zernikes.py:297-315 (``noll_indices`` :99-119, radial polynomial :122-176, azimuthal part and
+normalisation :179-204, aperture support rho <= 1 :227-254), pinned by tests/golden/
+reference_geometry.npz."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+__all__ = ["noll_indices", "zernike", "zernike_basis"]
+
+
+def noll_indices(j: int):
+    """Noll index j >= 1 -> (n, m); m < 0 are the sine terms (odd j)."""
+    if j < 1:
+        raise ValueError("The Zernike index must be greater than 0.")
+    n = int(math.ceil((-1 + math.sqrt(1 + 8 * j)) / 2) - 1)
+    first = n * (n + 1) // 2 + 1                  # smallest j of radial order n
+    # |m| values of row n in Noll order: n even: 0, 2, 2, 4, 4, ...; n odd: 1, 1, 3, 3, ...
+    idx = j - first
+    m_abs = 2 * ((idx + 1) // 2) if n % 2 == 0 else 2 * (idx // 2) + 1
+    if m_abs == 0:
+        return n, 0
+    return n, (m_abs if j % 2 == 0 else -m_abs)    # even j: cosine term
+
+
+def zernike(j: int, coordinates, diameter: float = 2.0):
+    """Z_j on cartesian `coordinates` [2, npix, npix] (x first), zero outside the unit disk of
+    the given diameter."""
+    c = np.asarray(coordinates, dtype=np.float64) / (float(diameter) / 2)
+    rho, theta = np.hypot(c[0], c[1]), np.arctan2(c[1], c[0])
+    n, m = noll_indices(j)
+    ma = abs(m)
+    radial = np.zeros_like(rho)
+    for k in range((n - ma) // 2 + 1):
+        coef = ((-1) ** k * math.factorial(n - k)
+                / (math.factorial(k) * math.factorial((n + ma) // 2 - k) * math.factorial((n - ma) // 2 - k)))
+        radial += coef * rho ** (n - 2 * k)
+    norm = math.sqrt(n + 1) * (math.sqrt(2) if m != 0 else 1.0)
+    az = np.cos(ma * theta) if m >= 0 else np.sin(ma * theta)
+    return ((rho <= 1.0) * radial * norm * az).astype(np.float32)
+
+
+def zernike_basis(js, coordinates, diameter: float = 2.0):
+    return np.stack([zernike(int(j), coordinates, diameter) for j in js])

@@ -44,30 +44,23 @@ def _circ(n, diameter):
     return (np.hypot(X, Y) <= diameter / 2).astype(np.float32)
 
 
-def _smooth_basis(n, diameter, nz, rng, T):
-    """nz smooth low-order polynomial modes on the aperture (stand-in for Zernike Noll
-    4..), unit-rms over the aperture."""
+def _zernike_opd_basis(n, diameter, nz, T):
+    """nz Zernike modes from Noll 4 (defocus) upwards on the aperture, unit rms, as in the
+    reference tutorials (``dlu.zernike_basis(np.arange(4, 4 + nz), coords, diameter)``)."""
+    from .utils.zernikes import zernike_basis
     X, Y = _coords(n, diameter)
-    x, y = X / (diameter / 2), Y / (diameter / 2)
-    modes = []
-    pw = [(i, j) for d in range(2, 8) for i in range(d + 1) for j in [d - i]]
-    for i, j in pw[:nz]:
-        m = (x ** i) * (y ** j) * T
-        m = m - m.sum() / max(T.sum(), 1) * T
-        m = m / np.sqrt((m ** 2).sum() / max(T.sum(), 1))
-        modes.append(m.astype(np.float32))
-    return np.stack(modes)
+    return zernike_basis(range(4, 4 + nz), np.stack([X, Y]), diameter) * T
 
 
 def config(name: str):
     """Returns a dict: wf_npixels, diameter, psf_npixels, psf_pixel_scale (arcsec),
     oversample, transmission, basis (metres per unit coefficient), coefficients,
     wavelengths, weights, positions [S,2] rad, fluxes [S], G (psf cotangent)."""
-    if name == "c1":      # 256 px circular aperture + 10-term basis, 1 source, 1 wavelength, -> 128
+    if name == "c1":      # 256 px circular aperture + 10-term Zernike OPD, 1 source, 1 wavelength, -> 128
         rng = np.random.default_rng(0)
         n, d = 256, 1.0
         T = _circ(n, d)
-        basis = _smooth_basis(n, d, 10, rng, T) * np.float32(1e-9)
+        basis = _zernike_opd_basis(n, d, 10, T) * np.float32(1e-9)
         out = dict(wf_npixels=n, diameter=d, psf_npixels=128, psf_pixel_scale=0.05, oversample=1,
                    wavelengths=np.array([1.0e-6], np.float32),
                    coefficients=(20 * rng.standard_normal(10)).astype(np.float32))
@@ -75,7 +68,7 @@ def config(name: str):
         rng = np.random.default_rng(1)
         n, d = 512, 1.0
         T = _circ(n, d)
-        basis = _smooth_basis(n, d, 10, rng, T) * np.float32(1e-9)
+        basis = _zernike_opd_basis(n, d, 10, T) * np.float32(1e-9)
         out = dict(wf_npixels=n, diameter=d, psf_npixels=256, psf_pixel_scale=0.025, oversample=1,
                    wavelengths=np.linspace(0.9e-6, 1.1e-6, 32).astype(np.float32),
                    coefficients=(20 * rng.standard_normal(10)).astype(np.float32))
@@ -91,7 +84,7 @@ def config(name: str):
         rng = np.random.default_rng(9)
         n, d = 128, 1.0
         T = _circ(n, d)
-        basis = _smooth_basis(n, d, 4, rng, T) * np.float32(1e-9)
+        basis = _zernike_opd_basis(n, d, 4, T) * np.float32(1e-9)
         out = dict(wf_npixels=n, diameter=d, psf_npixels=64, psf_pixel_scale=0.05, oversample=1,
                    wavelengths=np.linspace(0.95e-6, 1.05e-6, 3).astype(np.float32),
                    coefficients=(20 * rng.standard_normal(4)).astype(np.float32))

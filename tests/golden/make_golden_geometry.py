@@ -1,5 +1,5 @@
 """Generate tests/golden/reference_geometry.npz by EXECUTING the reference's own
-src/dLux/utils/{units,coordinates,geometry}.py on the NumPy-backed jax stand-in of
+src/dLux/utils/{units,coordinates,geometry,zernikes}.py on the NumPy-backed jax stand-in of
 make_golden.py (build container only; see that file for the approach)."""
 from __future__ import annotations
 
@@ -45,8 +45,21 @@ def main():
     jax.lax.switch = lambda idx, fns: fns[int(idx)]()
     jax.lax.reduce = None
     jax.lax.bitwise_or = None
+    # zernikes.py: float32 pow / exp / lgamma / cond, equinox.filter_jit as the identity
+    import math
+    import types
+    from scipy.special import gammaln
+    for name in ("ceil floor".split()):
+        setattr(jnp, name, getattr(onp, name))
+    jax.lax.pow = lambda a, b: onp.power(onp.asarray(a, onp.float32), onp.asarray(b, onp.float32)).astype(onp.float32)
+    jax.lax.exp = lambda x: onp.exp(onp.asarray(x, onp.float32)).astype(onp.float32)
+    jax.lax.lgamma = lambda x: onp.asarray(gammaln(onp.asarray(x, onp.float32)), onp.float32)
+    jax.lax.cond = lambda pred, t, f, x: t(x) if bool(pred) else f(x)
+    eqx = types.ModuleType("equinox")
+    eqx.filter_jit = lambda fn: fn
+    sys.modules["equinox"] = eqx
     utils = sys.modules["dLux.utils"]
-    for name in ("units", "geometry"):
+    for name in ("units", "geometry", "zernikes"):
         spec = importlib.util.spec_from_file_location(f"dLux.utils.{name}",
                                                       os.path.join(MG.REF, "utils", f"{name}.py"))
         mod = importlib.util.module_from_spec(spec)
@@ -88,6 +101,10 @@ def main():
                 out[f"{name}_{int(inv)}_{cname}"] = onp.asarray(fn(c.copy(), inv), dtype=onp.float32)
     # a soften() on a constant array (the `cond` branch)
     out["soften_constant"] = onp.asarray(geo.soften(onp.full((4, 4), 2.0, onp.float32), f32(0.5)), onp.float32)
+    # Zernike basis, Noll 1..15, on the unit-radius pupil of the same grid
+    zer = sys.modules["dLux.utils.zernikes"]
+    out["zernikes_1_15"] = onp.asarray(zer.zernike_basis(list(range(1, 16)), coords, f32(diam)), onp.float32)
+    out["noll_nm_1_21"] = onp.array([zer.noll_indices(j) for j in range(1, 22)], onp.int64)
     path = os.path.join(HERE, "reference_geometry.npz")
     onp.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays", os.path.getsize(path), "bytes")

@@ -77,3 +77,21 @@ def test_shape_parameters_are_differentiable():
     f = lambda rr: float(G.soft_circle(G.translate_coords(c, t.detach()), rr, 0.05).sum())
     fd = (f(0.7 + eps) - f(0.7 - eps)) / (2 * eps)
     assert abs(float(r.grad) - fd) < 1e-4 * abs(fd)
+
+
+def test_zernike_basis_matches_reference(gold):
+    # utils/zernikes.py:99-119, 297-315 executed by make_golden_geometry.py: Noll (n, m) table and
+    # the first 15 polynomials (the reference evaluates factorials as exp(lgamma) in float32,
+    # hence the 2e-5 tolerance relative to the polynomial's peak)
+    from dlux_b200.utils.zernikes import noll_indices, zernike_basis
+    nm = gold["noll_nm_1_21"]
+    assert [tuple(r) for r in nm] == [noll_indices(j) for j in range(1, 22)]
+    want = gold["zernikes_1_15"]
+    got = zernike_basis(range(1, 16), gold["coords"], 2.0)
+    assert got.shape == want.shape and got.dtype == np.float32
+    for j in range(15):
+        np.testing.assert_allclose(got[j], want[j], rtol=0, atol=2e-5 * np.abs(want[j]).max(), err_msg=f"Z{j + 1}")
+    # unit rms over the disk (piston excluded): the normalisation the coefficients are quoted in
+    inside = np.hypot(*gold["coords"]) <= 1.0
+    for j in range(1, 15):
+        assert abs(np.sqrt((got[j][inside] ** 2).mean()) - 1.0) < 0.06
