@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .layers import (AberratedLayer, BasisLayer, BasisOptic, Normalise, Optic, OpticalLayer,
+from .layers import (AberratedLayer, BasisLayer, BasisOptic, Normalise, Optic,
                      TransmissiveLayer)
 from .utils import propagation as _prop
 from .wavefronts import Wavefront

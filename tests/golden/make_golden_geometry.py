@@ -46,7 +46,6 @@ def main():
     jax.lax.reduce = None
     jax.lax.bitwise_or = None
     # zernikes.py: float32 pow / exp / lgamma / cond, equinox.filter_jit as the identity
-    import math
     import types
     from scipy.special import gammaln
     for name in ("ceil floor".split()):

@@ -1,6 +1,6 @@
 """BASELINE configs 1 and 2 through the public API on one GPU (PSF + gradient w.r.t. the Zernike
 coefficients), fused route."""
-import sys, os, time, numpy as np, torch
+import sys, os, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dlux_b200 as dl
 from dlux_b200 import workloads

@@ -1,7 +1,7 @@
 """Host-side profile of the public-API step (the bench's e2e arm): where the CPU time of one
 PSF+gradient goes.  python tools/e2e_profile.py"""
 import cProfile, pstats, sys, os, time
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dlux_b200 as dl
 from dlux_b200 import workloads, distributed as D

@@ -1,5 +1,5 @@
 """Idle gaps between the kernels of one device-resident step (torch profiler timeline)."""
-import sys, os, json, numpy as np, torch
+import sys, os, json, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torch.profiler import profile, ProfilerActivity
 exec(open(os.path.join(os.path.dirname(__file__), "graph_probe.py")).read().split("def timed")[0])

@@ -2,7 +2,7 @@ import sys, numpy as np, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import dlux_b200 as dl
 from oracle import mft_oracle as O
-from test_gpu_parity import _optics_dict, _system
+from test_gpu_parity import _optics_dict
 dev = torch.device('cuda:0')
 rng = np.random.default_rng(0)
 x = ((rng.standard_normal((2, 130, 130)) + 1j*rng.standard_normal((2, 130, 130)))/130).astype(np.complex64)

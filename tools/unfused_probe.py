@@ -1,6 +1,6 @@
 """C3 through the layer-by-layer route (fused=False): one batched wavefront, torch elementwise
 pupil ops, batched dlux_mft_c64 + its adjoint -- against the fused route."""
-import sys, os, time, numpy as np, torch
+import sys, os, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dlux_b200 as dl
 from dlux_b200 import workloads
