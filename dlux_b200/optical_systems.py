@@ -66,7 +66,7 @@ class BaseOpticalSystem:
                 "Pass offset as [on_axis_x, on_axis_y] angles in radians.")
         if wl_t is not None:
             if return_wf or not (getattr(self, "fused", False) and hasattr(self, "fused_propagate")
-                                 and self._fusable() is not None):
+                                 and self._can_fuse()):
                 raise ValueError("differentiable wavelengths need the fused route (pupil-only layer stack)")
             off = offset if torch.is_tensor(offset) else _np32(offset)
             return self.fused_propagate(wl_t, off.reshape(1, 2), weights.reshape(1, -1))
@@ -164,8 +164,28 @@ class _FocalSystem(LayeredOpticalSystem):
         return wf if return_wf else wf.psf
 
     # -- fused route ----------------------------------------------------------------
+    def _can_fuse(self) -> bool:
+        """Structure-only version of ``_fusable`` (no layer is evaluated): is the stack pupil-only,
+        with no transmission applied after a normalisation?"""
+        from .apertures import _DynamicAperture
+        normalise = False
+        for layer in self.layers.values():
+            dyn = isinstance(layer, _DynamicAperture)
+            if not dyn and type(layer) not in (TransmissiveLayer, AberratedLayer, BasisLayer, Optic,
+                                                BasisOptic, Normalise):
+                return False
+            has_t = dyn or getattr(layer, "transmission", None) is not None or (
+                isinstance(layer, BasisLayer) and layer.effect not in ("opd", "phase"))
+            if has_t and normalise:
+                return False
+            if isinstance(layer, Normalise) or getattr(layer, "normalise", False):
+                normalise = True
+        return True
+
     def _fusable(self):
         """Collapse a pupil-only stack into (T, opd, phase, normalise) or None."""
+        if not self._can_fuse():
+            return None
         T = opd = phase = None
         normalise = False
         t_after_norm = False
@@ -287,7 +307,7 @@ class _FocalSystem(LayeredOpticalSystem):
                                          npix, normalise, self.precision)
 
     def _propagate(self, wavelengths, offset, weights, return_wf):
-        if self.fused and not return_wf and self._fusable() is not None:
+        if self.fused and not return_wf and self._can_fuse():
             off = offset if torch.is_tensor(offset) else _np32(offset)
             return self.fused_propagate(wavelengths, off.reshape(1, 2), weights.reshape(1, -1))
         return super()._propagate(wavelengths, offset, weights, return_wf)

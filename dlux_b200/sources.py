@@ -84,7 +84,7 @@ class PointSources(_Source):
         else:
             weights = w[None, :] * self.flux[:, None]
         if getattr(optics, "fused", False) and not return_wf and hasattr(optics, "fused_propagate") \
-                and optics._fusable() is not None:
+                and optics._can_fuse():
             return optics.fused_propagate(self.wavelengths, self.position, weights)
         out = None
         for s in range(len(self.position)):
@@ -130,7 +130,7 @@ class BinarySource(_Source):
             w = w[None, :].expand(2, -1)
         weights = w * flux[:, None]
         if getattr(optics, "fused", False) and not return_wf and hasattr(optics, "fused_propagate") \
-                and optics._fusable() is not None:
+                and optics._can_fuse():
             return optics.fused_propagate(self.wavelengths, positions, weights)
         out = None
         for s in range(2):

@@ -102,6 +102,7 @@ def test_fusable_logic_and_validation():
     # an MFT layer in the stack is not pupil-only
     s3 = mk([dl.Optic(T, device="cpu"), dl.MFT(4, 1e-7)])
     assert s3._fusable() is None
+    assert s1._can_fuse() and not s2._can_fuse() and not s3._can_fuse()
     # evaluating a basis needs the CUDA kernel: loud error on a CPU tensor
     s4 = mk([dl.BasisOptic(basis, T, np.zeros(2, np.float32), normalise=True, device="cpu")])
     with pytest.raises(ValueError, match="CUDA tensor"):
