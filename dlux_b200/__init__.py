@@ -7,6 +7,8 @@ CPU fallback (the native library is loaded lazily and its absence is an error)."
 from . import utils
 from .apertures import (CircularAperture, CompoundAperture, CoordTransform, MultiAperture,
                         RectangularAperture, RegPolyAperture, Spider, SquareAperture)
+from .detectors import (PSF, AddConstant, ApplyJitter, ApplyPixelResponse, ApplySaturation, DetectorLayer,
+                        Downsample, LayeredDetector, Telescope)
 from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, MFT, Normalise, Optic, OpticalLayer,
                      Tilt, TransmissiveLayer)
 from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, CartesianOpticalSystem,
@@ -20,4 +22,6 @@ __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "Aberrated
            "Tilt", "Normalise", "Optic", "BasisOptic", "MFT", "FFT", "CoordSpec", "BaseOpticalSystem",
            "LayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
            "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
-           "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture"]
+           "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "PSF", "DetectorLayer",
+           "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",
+           "LayeredDetector", "Telescope"]

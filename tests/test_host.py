@@ -156,3 +156,33 @@ def test_convolve_same_matches_scipy():
         k = rng.uniform(0, 1, shape)
         got = convolve_same(torch.as_tensor(img), torch.as_tensor(k)).numpy()
         np.testing.assert_allclose(got, convolve(img, k, mode="same"), rtol=1e-10, atol=1e-12)
+
+
+def test_detector_layers_cpu():
+    # layers/detector_layers.py:100-296, detectors.py:103-128, psfs.py:74-110 on CPU tensors
+    import torch
+    from scipy.signal import convolve
+    from scipy.stats import norm
+    import dlux_b200 as dl
+    rng = np.random.default_rng(9)
+    img = rng.uniform(0, 1, (24, 24)).astype(np.float32)
+    psf = dl.PSF(img, 0.1)
+    resp = rng.uniform(0.9, 1.1, (24, 24)).astype(np.float32)
+    jit = dl.ApplyJitter(1.5, kernel_size=5, oversample=3)
+    # the kernel: normal pdf on linspace(-5, 5, 15), outer product, normalised, summed 3x3
+    g = norm.pdf(np.linspace(-5, 5, 15), scale=1.5)
+    k = np.outer(g, g)
+    k = (k / k.sum()).reshape(5, 3, 5, 3).sum((1, 3))
+    np.testing.assert_allclose(jit.kernel().numpy(), k, rtol=1e-5)
+    det = dl.LayeredDetector([("resp", dl.ApplyPixelResponse(resp)), ("jitter", jit), ("sat", dl.ApplySaturation(0.9)),
+                              ("bias", dl.AddConstant(0.01)), ("bin", dl.Downsample(4))])
+    want = np.minimum(convolve(img * resp, k, mode="same"), 0.9) + 0.01
+    want = want.reshape(6, 4, 6, 4).sum((1, 3))
+    got = det.model(psf)
+    np.testing.assert_allclose(got.numpy(), want, rtol=2e-5, atol=1e-6)
+    out = det(psf, return_psf=True)
+    assert abs(float(out.pixel_scale) - 0.4) < 1e-6 and out.npixels == 6 and det.jitter is jit
+    with pytest.raises(ValueError):
+        dl.ApplyPixelResponse(np.ones(3))
+    with pytest.raises(TypeError):
+        dl.LayeredDetector([object()])
