@@ -18,8 +18,9 @@
 // * B operand = the data (PlaneSet, common.cuh): tf32 "hi" planes in float32 plus bf16 copies
 //   of hi and of the residual lo, streamed by TMA (cp.async.bulk.tensor.cta_group::2, K-major,
 //   SWIZZLE_64B for the 64-byte fp32 rows and SWIZZLE_32B for the 32-byte bf16 rows).  Each CTA
-//   holds 64 of the 128 rows of a tile: 32 KiB stages (both tiles), a 6-deep ring, completion
-//   bytes counted on the leader CTA's mbarrier.  Shared memory carries only this operand.
+//   holds 64 of the 128 rows of a tile: 32 KiB stages (both tiles), a 5-deep ring, completion
+//   bytes counted on the leader CTA's mbarrier.  Shared memory carries this operand and the
+//   64 KiB of epilogue staging.
 // * Split precision ("TF32 + 2xBF16"): per 16-k chunk and tile, 4 tcgen05.mma kind::tf32
 //   (hi*hi, K=8) + 4 kind::f16 bf16 MMAs (hi*lo and lo*hi, K=16) accumulate into the same
 //   fp32 TMEM accumulator -- 8 MMA slots instead of the 12 of 3xTF32; lo*lo is dropped.
@@ -35,6 +36,11 @@
 //   (both CTAs' drain warpgroups) -- remote arrivals are mbarrier.arrive.relaxed.cluster.  The
 //   "empty" side is local to each CTA and signalled by tcgen05.commit ... multicast::cluster:
 //   emptyA, emptyG, tfull.
+// * Epilogues: EPI_PLANES (the intermediate of a two-stage transform) goes out through TMA
+//   stores -- every TMEM lane is one output row, so each drain thread splits and packs its
+//   own 16-column slice into the swizzled box layout of its plane and the TMA writes the six
+//   boxes of the warp asynchronously, double-buffered, clipping at the matrix edge.  EPI_C64
+//   (final complex64 result) is transposed through shared memory into 128-byte row segments.
 // * Persistent CTAs, one per SM, 20 warps in 5 warpgroups: WG0 / WG1 = drain + fused
 //   epilogue of tile a / b (setmaxnreg.inc: 128 running totals per thread), WG2 = TMA
 //   producer + one MMA issuer warp per tile (setmaxnreg.dec), WG3 / WG4 = phasor generators
@@ -56,14 +62,17 @@ constexpr int NB = 64;             // output coordinates per tile; 2*NB TMEM lan
 constexpr int BK = 16;             // k per pipeline stage = one 64-byte swizzle row of fp32
 constexpr int UMMA_K = 8;          // kind::tf32
 constexpr int ROWS_CTA = BM / 2;   // rows of a data tile resident in this CTA's shared memory (the peer holds the rest)
-constexpr int A_STAGES = 6;        // data ring (TMA), each stage holds this CTA's half of both tiles
+#ifndef DLUX_A_STAGES
+#define DLUX_A_STAGES 5            // 6 = deeper ring, single-buffered epilogue staging (0.8 % slower)
+#endif
+constexpr int A_STAGES = DLUX_A_STAGES;   // data ring (TMA), each stage holds this CTA's half of both tiles
 constexpr int G_STAGES = 2;        // phasor ring (TMEM)
 constexpr int PLANE_BYTES = ROWS_CTA * BK * 4;      // one fp32 (tf32) plane of a tile-chunk
 constexpr int BPLANE_BYTES = ROWS_CTA * BK * 2;     // one bf16 plane
 constexpr int BPL_BASE = 2 * PLANE_BYTES;           // bf16 planes follow the two fp32 planes
 constexpr int TILE_BYTES = 2 * PLANE_BYTES + 4 * BPLANE_BYTES;  // 16 KiB: my half of a tile-chunk
 constexpr int A_BYTES = 2 * TILE_BYTES;             // 32 KiB: tiles a and b
-constexpr int RING_BYTES = A_STAGES * A_BYTES;      // 192 KiB
+constexpr int RING_BYTES = A_STAGES * A_BYTES;      // 160 KiB
 #ifndef DLUX_FLUSH_CHUNKS
 #define DLUX_FLUSH_CHUNKS 4
 #endif
@@ -87,7 +96,11 @@ constexpr int REGS_EPI = 152, REGS_CTRL = 40, REGS_GEN = 64;        // setmaxnre
 static_assert(256 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_GEN),
               "register budget");
 constexpr int CLUSTER = 2;         // the CTA pair of a cta_group::2 MMA
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 2560 /*epilogue staging*/;
+constexpr int BAR_BYTES = 1024;     // barriers + TMEM slot (keeps the staging 1 KiB aligned)
+constexpr int STG_SLICE_BYTES = 4096;                      // one 16-column slice of the six planes of a warp
+constexpr int STG_BUFS = A_STAGES >= 6 ? 1 : 2;            // a 5-stage ring leaves room to double-buffer it
+constexpr int STG_WARP_BYTES = STG_BUFS * STG_SLICE_BYTES; // epilogue staging per drain warp
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + BAR_BYTES + NUM_EPI_WARPS * STG_WARP_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -162,6 +175,18 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
 __device__ __forceinline__ void umma_commit_mc2(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// bulk tensor store shared -> global (rows / columns beyond the tensor are clipped)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -393,6 +418,74 @@ __device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int
   }
 }
 
+// EPI_PLANES through TMA stores.  Thread = TMEM lane = one output row (coordinate j = lane / 2,
+// real or imaginary part = lane % 2) holding that row's 128 columns: no transposition is needed
+// -- each lane scales, splits and packs its own 16-column slice straight into the box layout of
+// its plane (16 rows x 16 columns; SWIZZLE_64B for the 64-byte fp32 rows, SWIZZLE_32B for the
+// 32-byte bf16 rows), and one lane hands the six boxes of the warp to the TMA, which writes
+// them asynchronously and clips what lies beyond the matrix.  Staging per warp (4 KiB):
+// [hi re 1 KiB | hi im 1 KiB | bf16 hi re, lo re, hi im, lo im 512 B each].
+__device__ __forceinline__ void tile_epilogue_tma(const GemmParams& p, int item, int nq0, int m0, int lane,
+                                                  float (&tot)[BM], uint32_t stg,
+                                                  const CUtensorMap* o_hr, const CUtensorMap* o_hi,
+                                                  const CUtensorMap* o_b0, const CUtensorMap* o_b1,
+                                                  const CUtensorMap* o_b2, const CUtensorMap* o_b3) {
+  const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
+  const int mmax = p.rows - m0;
+  const int j = lane >> 1, part = lane & 1;
+  const uint32_t sw64 = (uint32_t)((j >> 1) & 3), sw32 = (uint32_t)((j >> 2) & 1);
+  const uint32_t stg0 = stg;
+#pragma unroll
+  for (int s = 0; s < BM / 16; ++s) {
+    const int c0 = s * 16;
+    if (c0 >= mmax) break;  // warp-uniform: the rest of the tile lies beyond the matrix
+    stg = stg0 + (s % STG_BUFS) * STG_SLICE_BYTES;
+    const uint32_t hi_row = stg + part * 1024 + j * 64;            // my row of the fp32 plane box
+    const uint32_t bh_row = stg + 2048 + part * 1024 + j * 32;     // ... of the bf16 hi box
+    const uint32_t bl_row = bh_row + 512;                          // ... of the bf16 lo box
+    if (s >= STG_BUFS) {    // the TMA has read this buffer's previous slice
+      if (lane == 0) { if (STG_BUFS == 1) bulk_wait_read(); else bulk_wait_read1(); }
+      __syncwarp();
+    }
+    uint32_t bh[8], bl[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {   // (the re / im lanes of a pair hit the same banks: 2-way, cheap)
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = tot[c0 + 4 * c + e] * sc;
+        h[e] = tf32_hi(v);
+        l[e] = v - h[e];
+      }
+      st_shared_v4(hi_row + (((uint32_t)c ^ sw64) << 4), __float_as_uint(h[0]), __float_as_uint(h[1]),
+                   __float_as_uint(h[2]), __float_as_uint(h[3]));
+      bh[2 * c] = pack_bf16(h[0], h[1]);
+      bh[2 * c + 1] = pack_bf16(h[2], h[3]);
+      bl[2 * c] = pack_bf16(l[0], l[1]);
+      bl[2 * c + 1] = pack_bf16(l[2], l[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      st_shared_v4(bh_row + (((uint32_t)c ^ sw32) << 4), bh[4 * c], bh[4 * c + 1], bh[4 * c + 2], bh[4 * c + 3]);
+      st_shared_v4(bl_row + (((uint32_t)c ^ sw32) << 4), bl[4 * c], bl[4 * c + 1], bl[4 * c + 2], bl[4 * c + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes, before the TMA reads them
+    __syncwarp();
+    if (lane == 0) {
+      const int col = m0 + c0;
+      tma_store_3d(o_hr, stg, col, nq0, item);
+      tma_store_3d(o_hi, stg + 1024, col, nq0, item);
+      tma_store_3d(o_b0, stg + 2048, col, nq0, item);          // bf16 hi re
+      tma_store_3d(o_b1, stg + 2048 + 512, col, nq0, item);    // bf16 lo re
+      tma_store_3d(o_b2, stg + 3072, col, nq0, item);          // bf16 hi im
+      tma_store_3d(o_b3, stg + 3072 + 512, col, nq0, item);    // bf16 lo im
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read();  // the staging buffer is free again (the next user may be the C64 path)
+  __syncwarp();
+}
+
 // The 8 MMAs of one tile and one 16-k chunk:
 //   D (+)= G1_hi * Re_hi^T + G2_hi * Im_hi^T                                  (tf32, two k-steps)
 //        + G1_hi * Re_lo^T + G1_lo * Re_hi^T + G2_hi * Im_lo^T + G2_lo * Im_hi^T   (bf16, K = 16)
@@ -457,6 +550,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                const __grid_constant__ CUtensorMap mapb0, const __grid_constant__ CUtensorMap mapb1,
                const __grid_constant__ CUtensorMap mapb2, const __grid_constant__ CUtensorMap mapb3,
+               const __grid_constant__ CUtensorMap omap0, const __grid_constant__ CUtensorMap omap1,
+               const __grid_constant__ CUtensorMap omapb0, const __grid_constant__ CUtensorMap omapb1,
+               const __grid_constant__ CUtensorMap omapb2, const __grid_constant__ CUtensorMap omapb3,
                const TcParams tp) {
   extern __shared__ uint8_t smem_raw[];
   const GemmParams& p = tp.g;
@@ -481,6 +577,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb1));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb2));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb3));
+    if (tp.g.mode == EPI_PLANES) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&omap0));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&omap1));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb0));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb1));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb2));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb3));
+    }
   }
   if (warp == WARP_MMA && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
@@ -637,7 +741,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     long long dbg_w = 0, dbg_e = 0, dbg_n = 0;
     const long long dbg_start = clock64();
 #endif
-    float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256 + warp * STG_BYTES);
+    float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + BAR_BYTES + warp * STG_WARP_BYTES);
+    const uint32_t stg_addr = smem_base + RING_BYTES + BAR_BYTES + warp * STG_WARP_BYTES;
     for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
       const int item = unit / units_per_item;
       const int t = unit % units_per_item;
@@ -688,12 +793,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #ifdef DLUX_DEBUG_NOEPI
       if (m0 < p.rows && tot[5] == 123.456f) tile_epilogue(p, item, nq0, m0, lane, tot, stg);
 #else
-      if (m0 < p.rows) tile_epilogue(p, item, nq0, m0, lane, tot, stg);  // warp-uniform condition
+      if (m0 < p.rows) {  // warp-uniform condition
+        if (p.mode == EPI_PLANES)
+          tile_epilogue_tma(p, item, nq0, m0, lane, tot, stg_addr, &omap0, &omap1, &omapb0, &omapb1, &omapb2, &omapb3);
+        else
+          tile_epilogue(p, item, nq0, m0, lane, tot, stg);
+      }
 #endif
 #ifdef DLUX_DEBUG_TIMING
       dbg_e += clock64() - te0_; ++dbg_n;
 #endif
     }
+    if (lane == 0) bulk_wait_all();  // my bulk stores have completed before the CTA retires
 #ifdef DLUX_DEBUG_TIMING
     if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0)
       printf("DRAIN%d: total %lld  wait tfull %lld  epilogue %lld  units %lld\n", which, clock64() - dbg_start, dbg_w,
@@ -885,6 +996,27 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
       return DLUX_ERR_CUDA;
     }
   }
+  // output planes of EPI_PLANES, written by TMA stores: [n_items][n_out][rows], box 16 x 16
+  CUtensorMap omaps[6];
+  for (int i = 0; i < 6; ++i) {
+    if (p.mode != EPI_PLANES) { omaps[i] = maps[i]; continue; }   // unused by the C64 epilogue
+    const bool bf = i >= 2;
+    const cuuint64_t esz = bf ? 2 : 4;
+    const cuuint64_t pitch = bf ? pitch8(p.rows) : pitch4(p.rows);
+    cuuint64_t dims[3] = {(cuuint64_t)p.rows, (cuuint64_t)p.n_out, (cuuint64_t)p.n_items};
+    cuuint64_t strides[2] = {pitch * esz, pitch * esz * (cuuint64_t)p.n_out};
+    cuuint32_t box[3] = {16, 16, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    void* base = bf ? (void*)p.out.b[i - 2] : (void*)p.out.hi[i];
+    CUresult r = s.encode(&omaps[i], bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          bf ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[dlux_b200] cuTensorMapEncodeTiled (output plane %d) failed: %d\n", i, (int)r);
+      return DLUX_ERR_CUDA;
+    }
+  }
   TcParams tp;
   tp.g = p;
   tp.tiles_mp = (p.rows + 2 * BM - 1) / (2 * BM);
@@ -907,7 +1039,8 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], tp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                     omaps[0], omaps[1], omaps[2], omaps[3], omaps[4], omaps[5], tp);
   if (e != cudaSuccess) {
     fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
     return DLUX_ERR_CUDA;
