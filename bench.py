@@ -321,8 +321,8 @@ def run_ours(args):
                                   "in tf32-equivalent time (frac_executed); the GPU runs this kernel under "
                                   "sw_power_cap",
                      # dram__bytes_read+write per launch, mean of the 4 GEMM launches of a step
-                     # (profiles/r1_pair_gemm_tc_raw.csv): (1.249+0.582+0.282+0.552 + 0.521+0.122+0.499+0.502)/4 GB
-                     "traffic": 1.077e9, "traffic_algorithmic": 1.05e9,
+                     # (profiles/r1_tma_gemm_tc_raw.csv): (1.240+0.581+0.280+0.550 + 0.520+0.126+0.493+0.502)/4 GB
+                     "traffic": 1.073e9, "traffic_algorithmic": 1.05e9,
                      "gemm_ms_per_step": gemm_ms / args.steps,
                      "gemm_share_of_step": (gemm_ms / args.steps) / ms_step,
                      "gemm_launches_per_step": gemm_launches / args.steps},
