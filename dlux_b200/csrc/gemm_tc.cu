@@ -40,7 +40,10 @@
 //   stores -- every TMEM lane is one output row, so each drain thread splits and packs its
 //   own 16-column slice into the swizzled box layout of its plane and the TMA writes the six
 //   boxes of the warp asynchronously, double-buffered, clipping at the matrix edge.  EPI_C64
-//   (final complex64 result) is transposed through shared memory into 128-byte row segments.
+//   (final complex64 result) does the same with one SWIZZLE_128B box of 16 rows x 16 complex
+//   per warp and slice (real lane -> even words, imaginary lane -> odd words); only an odd
+//   row length (global pitch not a multiple of 16 bytes) takes the load/store epilogue, which
+//   transposes through shared memory into 128-byte row segments.
 // * Persistent CTAs, one per SM, 20 warps in 5 warpgroups: WG0 / WG1 = drain + fused
 //   epilogue of tile a / b (setmaxnreg.inc: 128 running totals per thread), WG2 = TMA
 //   producer + one MMA issuer warp per tile (setmaxnreg.dec), WG3 / WG4 = phasor generators
@@ -486,6 +489,50 @@ __device__ __forceinline__ void tile_epilogue_tma(const GemmParams& p, int item,
   __syncwarp();
 }
 
+// EPI_C64 through TMA stores (needs an even row length: the global row pitch must be a multiple
+// of 16 bytes).  The box of a warp and slice is 16 rows x 16 complex = 128-byte rows, SWIZZLE_128B;
+// the real lane of a row writes the even words, the imaginary lane the odd ones.  Four 2 KiB
+// buffers per warp: up to three slices in flight.
+constexpr int C64_SLICE_BYTES = 2048;
+constexpr int C64_BUFS = STG_WARP_BYTES / C64_SLICE_BYTES;   // 4 (2 with the 6-stage ring)
+__device__ __forceinline__ void bulk_wait_read_n(int n) {
+  if (n <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (n == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else if (n == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+}
+__device__ __forceinline__ void tile_epilogue_c64_tma(const GemmParams& p, int item, int nq0, int m0, int lane,
+                                                      float (&tot)[BM], uint32_t stg0, const CUtensorMap* o_c) {
+  const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
+  const int mmax = p.rows - m0;
+  const int j = lane >> 1, part = lane & 1;
+  const uint32_t row = (uint32_t)j * 128 + (uint32_t)part * 4;
+  const uint32_t sw = (uint32_t)(j & 7);
+#pragma unroll
+  for (int s = 0; s < BM / 16; ++s) {
+    const int c0 = s * 16;
+    if (c0 >= mmax) break;  // warp-uniform
+    const uint32_t stg = stg0 + (s % C64_BUFS) * C64_SLICE_BYTES;
+    if (s >= C64_BUFS) {    // the TMA has read this buffer's previous slice
+      if (lane == 0) bulk_wait_read_n(C64_BUFS - 1);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const uint32_t a = stg + row + ((((uint32_t)(c >> 1)) ^ sw) << 4) + (uint32_t)(c & 1) * 8;
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(__float_as_uint(tot[c0 + c] * sc)) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(o_c, stg, 2 * (m0 + c0), nq0, item);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read();
+  __syncwarp();
+}
+
 // The 8 MMAs of one tile and one 16-k chunk:
 //   D (+)= G1_hi * Re_hi^T + G2_hi * Im_hi^T                                  (tf32, two k-steps)
 //        + G1_hi * Re_lo^T + G1_lo * Re_hi^T + G2_hi * Im_lo^T + G2_lo * Im_hi^T   (bf16, K = 16)
@@ -544,6 +591,7 @@ __device__ __forceinline__ PartialSchedule partial_schedule(int kc, int k_chunks
 struct TcParams {
   GemmParams g;
   int tiles_mp, tiles_np, n_units, k_chunks;  // pairs of 128-row data tiles, pairs of 64-column n-tiles
+  int c64_tma;                                // EPI_C64 output goes through TMA stores (even row length)
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -553,7 +601,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
                const __grid_constant__ CUtensorMap omap0, const __grid_constant__ CUtensorMap omap1,
                const __grid_constant__ CUtensorMap omapb0, const __grid_constant__ CUtensorMap omapb1,
                const __grid_constant__ CUtensorMap omapb2, const __grid_constant__ CUtensorMap omapb3,
-               const TcParams tp) {
+               const __grid_constant__ CUtensorMap omapc, const TcParams tp) {
   extern __shared__ uint8_t smem_raw[];
   const GemmParams& p = tp.g;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -584,6 +632,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb1));
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb2));
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb3));
+    } else if (tp.c64_tma) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapc));
     }
   }
   if (warp == WARP_MMA && lane == 0) {
@@ -796,6 +846,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       if (m0 < p.rows) {  // warp-uniform condition
         if (p.mode == EPI_PLANES)
           tile_epilogue_tma(p, item, nq0, m0, lane, tot, stg_addr, &omap0, &omap1, &omapb0, &omapb1, &omapb2, &omapb3);
+        else if (tp.c64_tma)
+          tile_epilogue_c64_tma(p, item, nq0, m0, lane, tot, stg_addr, &omapc);
         else
           tile_epilogue(p, item, nq0, m0, lane, tot, stg);
       }
@@ -1017,8 +1069,25 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
       return DLUX_ERR_CUDA;
     }
   }
+  // complex64 result of EPI_C64 as a float32 tensor [n_items][n_out][2 * rows], box 32 x 16
+  CUtensorMap omapc = maps[0];
+  const int c64_tma = (p.mode == EPI_C64 && (p.rows % 2) == 0 && ((uintptr_t)p.out_c64 & 15) == 0) ? 1 : 0;
+  if (c64_tma) {
+    cuuint64_t dims[3] = {(cuuint64_t)2 * p.rows, (cuuint64_t)p.n_out, (cuuint64_t)p.n_items};
+    cuuint64_t strides[2] = {(cuuint64_t)p.rows * 8, (cuuint64_t)p.rows * 8 * (cuuint64_t)p.n_out};
+    cuuint32_t box[3] = {32, 16, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = s.encode(&omapc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.out_c64, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[dlux_b200] cuTensorMapEncodeTiled (complex64 output) failed: %d\n", (int)r);
+      return DLUX_ERR_CUDA;
+    }
+  }
   TcParams tp;
   tp.g = p;
+  tp.c64_tma = c64_tma;
   tp.tiles_mp = (p.rows + 2 * BM - 1) / (2 * BM);
   tp.tiles_np = (p.n_out + CLUSTER * NB - 1) / (CLUSTER * NB);
   const long long total = (long long)tp.tiles_mp * tp.tiles_np * p.n_items;
@@ -1040,7 +1109,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                     omaps[0], omaps[1], omaps[2], omaps[3], omaps[4], omaps[5], tp);
+                                     omaps[0], omaps[1], omaps[2], omaps[3], omaps[4], omaps[5], omapc, tp);
   if (e != cudaSuccess) {
     fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
     return DLUX_ERR_CUDA;
