@@ -293,131 +293,53 @@ constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BM >> 3) << 17) | ((uin
 constexpr uint32_t IDESC = IDESC_SHAPE | (2u << 7) | (2u << 10);
 constexpr uint32_t IDESC_BF16 = IDESC_SHAPE | (1u << 7) | (1u << 10);
 
-// Fused epilogue of one tile, staged through shared memory so that every global access is
-// coalesced.  Thread = TMEM lane: within warp q, lane 2j' carries Re(Out[n][m0 + c]) and lane
-// 2j'+1 Im(...) of output row n = nq0 + j' for the 128 data rows c.  In slices of 16 columns
-// each lane drops its values (already scaled) into a [32 rows][16 cols] fp32 staging tile,
-// and the warp reads it back with lanes running along m: 64- or 128-byte row segments per
-// store instruction, real and imaginary parts of one element meeting in one thread.
+// Load/store epilogue of EPI_C64 for an ODD row length (the global row pitch is then not a
+// multiple of 16 bytes and the TMA cannot be used), staged through shared memory so that the
+// global accesses are coalesced.  Thread = TMEM lane: within warp q, lane 2j' carries
+// Re(Out[n][m0 + c]) and lane 2j'+1 Im(...) of output row n = nq0 + j' for the 128 data rows c.
+// In slices of 16 columns each lane drops its values (already scaled) into a [32 rows][16 cols]
+// fp32 staging tile, and the warp reads it back with lanes running along m: real and imaginary
+// parts of one element meet in one thread and leave as 8-byte complex stores.
 constexpr int STG_COLS = 16;
 constexpr int STG_PITCH = 20;                       // floats; conflict-free 128-bit row writes
 constexpr int STG_BYTES = 32 * STG_PITCH * 4;       // 2560 B per warp
+static_assert(STG_BYTES <= STG_WARP_BYTES, "staging");
 
-__device__ __forceinline__ void tile_epilogue(const GemmParams& p, int item, int nq0, int m0, int lane,
-                                              float (&tot)[BM], float* stg) {
+__device__ __forceinline__ void tile_epilogue_c64_lsu(const GemmParams& p, int item, int nq0, int m0, int lane,
+                                                      float (&tot)[BM], float* stg) {
   const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
   const int mmax = p.rows - m0;  // tile columns c < mmax are valid
-  if (p.mode == EPI_PLANES) {
-    // read-back mapping: lane -> staging rows r = lane/4 + 8*it (it = 0..3), 4 columns at
-    // 4*(lane%4).  r & 1 (real / imaginary row) does not depend on `it`; the output row
-    // advances by 4 per `it`: base pointers are formed once per tile.
-    const int cc = 4 * (lane & 3);
-    const int part = (lane >> 2) & 1;
-    const int n_first = nq0 + (lane >> 3);
-#ifdef DLUX_DEBUG_NOSTG  // timing experiment: all the epilogue's work, its stores redirected to shared memory
-    const bool real = tot[5] == 123.456f;
-    const int p4 = real ? pitch4(p.rows) : 0, p8 = real ? pitch8(p.rows) : 0;
-    const size_t row0 = (size_t)item * p.n_out + n_first;
-    float* hp0 = real ? p.out.hi[part] + row0 * p4 + m0 + cc : stg + cc;
-    __nv_bfloat16* hb0 = real ? p.out.b[2 * part] + row0 * p8 + m0 + cc : reinterpret_cast<__nv_bfloat16*>(stg) + cc;
-    __nv_bfloat16* lb0 = real ? p.out.b[2 * part + 1] + row0 * p8 + m0 + cc : reinterpret_cast<__nv_bfloat16*>(stg) + cc;
-#else
-    const int p4 = pitch4(p.rows), p8 = pitch8(p.rows);
-    const size_t row0 = (size_t)item * p.n_out + n_first;
-    float* hp0 = p.out.hi[part] + row0 * p4 + m0 + cc;
-    __nv_bfloat16* hb0 = p.out.b[2 * part] + row0 * p8 + m0 + cc;
-    __nv_bfloat16* lb0 = p.out.b[2 * part + 1] + row0 * p8 + m0 + cc;
-#endif
+  // lane -> output row j = lane/8 + 4*it (it = 0..3), complex pair at columns 2*(lane%8)
+  const int cc = 2 * (lane & 7);
+  const int j0 = lane >> 3;
+  float2* out0 = p.out_c64 + ((size_t)item * p.n_out + nq0 + j0) * p.rows + m0 + cc;
 #pragma unroll
-    for (int s = 0; s < BM / STG_COLS; ++s) {
-      const int c0 = s * STG_COLS;
+  for (int s = 0; s < BM / STG_COLS; ++s) {
+    const int c0 = s * STG_COLS;
 #pragma unroll
-      for (int v = 0; v < STG_COLS / 4; ++v)
-        *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * v) =
-            make_float4(tot[c0 + 4 * v] * sc, tot[c0 + 4 * v + 1] * sc, tot[c0 + 4 * v + 2] * sc,
-                        tot[c0 + 4 * v + 3] * sc);
-      __syncwarp();
-      if (c0 < mmax) {  // warp-uniform
-        float4 v[4];
+    for (int v = 0; v < STG_COLS / 4; ++v)
+      *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * v) =
+          make_float4(tot[c0 + 4 * v] * sc, tot[c0 + 4 * v + 1] * sc, tot[c0 + 4 * v + 2] * sc,
+                      tot[c0 + 4 * v + 3] * sc);
+    __syncwarp();
+    if (c0 < mmax) {  // warp-uniform
+      float2 re[4], im[4];
 #pragma unroll
-        for (int it = 0; it < 4; ++it)
-          v[it] = *reinterpret_cast<const float4*>(stg + ((lane >> 2) + 8 * it) * STG_PITCH + cc);
+      for (int it = 0; it < 4; ++it) {
+        const int j = j0 + 4 * it;
+        re[it] = *reinterpret_cast<const float2*>(stg + (2 * j) * STG_PITCH + cc);
+        im[it] = *reinterpret_cast<const float2*>(stg + (2 * j + 1) * STG_PITCH + cc);
+      }
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          if (n_first + 4 * it < p.n_out) {
-            float4 h;
-            h.x = tf32_hi(v[it].x); h.y = tf32_hi(v[it].y); h.z = tf32_hi(v[it].z); h.w = tf32_hi(v[it].w);
-            float* hp = hp0 + (size_t)(4 * it) * p4 + c0;
-            __nv_bfloat16* hb = hb0 + (size_t)(4 * it) * p8 + c0;
-            __nv_bfloat16* lb = lb0 + (size_t)(4 * it) * p8 + c0;
-            if (c0 + cc + 4 <= mmax) {  // pitches, m0, c0, cc are multiples of 4: aligned vector stores
-              *reinterpret_cast<float4*>(hp) = h;
-              uint2 wh, wl;
-              wh.x = pack_bf16(h.x, h.y); wh.y = pack_bf16(h.z, h.w);
-              wl.x = pack_bf16(v[it].x - h.x, v[it].y - h.y); wl.y = pack_bf16(v[it].z - h.z, v[it].w - h.w);
-              *reinterpret_cast<uint2*>(hb) = wh;
-              *reinterpret_cast<uint2*>(lb) = wl;
-            } else {
-              const float hh[4] = {h.x, h.y, h.z, h.w}, vv[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (c0 + cc + e < mmax) {
-                  hp[e] = hh[e];
-                  hb[e] = __float2bfloat16_rn(hh[e]);
-                  lb[e] = __float2bfloat16_rn(vv[e] - hh[e]);
-                }
-            }
-          }
+      for (int it = 0; it < 4; ++it) {
+        if (nq0 + j0 + 4 * it < p.n_out) {
+          float2* out = out0 + (size_t)(4 * it) * p.rows + c0;
+          if (c0 + cc < mmax) out[0] = make_float2(re[it].x, im[it].x);
+          if (c0 + cc + 1 < mmax) out[1] = make_float2(re[it].y, im[it].y);
         }
       }
-      __syncwarp();
     }
-  } else {  // EPI_C64
-    // lane -> output row j = lane/8 + 4*it (it = 0..3), complex pair at columns 2*(lane%8)
-    const int cc = 2 * (lane & 7);
-    const int j0 = lane >> 3;
-    const bool vec = (p.rows & 1) == 0;  // 16-byte alignment of (n * rows + even column) complex pairs
-#ifdef DLUX_DEBUG_NOSTG
-    const bool real = tot[5] == 123.456f;
-    const int prow = real ? p.rows : 0;
-    float2* out0 = real ? p.out_c64 + ((size_t)item * p.n_out + nq0 + j0) * p.rows + m0 + cc
-                        : reinterpret_cast<float2*>(stg) + cc;
-#else
-    const int prow = p.rows;
-    float2* out0 = p.out_c64 + ((size_t)item * p.n_out + nq0 + j0) * p.rows + m0 + cc;
-#endif
-#pragma unroll
-    for (int s = 0; s < BM / STG_COLS; ++s) {
-      const int c0 = s * STG_COLS;
-#pragma unroll
-      for (int v = 0; v < STG_COLS / 4; ++v)
-        *reinterpret_cast<float4*>(stg + lane * STG_PITCH + 4 * v) =
-            make_float4(tot[c0 + 4 * v] * sc, tot[c0 + 4 * v + 1] * sc, tot[c0 + 4 * v + 2] * sc,
-                        tot[c0 + 4 * v + 3] * sc);
-      __syncwarp();
-      if (c0 < mmax) {  // warp-uniform
-        float2 re[4], im[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int j = j0 + 4 * it;
-          re[it] = *reinterpret_cast<const float2*>(stg + (2 * j) * STG_PITCH + cc);
-          im[it] = *reinterpret_cast<const float2*>(stg + (2 * j + 1) * STG_PITCH + cc);
-        }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          if (nq0 + j0 + 4 * it < p.n_out) {
-            float2* out = out0 + (size_t)(4 * it) * prow + c0;
-            if (vec && c0 + cc + 2 <= mmax) {
-              *reinterpret_cast<float4*>(out) = make_float4(re[it].x, im[it].x, re[it].y, im[it].y);
-            } else {
-              if (c0 + cc < mmax) out[0] = make_float2(re[it].x, im[it].x);
-              if (c0 + cc + 1 < mmax) out[1] = make_float2(re[it].y, im[it].y);
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
+    __syncwarp();
   }
 }
 
@@ -841,7 +763,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       const long long te0_ = clock64();
 #endif
 #ifdef DLUX_DEBUG_NOEPI
-      if (m0 < p.rows && tot[5] == 123.456f) tile_epilogue(p, item, nq0, m0, lane, tot, stg);
+      if (m0 < p.rows && tot[5] == 123.456f) tile_epilogue_c64_lsu(p, item, nq0, m0, lane, tot, stg);
 #else
       if (m0 < p.rows) {  // warp-uniform condition
         if (p.mode == EPI_PLANES)
@@ -849,7 +771,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         else if (tp.c64_tma)
           tile_epilogue_c64_tma(p, item, nq0, m0, lane, tot, stg_addr, &omapc);
         else
-          tile_epilogue(p, item, nq0, m0, lane, tot, stg);
+          tile_epilogue_c64_lsu(p, item, nq0, m0, lane, tot, stg);
       }
 #endif
 #ifdef DLUX_DEBUG_TIMING
