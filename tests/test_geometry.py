@@ -95,3 +95,41 @@ def test_zernike_basis_matches_reference(gold):
     inside = np.hypot(*gold["coords"]) <= 1.0
     for j in range(1, 15):
         assert abs(np.sqrt((got[j][inside] ** 2).mean()) - 1.0) < 0.06
+
+
+def test_aperture_layers_on_a_cpu_wavefront():
+    # layers/apertures.py:134-152, 1005-1117: a dynamic aperture multiplies the wavefront by its
+    # transmission on the wavefront's own coordinates; Compound = product, Multi = sum
+    import dlux_b200 as dl
+    wf = dl.Wavefront(1e-6, 32, diameter=2.0, device="cpu")
+    primary = dl.CircularAperture(np.float32(0.8), softening=2.0)
+    secondary = dl.CircularAperture(np.float32(0.2), occulting=True, softening=2.0)
+    spider = dl.Spider(np.float32(0.05), [0.0, 90.0, 180.0, 270.0])
+    comp = dl.CompoundAperture([("primary", primary), ("secondary", secondary), ("spider", spider)], normalise=True)
+    coords, ps = wf.coordinates(), wf.pixel_scale
+    want = primary.transmission(coords, ps) * secondary.transmission(coords, ps) * spider.transmission(coords, ps)
+    out = comp(wf)
+    np.testing.assert_allclose(out.amplitude.numpy() ** 2 / (out.amplitude.numpy() ** 2).sum(),
+                               (want.numpy() ** 2) / (want.numpy() ** 2).sum(), rtol=1e-5, atol=1e-9)
+    assert abs(float(out.power) - 1.0) < 1e-5 and comp.primary is primary
+    holes = [dl.CircularAperture(np.float32(0.15), dl.CoordTransform(translation=np.array([x, y], np.float32)))
+             for x, y in ((0.4, 0.0), (-0.3, 0.35), (0.0, -0.5))]
+    multi = dl.MultiAperture(holes)
+    t = multi.transmission(coords, ps)
+    np.testing.assert_allclose(t.numpy(), sum(h.transmission(coords, ps) for h in holes).numpy(), rtol=1e-6)
+    assert 0.99 < float(t.max()) <= 1.0 + 1e-6
+    hexa = dl.RegPolyAperture(6, np.float32(0.7), dl.CoordTransform(rotation=np.float32(0.1)))
+    sq = dl.SquareAperture(np.float32(1.0))
+    rect = dl.RectangularAperture(np.float32(0.5), np.float32(1.2))
+    for ap in (hexa, sq, rect):
+        tt = ap.transmission(coords, ps)
+        assert tt.shape == (32, 32) and float(tt.min()) >= 0 and float(tt.max()) <= 1 + 1e-6
+    assert float(rect.transmission(coords, ps).sum()) < float(sq.transmission(coords, ps).sum())
+    with pytest.raises(TypeError):
+        dl.CircularAperture(0.5, transformation="shift")
+    with pytest.raises(ValueError):
+        dl.CircularAperture(0.5, softening=0.0)
+    with pytest.raises(ValueError):
+        dl.CoordTransform(translation=[1.0])
+    with pytest.raises(TypeError):
+        dl.CompoundAperture([object()])
