@@ -89,6 +89,60 @@ def make_mft():
     return MFT
 
 
+class _PolyDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("n_pupil", "n_psf", "n_wavels", "n_sources", "normalise",
+                                              "precision", "save_field", "reserved")]
+
+
+def make_polypsf(n_pupil, n_psf, normalise=True, precision=0):
+    """Fused polychromatic PSF with a custom VJP over ``dlux_polypsf_fwd/bwd``:
+
+        psf = polypsf(transmission, opd, wavenumber, scale_out, norm, weights, delta_xy)
+
+    transmission, opd [N, N]; wavenumber, scale_out, norm [L]; weights [S, L]; delta_xy [S, L, 2]
+    (fringes).  Differentiable w.r.t. every operand (what ``jax.grad`` through
+    ``OpticalSystem.propagate`` returns).  An ``OpticalSystem.propagate`` override forms the
+    operands with the reference's own float32 expressions (optical_systems.py:147-223)."""
+    lib = ctypes.CDLL(_LIB)
+    jax.ffi.register_ffi_target("dlux_polypsf_fwd", jax.ffi.pycapsule(lib.dlux_polypsf_fwd_ffi), platform="CUDA")
+    jax.ffi.register_ffi_target("dlux_polypsf_bwd", jax.ffi.pycapsule(lib.dlux_polypsf_bwd_ffi), platform="CUDA")
+    _core.dlux_polypsf_scratch_bytes.restype = ctypes.c_size_t
+    attrs = dict(n_pupil=np.int32(n_pupil), n_psf=np.int32(n_psf), normalise=np.int32(bool(normalise)),
+                 precision=np.int32(precision))
+    empty = jnp.zeros((0,), jnp.float32)
+
+    def _scratch(L, S):
+        d = _PolyDesc(n_pupil, n_psf, L, S, int(bool(normalise)), precision, 1, 0)
+        return jax.ShapeDtypeStruct((_core.dlux_polypsf_scratch_bytes(ctypes.byref(d)),), jnp.uint8)
+
+    @jax.custom_vjp
+    def polypsf(transmission, opd, wavenumber, scale_out, norm, weights, delta_xy):
+        return _fwd(transmission, opd, wavenumber, scale_out, norm, weights, delta_xy)[0]
+
+    def _fwd(transmission, opd, wavenumber, scale_out, norm, weights, delta_xy):
+        S, L = weights.shape
+        outs = (jax.ShapeDtypeStruct((n_psf, n_psf), jnp.float32),
+                jax.ShapeDtypeStruct((S * L, n_psf, n_psf), jnp.complex64), _scratch(L, S))
+        psf, field, _ = jax.ffi.ffi_call("dlux_polypsf_fwd", outs)(
+            transmission, opd, empty, wavenumber, scale_out, norm, weights, delta_xy, **attrs)
+        return psf, (transmission, opd, wavenumber, scale_out, norm, weights, delta_xy, field)
+
+    def _bwd(res, psf_bar):
+        transmission, opd, wavenumber, scale_out, norm, weights, delta_xy, field = res
+        S, L = weights.shape
+        f32 = lambda *shape: jax.ShapeDtypeStruct(shape, jnp.float32)
+        outs = (f32(n_pupil, n_pupil), f32(0), f32(S, L), f32(S, L, 2), f32(n_pupil, n_pupil), f32(S, L),
+                f32(S, L), _scratch(L, S))
+        opd_b, _, w_b, d_b, t_b, s_b, k_b, _ = jax.ffi.ffi_call("dlux_polypsf_bwd", outs)(
+            transmission, opd, empty, wavenumber, scale_out, norm, weights, delta_xy, field,
+            psf_bar.astype(jnp.float32), **attrs)
+        norm_b = 2.0 * (weights * w_b).sum(0) / norm        # the PSF is quadratic in norm
+        return t_b, opd_b, k_b.sum(0), s_b.sum(0), norm_b, w_b, d_b
+
+    polypsf.defvjp(_fwd, _bwd)
+    return polypsf
+
+
 def install():
     """Monkey-patch dLux (both the defining module and the re-exported copy)."""
     import dLux.utils as dlu
