@@ -210,7 +210,7 @@ def run_ours(args):
 
     # the model is built once (as in a fitting loop); every step gets new coefficients and a new
     # image-plane cotangent from the host
-    e2e_layer = dl.BasisOptic(basis_d, T_d, coeffs_d, "opd", normalise=True, device=dev)
+    e2e_layer = dl.BasisOptic(basis_d, T_d, coeffs_d, normalise=True, effect="opd", device=dev)
     optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("pupil", e2e_layer)], cfg["psf_npixels"],
                                      cfg["psf_pixel_scale"], cfg["oversample"], device=dev)
 

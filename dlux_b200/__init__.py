@@ -7,12 +7,14 @@ CPU fallback (the native library is loaded lazily and its absence is an error)."
 from . import utils
 from .apertures import (CircularAperture, CompoundAperture, CoordTransform, MultiAperture,
                         RectangularAperture, RegPolyAperture, Spider, SquareAperture)
-from .detectors import (PSF, AddConstant, ApplyJitter, ApplyPixelResponse, ApplySaturation, DetectorLayer,
+from .psfs import PSF
+from .detectors import (AddConstant, ApplyJitter, ApplyPixelResponse, ApplySaturation, DetectorLayer,
                         Downsample, LayeredDetector, Telescope)
 from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, MFT, Normalise, Optic, OpticalLayer,
                      Tilt, TransmissiveLayer)
 from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, CartesianOpticalSystem,
-                              LayeredOpticalSystem)
+                              LayeredOpticalSystem, OpticalSystem, ParametricLayeredOpticalSystem,
+                              ParametricOpticalSystem)
 from .sources import (BinarySource, PointResolvedSource, PointSource, PointSources, ResolvedSource,
                       Scene)
 from .wavefronts import CoordSpec, Wavefront
@@ -20,7 +22,8 @@ from .wavefronts import CoordSpec, Wavefront
 __version__ = "0.1.0"
 __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer",
            "Tilt", "Normalise", "Optic", "BasisOptic", "MFT", "FFT", "CoordSpec", "BaseOpticalSystem",
-           "LayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
+           "OpticalSystem", "ParametricOpticalSystem",
+           "LayeredOpticalSystem", "ParametricLayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
            "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "PSF", "DetectorLayer",
            "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",

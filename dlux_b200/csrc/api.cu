@@ -13,6 +13,7 @@ static std::atomic<uint64_t> g_launches{0};
 static thread_local int g_last_cuda_error = 0;
 
 void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void note_cuda_error(int code) { g_last_cuda_error = code; }
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -259,7 +260,10 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
   int rc = check_mft_desc(d);
   if (rc != DLUX_OK) return rc;
   if (!in || !out || !scale_out || !scratch) return DLUX_ERR_ARG;
-  if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)scratch) & 15) return DLUX_ERR_ALIGN;
+  // `in` is read as float2 (an odd-N slice of a batched phasor is only 8-byte aligned); `out`
+  // and `scratch` are TMA targets
+  if (((uintptr_t)out | (uintptr_t)scratch) & 15) return DLUX_ERR_ALIGN;
+  if ((uintptr_t)in & 7) return DLUX_ERR_ALIGN;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   MftScratch s;
   bool ok = true;

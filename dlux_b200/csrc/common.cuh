@@ -158,6 +158,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
 // launch counters / error plumbing (api.cu)
 void note_launch(int n = 1);
 int check_launch(const char* what);
+void note_cuda_error(int code);   // remembered for dlux_last_cuda_error()
 
 // kernels' host launchers
 int launch_gemm_simt(const GemmParams& p, cudaStream_t st);

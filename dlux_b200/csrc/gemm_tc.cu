@@ -912,31 +912,41 @@ struct TcState {
   int num_sms = 0;
   int cc_major = 0;
   int rc = DLUX_OK;
+  bool ready = false;
 };
 
+// Kernel attributes (the dynamic shared-memory opt-in) and the SM count are PER DEVICE: one
+// state per device ordinal, initialised on the first launch on that device.
 TcState& tc_state() {
-  static TcState st;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { st.rc = DLUX_ERR_CUDA; return; }
-    cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&st.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
-    if (st.cc_major != 10) { st.rc = DLUX_ERR_UNSUPPORTED; return; }
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess || !fn) {
-      st.rc = DLUX_ERR_CUDA;
-      return;
-    }
-    st.encode = (EncodeTiledFn)fn;
-    if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-        cudaSuccess) {
-      st.rc = DLUX_ERR_CUDA;
-      return;
-    }
-  });
+  constexpr int MAX_DEV = 64;
+  static TcState states[MAX_DEV];
+  static std::mutex mu;
+  static TcState bad;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) {
+    bad.rc = DLUX_ERR_CUDA;
+    return bad;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  TcState& st = states[dev];
+  if (st.ready) return st;
+  st.ready = true;
+  cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&st.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (st.cc_major != 10) { st.rc = DLUX_ERR_UNSUPPORTED; return st; }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !fn) {
+    st.rc = DLUX_ERR_CUDA;
+    return st;
+  }
+  st.encode = (EncodeTiledFn)fn;
+  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+      cudaSuccess) {
+    st.rc = DLUX_ERR_CUDA;
+    return st;
+  }
   return st;
 }
 
@@ -1034,6 +1044,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
                                      omaps[0], omaps[1], omaps[2], omaps[3], omaps[4], omaps[5], omapc, tp);
   if (e != cudaSuccess) {
     fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
+    note_cuda_error((int)e);
     return DLUX_ERR_CUDA;
   }
   note_launch();

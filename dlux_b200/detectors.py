@@ -1,4 +1,4 @@
-"""Image-plane tail after the MFT path (SURVEY 8f NEXT-4): the ``PSF`` container, the detector
+"""Image-plane tail after the MFT path (SURVEY 8f NEXT-4): the detector
 layers that act on it and ``Telescope``, which chains optics -> source -> detector.  Mirrors
 /root/reference/src/dLux/psfs.py:14-111, layers/detector_layers.py:100-296, detectors.py:47-128
 and instruments.py:37-172.  Everything here is O(M^2) torch arithmetic on the oversampled PSF the
@@ -12,62 +12,12 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from .sources import Scene, _Source, convolve_same
+from .psfs import PSF
+from .sources import Scene, _Source
 from .utils.array_ops import downsample
 
 __all__ = ["PSF", "DetectorLayer", "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant",
            "Downsample", "LayeredDetector", "Telescope", "gaussian_kernel"]
-
-
-class PSF:
-    """psfs.py:14-111: PSF array + pixel scale."""
-
-    def __init__(self, data, pixel_scale):
-        self.data = data if torch.is_tensor(data) else torch.as_tensor(np.asarray(data, dtype=np.float32))
-        self.pixel_scale = pixel_scale if torch.is_tensor(pixel_scale) else torch.as_tensor(
-            np.asarray(pixel_scale, dtype=np.float32), device=self.data.device)
-
-    def set(self, **kw):
-        new = copy.copy(self)
-        for k, v in kw.items():
-            setattr(new, k, v)
-        return new
-
-    @property
-    def npixels(self):
-        return self.data.shape[-1]
-
-    @property
-    def ndim(self):
-        return self.pixel_scale.dim()
-
-    def downsample(self, n: int):                      # psfs.py:74-91: sum over n x n blocks
-        return self.set(data=downsample(self.data, n, mean=False), pixel_scale=self.pixel_scale * n)
-
-    def convolve(self, other):                         # psfs.py:93-110
-        other = other if torch.is_tensor(other) else torch.as_tensor(np.asarray(other, np.float32))
-        return self.set(data=convolve_same(self.data, other.to(self.data.device, self.data.dtype)))
-
-    def _op(self, other, fn):
-        if other is None:
-            return self
-        if isinstance(other, PSF):
-            other = other.data
-        if isinstance(other, np.ndarray):
-            other = torch.as_tensor(other, device=self.data.device)
-        return self.set(data=fn(self.data, other))
-
-    def __add__(self, other):
-        return self._op(other, lambda a, b: a + b)
-
-    def __sub__(self, other):
-        return self._op(other, lambda a, b: a - b)
-
-    def __mul__(self, other):
-        return self._op(other, lambda a, b: a * b)
-
-    def __truediv__(self, other):
-        return self._op(other, lambda a, b: a / b)
 
 
 def gaussian_kernel(sigma, npixels: int, extent: float = 5.0, device=None):

@@ -64,15 +64,20 @@ def all_reduce_grads(params: Sequence[torch.Tensor], group=None) -> None:
     """Sum the .grad of replicated parameters across ranks (one flat all-reduce)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    params = list(params)
+    if not params:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    # a rank whose shard is empty has no .grad: it contributes zeros, so that every rank enters the
+    # collective with the same buffer
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].reshape(g.shape))
-        off += g.numel()
+    for p in params:
+        p.grad.copy_(flat[off:off + p.numel()].reshape(p.shape))
+        off += p.numel()
 
 
 def sharded_point_sources_model(optics, wavelengths, positions, fluxes, weights=None, group=None,
@@ -98,5 +103,12 @@ def sharded_point_sources_model(optics, wavelengths, positions, fluxes, weights=
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     ss, ls = shard_sources_or_wavelengths(S, L, world, rank)
     fn = model_fn if model_fn is not None else optics.fused_propagate
-    psf = fn(wavelengths[ls], positions[ss], w_sl[ss, ls])
+    if ss.stop - ss.start == 0 or ls.stop - ls.start == 0:
+        # more ranks than sources and than wavelengths: this rank owns nothing but must still take
+        # part in the all-reduce (the others would block in it otherwise)
+        npix = optics._focal_args()[0]
+        psf = torch.zeros((npix, npix), dtype=torch.float32, device=getattr(optics, "device", "cpu"),
+                          requires_grad=True)
+    else:
+        psf = fn(wavelengths[ls], positions[ss], w_sl[ss, ls])
     return all_reduce_sum(psf, group)

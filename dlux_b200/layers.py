@@ -58,12 +58,16 @@ class AberratedLayer(OpticalLayer):
 
 
 class BasisLayer(OpticalLayer):
-    def __init__(self, basis=None, coefficients=None, effect: str = "opd", device=None):
+    def __init__(self, basis=None, coefficients=None, effect: str = "opd", device=None,
+                 coefficient_shape=None):
         self.basis = _arr(basis, device)
-        if coefficients is None and self.basis is not None:
-            coefficients = torch.zeros(self.basis.shape[:-2], dtype=torch.float32,
-                                       device=self.basis.device)
+        if coefficients is None and self.basis is not None:    # optical_layers.py:284-296
+            shape = tuple(self.basis.shape[:-2]) if coefficient_shape is None else tuple(coefficient_shape)
+            coefficients = torch.zeros(shape, dtype=torch.float32, device=self.basis.device)
         self.coefficients = _arr(coefficients, device)
+        if self.basis is not None and tuple(self.basis.shape[:self.coefficients.dim()]) != tuple(
+                self.coefficients.shape):
+            raise ValueError("The coefficient shape must match the leading basis dimensions.")
         if effect not in ("opd", "phase", "amplitude"):
             raise ValueError("effect must be 'opd', 'phase', or 'amplitude'.")
         self.effect = effect
@@ -115,10 +119,11 @@ class Optic(TransmissiveLayer, AberratedLayer):
 
 
 class BasisOptic(TransmissiveLayer, BasisLayer):
-    def __init__(self, basis, transmission=None, coefficients=None, effect: str = "opd",
-                 normalise: bool = False, device=None):
+    def __init__(self, basis, transmission=None, coefficients=None, normalise: bool = False,
+                 effect: str = "opd", coefficient_shape=None, device=None):
+        # layers/optics.py:122-152 argument order
         TransmissiveLayer.__init__(self, transmission, normalise, device)
-        BasisLayer.__init__(self, basis, coefficients, effect, device)
+        BasisLayer.__init__(self, basis, coefficients, effect, device, coefficient_shape)
 
     def __call__(self, wavefront):                     # layers/optics.py:168-175
         if self.transmission is not None:

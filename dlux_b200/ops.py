@@ -139,20 +139,109 @@ class MFTFunction(torch.autograd.Function):
     the primitive's transpose rule would call).  The backward is itself an ``MFTFunction``
     (adjoint flag flipped), so the operator is closed under differentiation: Hessians /
     Hessian-vector products of a loss through the layer-by-layer route work by double backward
-    (SURVEY 8f NEXT-1, second order)."""
+    (SURVEY 8f NEXT-1, second order).
+
+    The geometry operands are differentiable too (first order), as ``jax.grad`` differentiates
+    ``transfer_matrix`` / ``calc_nfringes`` (propagation.py:110-127, 165-175, 246-254): with the
+    phasors exp(sgn 2 pi i x u), x = (i - (N-1)/2 - shift)/N, u = s (a - (M-1)/2 - shift) - delta,
+
+        d out / d s       = sgn 2 pi i (a~ D_y + b~ D_x),   a~ = a - (M-1)/2 - shift
+        d out / d delta_x = -sgn 2 pi i D_x                  (same for y)
+        d out / d shift_x = sgn 2 pi i (-(u_b / N) out - s D_x)
+        d out / d norm    = out / norm
+
+    where D_x = MFT(P x_j) and D_y = MFT(x_i P) are two more transforms of the index-weighted
+    input (one batched call); each cotangent is Re <g, d out / d theta> per batch item."""
 
     @staticmethod
     def forward(ctx, phasor, scale_out, n_other, shift_xy, delta_xy, norm, inverse, precision, adjoint=False):
         ctx.n_self = phasor.shape[-1]
+        ctx.n_other = n_other
         ctx.args = (scale_out, shift_xy, delta_xy, norm, inverse, precision, bool(adjoint))
-        return mft_c64(phasor, scale_out, n_other, shift_xy, delta_xy, norm, inverse, bool(adjoint), precision)
+        out = mft_c64(phasor, scale_out, n_other, shift_xy, delta_xy, norm, inverse, bool(adjoint), precision)
+        geo = [t for t in (scale_out, shift_xy, delta_xy, norm) if torch.is_tensor(t) and t.requires_grad]
+        ctx.geo = bool(geo)
+        if ctx.geo:
+            if adjoint:
+                raise NotImplementedError("dlux_b200: geometry gradients of the adjoint MFT (second order "
+                                          "w.r.t. pixel scale / wavelength on the layer route) are not implemented")
+            ctx.save_for_backward(phasor, out)
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
         scale_out, shift_xy, delta_xy, norm, inverse, precision, adjoint = ctx.args
-        g = MFTFunction.apply(grad_out.contiguous(), scale_out, ctx.n_self, shift_xy, delta_xy, norm,
-                              inverse, precision, not adjoint)
-        return g, None, None, None, None, None, None, None, None
+        need = ctx.needs_input_grad
+        g_ph = None
+        if need[0]:
+            g_ph = MFTFunction.apply(grad_out.contiguous(), scale_out, ctx.n_self, shift_xy, delta_xy, norm,
+                                     inverse, precision, not adjoint)
+        g_s = g_sh = g_de = g_no = None
+        if ctx.geo and any(need[i] for i in (1, 3, 4, 5)):
+            phasor, out = ctx.saved_tensors
+            g_s, g_sh, g_de, g_no = _mft_geometry_bar(phasor.detach(), out.detach(), grad_out, scale_out, shift_xy,
+                                                      delta_xy, norm, ctx.n_other, inverse, precision, need)
+        return g_ph, g_s, None, g_sh, g_de, g_no, None, None, None
+
+
+def _mft_geometry_bar(phasor, out, g, scale_out, shift_xy, delta_xy, norm, n_out, inverse, precision, need):
+    """Cotangents of the MFT's geometry operands (see MFTFunction)."""
+    dev = phasor.device
+    N = phasor.shape[-1]
+    M = int(n_out)
+    P = phasor.reshape(-1, N, N)
+    B = P.shape[0]
+    G = g.reshape(B, M, M).to(torch.complex64)
+    O_ = out.reshape(B, M, M)
+
+    def per_item(v, width, fill):
+        if v is None:
+            return torch.full((B, width), fill, dtype=torch.float32, device=dev)
+        v = _f32(v.detach() if torch.is_tensor(v) else v, dev)
+        if v.numel() == width:
+            v = v.reshape(1, width).expand(B, width)
+        return v.reshape(B, width).contiguous()
+
+    s = per_item(scale_out, 1, 1.0).reshape(B)
+    sh = per_item(shift_xy, 2, 0.0)
+    de = None if delta_xy is None else per_item(delta_xy, 2, 0.0)
+    nrm = per_item(norm, 1, 1.0).reshape(B)
+    xin, uout = mft_coords(N, M, s, sh, de)                        # [B, 2, N], [B, 2, M] (axis 0 = x, 1 = y)
+    sgn = 1.0 if inverse else -1.0
+    two_pi_i = torch.tensor(complex(0.0, sgn * 2.0 * 3.141592653589793), dtype=torch.complex64, device=dev)
+    need_D = need[1] or need[3] or need[4]
+    if need_D:
+        # D_x: weight along columns (x axis), D_y: along rows (y axis); one batched transform
+        stacked = torch.cat([P * xin[:, 0, None, :], P * xin[:, 1, :, None]])
+        rep = lambda v: None if v is None else torch.cat([v, v])
+        D = mft_c64(stacked, rep(s), M, rep(sh), rep(de), rep(nrm), inverse, False, precision)
+        Dx, Dy = D[:B], D[B:]
+    inner = lambda a: (G.conj() * a).real.sum((-2, -1))            # Re <g, a> per item
+    idx = torch.arange(M, dtype=torch.float32, device=dev) - (M - 1) / 2
+
+    def shaped(v, like):
+        if like is None or not torch.is_tensor(like):
+            return None
+        if like.numel() == v.numel():
+            return v.reshape(like.shape)
+        if like.numel() * B == v.numel():                           # one value shared by the batch
+            return v.reshape(B, -1).sum(0).reshape(like.shape)
+        return v.sum().reshape(like.shape)
+
+    g_s = g_sh = g_de = g_no = None
+    if need[1]:
+        ax = idx[None, :] - sh[:, 0, None]                          # b~ (x, columns)
+        ay = idx[None, :] - sh[:, 1, None]                          # a~ (y, rows)
+        g_s = shaped(inner(two_pi_i * (ay[:, :, None] * Dy + ax[:, None, :] * Dx)), scale_out)
+    if need[4] and delta_xy is not None:
+        g_de = shaped(torch.stack([inner(-two_pi_i * Dx), inner(-two_pi_i * Dy)], -1), delta_xy)
+    if need[3] and shift_xy is not None:
+        gx = inner(two_pi_i * (-(uout[:, 0, None, :] / N) * O_ - s[:, None, None] * Dx))
+        gy = inner(two_pi_i * (-(uout[:, 1, :, None] / N) * O_ - s[:, None, None] * Dy))
+        g_sh = shaped(torch.stack([gx, gy], -1), shift_xy)
+    if need[5] and norm is not None:
+        g_no = shaped(inner(O_) / nrm, norm)
+    return g_s, g_sh, g_de, g_no
 
 
 # --------------------------------------------------------------------------- poly-PSF

@@ -21,10 +21,11 @@ from . import ops
 from .layers import (AberratedLayer, BasisLayer, BasisOptic, Normalise, Optic,
                      TransmissiveLayer)
 from .utils import propagation as _prop
+from .psfs import PSF
 from .wavefronts import Wavefront
 
-__all__ = ["BaseOpticalSystem", "LayeredOpticalSystem", "AngularOpticalSystem",
-           "CartesianOpticalSystem"]
+__all__ = ["BaseOpticalSystem", "OpticalSystem", "ParametricOpticalSystem", "LayeredOpticalSystem",
+           "ParametricLayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem"]
 
 
 def _np32(x):
@@ -34,11 +35,25 @@ def _np32(x):
 
 
 class BaseOpticalSystem:
+    """optical_systems.py:30-135: the abstract interface (propagate_mono / propagate / model)."""
+
     def propagate_mono(self, wavelength, offset=None, return_wf=False):  # pragma: no cover
         raise NotImplementedError
 
+    def propagate(self, wavelengths, offset=None, weights=None, return_wf=False, return_psf=False):  # pragma: no cover
+        raise NotImplementedError
+
+    def model(self, source, return_wf=False, return_psf=False):  # pragma: no cover
+        raise NotImplementedError
+
+
+class OpticalSystem(BaseOpticalSystem):
+    """optical_systems.py:138-231: polychromatic ``propagate`` and ``model``."""
+
     def propagate(self, wavelengths, offset=None, weights=None, return_wf=False, return_psf=False):
-        """optical_systems.py:147-223 (layer-by-layer route)."""
+        """optical_systems.py:147-223.  Returns the PSF array, or with ``return_wf`` the vectorised
+        ``Wavefront`` (phasor [L, M, M], sqrt(weight) applied, :213-220), or with ``return_psf`` a
+        ``PSF(psf, mean pixel scale)`` (:221-222)."""
         if return_wf and return_psf:
             raise ValueError(
                 "Cannot return both Wavefront and PSF objects. Choose one: "
@@ -69,8 +84,17 @@ class BaseOpticalSystem:
                                  and self._can_fuse()):
                 raise ValueError("differentiable wavelengths need the fused route (pupil-only layer stack)")
             off = offset if torch.is_tensor(offset) else _np32(offset)
-            return self.fused_propagate(wl_t, off.reshape(1, 2), weights.reshape(1, -1))
-        return self._propagate(wavelengths, offset, weights, return_wf)
+            psf = self.fused_propagate(wl_t, off.reshape(1, 2), weights.reshape(1, -1))
+            return PSF(psf, self._psf_pixel_scale_out(psf.device)) if return_psf else psf
+        out = self._propagate(wavelengths, offset, weights, return_wf)
+        if return_wf:
+            return out
+        return PSF(out, self._psf_pixel_scale_out(out.device)) if return_psf else out
+
+    def _psf_pixel_scale_out(self, device):
+        """``wf.pixel_scale.mean()`` of optical_systems.py:222 -- known without a wavefront for the
+        parametric systems; a generic layer stack propagates one wavelength's geometry to find it."""
+        raise NotImplementedError
 
     def _batchable(self):
         """True when every layer is one of this package's elementwise / MFT layers, which
@@ -91,14 +115,38 @@ class BaseOpticalSystem:
                 fields.append(wf.phasor * (w ** 0.5))
             fields = torch.stack(fields)
         if return_wf:
-            return fields
+            # the vectorised Wavefront that filter_vmap returns: every leaf gains the wavelength axis
+            L = fields.shape[0]
+            ps = wf.pixel_scale.reshape(-1)
+            ctr = wf.center.reshape(-1, 1) if wf.center.dim() > 1 else wf.center.reshape(1, 1)
+            return wf.set(phasor=fields, wavelength=torch.as_tensor(wavelengths, device=fields.device),
+                          pixel_scale=ps.expand(L).clone() if ps.numel() == 1 else ps,
+                          center=ctr.expand(L, 1).clone() if ctr.shape[0] == 1 else ctr)
+        self.__dict__["_last_pixel_scale"] = wf.pixel_scale.reshape(-1)[:1].mean()
         return (fields.real ** 2 + fields.imag ** 2).sum(0)
 
-    def model(self, source, return_wf=False, return_psf=False):   # optical_systems.py:225-260
+    def model(self, source, return_wf=False, return_psf=False):   # optical_systems.py:225-231
         return source.model(self, return_wf, return_psf)
 
 
-class LayeredOpticalSystem(BaseOpticalSystem):
+class ParametricOpticalSystem(OpticalSystem):
+    """optical_systems.py:234-292: a system with a parametrised output sampling."""
+
+    def _init_parametric(self, psf_npixels, psf_pixel_scale, oversample=1):
+        self.psf_npixels = int(psf_npixels)
+        self.oversample = int(oversample)
+        # a torch scalar (requires_grad) makes the pixel scale a fitted parameter of the fused route
+        self.psf_pixel_scale = (psf_pixel_scale if torch.is_tensor(psf_pixel_scale)
+                                else np.float32(psf_pixel_scale))
+
+    @property
+    def fov(self):                                      # :283-292
+        return self.psf_npixels * self.psf_pixel_scale
+
+
+class LayeredOpticalSystem(OpticalSystem):
+    """optical_systems.py:298-507."""
+
     def __init__(self, wf_npixels: int, diameter, layers, device=None, fused=True, precision=None):
         self.wf_npixels = int(wf_npixels)
         self.diameter = np.float32(diameter)
@@ -137,18 +185,40 @@ class LayeredOpticalSystem(BaseOpticalSystem):
             wf = layer(wf)
         return wf if return_wf else wf.psf
 
+    def _psf_pixel_scale_out(self, device):
+        ps = self.__dict__.get("_last_pixel_scale")
+        if ps is None:
+            raise ValueError("return_psf needs a propagated wavefront to read the pixel scale from")
+        return ps
 
-class _FocalSystem(LayeredOpticalSystem):
-    """Pupil-plane layers followed by one MFT to the focal plane."""
+    def insert_layer(self, layer, index: int):           # :465-491
+        items = list(self.layers.items())
+        items.insert(index, layer if isinstance(layer, tuple) else (type(layer).__name__, layer))
+        import copy
+        new = copy.copy(self)
+        new.layers = OrderedDict(items)
+        return new
+
+    def remove_layer(self, key: str):                    # :493-507
+        import copy
+        new = copy.copy(self)
+        new.layers = OrderedDict((k, v) for k, v in self.layers.items() if k != key)
+        return new
+
+
+class ParametricLayeredOpticalSystem(ParametricOpticalSystem, LayeredOpticalSystem):
+    """optical_systems.py:510-594: pupil-plane layers followed by one MFT ``to_focus`` whose output
+    sampling is parametrised (``psf_npixels``, ``psf_pixel_scale``, ``oversample``).  Subclasses
+    supply the unit conversion (``_focal_args``); this is the class the fused route hangs on."""
 
     def __init__(self, wf_npixels, diameter, layers, psf_npixels, psf_pixel_scale, oversample=1,
                  **kw):
-        super().__init__(wf_npixels, diameter, layers, **kw)
-        self.psf_npixels = int(psf_npixels)
-        self.oversample = int(oversample)
-        # a torch scalar (requires_grad) makes the pixel scale a fitted parameter of the fused route
-        self.psf_pixel_scale = (psf_pixel_scale if torch.is_tensor(psf_pixel_scale)
-                                else np.float32(psf_pixel_scale))
+        LayeredOpticalSystem.__init__(self, wf_npixels, diameter, layers, **kw)
+        self._init_parametric(psf_npixels, psf_pixel_scale, oversample)
+
+    def _psf_pixel_scale_out(self, device):
+        ps = self._focal_args()[1]
+        return ps.to(device) if torch.is_tensor(ps) else torch.as_tensor(np.float32(ps), device=device)
 
     # -- units --------------------------------------------------------------------
     def _focal_args(self):  # pragma: no cover - abstract
@@ -159,7 +229,7 @@ class _FocalSystem(LayeredOpticalSystem):
         return wavefront.propagate(npix, ps, fl, precision=self.precision)
 
     def propagate_mono(self, wavelength, offset=None, return_wf=False):   # :560-594
-        wf = super().propagate_mono(wavelength, offset, return_wf=True)
+        wf = LayeredOpticalSystem.propagate_mono(self, wavelength, offset, return_wf=True)
         wf = self.to_focus(wf)
         return wf if return_wf else wf.psf
 
@@ -313,7 +383,7 @@ class _FocalSystem(LayeredOpticalSystem):
         return super()._propagate(wavelengths, offset, weights, return_wf)
 
 
-class AngularOpticalSystem(_FocalSystem):
+class AngularOpticalSystem(ParametricLayeredOpticalSystem):
     """optical_systems.py:597-680: psf_pixel_scale in arcseconds."""
 
     def _focal_args(self):                              # :676-680
@@ -325,7 +395,7 @@ class AngularOpticalSystem(_FocalSystem):
                 None)
 
 
-class CartesianOpticalSystem(_FocalSystem):
+class CartesianOpticalSystem(ParametricLayeredOpticalSystem):
     """optical_systems.py:683-775: psf_pixel_scale in microns.  NOTE: the
     reference's ``to_focus`` (:771-775) does not forward ``focal_length`` to
     ``wavefront.propagate``; that behaviour is preserved, not fixed."""
@@ -341,3 +411,6 @@ class CartesianOpticalSystem(_FocalSystem):
             return (self.psf_npixels * self.oversample, p * np.float32(1e-6 / self.oversample), None)
         true_pixel_scale = np.float32(self.psf_pixel_scale / np.float32(self.oversample))
         return (self.psf_npixels * self.oversample, np.float32(1e-6 * true_pixel_scale), None)
+
+
+_FocalSystem = ParametricLayeredOpticalSystem     # former private name

@@ -223,8 +223,9 @@ class Wavefront:
         """wavefronts.py:729-772 -> dlu.MFT."""
         phasor = _prop.MFT(self.phasor, self.wavelength, self.pixel_scale, npixels, pixel_scale,
                            focal_length=focal_length, inverse=bool(inverse), precision=precision)
-        ps = torch.as_tensor(np.asarray(pixel_scale.detach().cpu() if torch.is_tensor(pixel_scale)
-                                        else pixel_scale, dtype=np.float32), device=phasor.device)
+        # a device tensor stays in the autograd graph: a later propagate reads it as pixel_scale_in
+        ps = pixel_scale.to(phasor.device, torch.float32) if torch.is_tensor(pixel_scale) else torch.as_tensor(
+            np.asarray(pixel_scale, dtype=np.float32), device=phasor.device)
         return self.set(phasor=phasor, pixel_scale=ps)
 
     def propagate_MFT(self, spec_out, focal_length=None, inverse=None, precision=None):

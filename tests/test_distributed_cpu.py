@@ -50,11 +50,19 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_sources, q):
+class _StubOptics:
+    """What an empty shard needs from the optics: the output size and the device."""
+    device = "cpu"
+
+    def _focal_args(self):
+        return 16, None, None
+
+
+def _worker(rank, world, port, n_sources, q, n_wavels=4):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     od = _optics()
-    wls = np.linspace(0.9e-6, 1.1e-6, 4).astype(np.float32)
+    wls = np.linspace(0.9e-6, 1.1e-6, n_wavels).astype(np.float32)
     rng = np.random.default_rng(1)
     pos = (rng.uniform(-1, 1, (n_sources, 2)) * 3e-7).astype(np.float32)
     flux = rng.uniform(0.5, 2.0, n_sources).astype(np.float32)
@@ -66,7 +74,7 @@ def _worker(rank, world, port, n_sources, q):
             out += O.propagate(od, w, p[s], np.asarray(w_sl[s]))
         return torch.as_tensor(out) * scale
 
-    psf = D.sharded_point_sources_model(None, wls, pos, flux, model_fn=model_fn)
+    psf = D.sharded_point_sources_model(_StubOptics(), wls, pos, flux, model_fn=model_fn)
     loss = (psf ** 2).sum()
     loss.backward()
     D.all_reduce_grads([scale])
@@ -75,13 +83,15 @@ def _worker(rank, world, port, n_sources, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_sources", [1, 3])
-def test_sharded_model_matches_single_process(n_sources):
+@pytest.mark.parametrize("n_sources,n_wavels", [(1, 4), (3, 4), (1, 1)])
+def test_sharded_model_matches_single_process(n_sources, n_wavels):
+    # (1, 1): more ranks than sources and than wavelengths -- one rank owns an EMPTY shard and must
+    # still join the all-reduce with zeros
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_sources, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_sources, q, n_wavels)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
@@ -89,7 +99,7 @@ def test_sharded_model_matches_single_process(n_sources):
         p.join(timeout=60)
         assert p.exitcode == 0
     od = _optics()
-    wls = np.linspace(0.9e-6, 1.1e-6, 4).astype(np.float32)
+    wls = np.linspace(0.9e-6, 1.1e-6, n_wavels).astype(np.float32)
     rng = np.random.default_rng(1)
     pos = (rng.uniform(-1, 1, (n_sources, 2)) * 3e-7).astype(np.float32)
     flux = rng.uniform(0.5, 2.0, n_sources).astype(np.float32)

@@ -168,7 +168,7 @@ def _optics_dict(N, M, nz, seed, oversample=1, pscale=0.05):
 
 def _system(od, dev, fused=True, prec=None):
     import dlux_b200 as dl
-    layer = dl.BasisOptic(od["basis"], od["transmission"], od["coefficients"], "opd", normalise=True,
+    layer = dl.BasisOptic(od["basis"], od["transmission"], od["coefficients"], normalise=True, effect="opd",
                           device=dev)
     return dl.AngularOpticalSystem(od["wf_npixels"], od["diameter"], [("aperture", layer)],
                                    od["psf_npixels"], od["psf_pixel_scale"], od["oversample"],
@@ -234,7 +234,7 @@ def test_phase_retrieval_gradient(dev, prec):
 
     coeffs = torch.as_tensor(od["coefficients"], device=dev).requires_grad_(True)
     wt = torch.as_tensor(w, device=dev).requires_grad_(True)
-    layer = dl.BasisOptic(od["basis"], od["transmission"], coeffs, "opd", normalise=True, device=dev)
+    layer = dl.BasisOptic(od["basis"], od["transmission"], coeffs, normalise=True, effect="opd", device=dev)
     sys_ = dl.AngularOpticalSystem(N, 1.0, [("aperture", layer)], M, 0.05, device=dev, precision=prec)
     psf = sys_.propagate(wls, off, wt)
     loss = (psf * torch.as_tensor(G, device=dev)).sum()
@@ -330,7 +330,7 @@ def test_layered_system_with_mft_layers_batched_route(dev):
     w = np.array([0.1, 0.2, 0.3, 0.4], np.float32)
     off = np.array([1.0e-7, 2.0e-7], np.float32)
     ps = O.arcsec2rad(np.float32(0.05))
-    mk_optic = lambda c: dl.BasisOptic(od["basis"], od["transmission"], c, "opd", normalise=True, device=dev)
+    mk_optic = lambda c: dl.BasisOptic(od["basis"], od["transmission"], c, normalise=True, effect="opd", device=dev)
     stop = torch.as_tensor((np.hypot(*np.mgrid[:N, :N] - (N - 1) / 2) <= 0.4 * N).astype(np.float32), device=dev)
     c = torch.as_tensor(od["coefficients"], device=dev).requires_grad_(True)
     layers = [("optic", mk_optic(c)), ("to_focal", dl.MFT(M, ps)),
@@ -442,7 +442,7 @@ def test_second_order_through_layer_route(dev):
     basis_d = torch.as_tensor(od["basis"], device=dev)
 
     def loss_gpu(c):
-        layer = dl.BasisOptic(basis_d, od["transmission"], c, "opd", normalise=True, device=dev)
+        layer = dl.BasisOptic(basis_d, od["transmission"], c, normalise=True, effect="opd", device=dev)
         sys_ = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, 0.05, device=dev, fused=False)
         psf = sys_.propagate(wls, None, w)
         return ((psf * 1e3 - torch.as_tensor(target.astype(np.float32), device=dev)) ** 2).sum()
@@ -532,7 +532,7 @@ def test_telescope_pipeline(dev):
     od = _optics_dict(N, M, 3, 51, oversample=4, pscale=0.2)
     wls = np.linspace(0.9e-6, 1.1e-6, 3).astype(np.float32)
     c = torch.as_tensor(od["coefficients"], device=dev).requires_grad_(True)
-    layer = dl.BasisOptic(od["basis"], od["transmission"], c, "opd", normalise=True, device=dev)
+    layer = dl.BasisOptic(od["basis"], od["transmission"], c, normalise=True, effect="opd", device=dev)
     optics = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, 0.2, 4, device=dev)
     sources = [("star", dl.PointSource(wls, np.array([1e-7, 0.0], np.float32), 5.0)),
                ("binary", dl.BinarySource(wls, None, 2.0, 8e-7, 0.3, 2.0))]
@@ -578,7 +578,7 @@ def test_pixel_scale_gradient(dev):
     fd = (loss64(p0 * (1 + eps)) - loss64(p0 * (1 - eps))) / (2 * eps * p0)
     for prec in PRECS:
         p = torch.tensor(p0, dtype=torch.float32, device=dev, requires_grad=True)
-        layer = dl.BasisOptic(od["basis"], od["transmission"], od["coefficients"], "opd", normalise=True,
+        layer = dl.BasisOptic(od["basis"], od["transmission"], od["coefficients"], normalise=True, effect="opd",
                               device=dev)
         sys_ = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, p, device=dev, precision=prec)
         psf = sys_.propagate(wls, off, w)
@@ -615,7 +615,7 @@ def test_wavelength_gradient(dev):
         dn_[l] -= h
         fd[l] = (loss64(up_) - loss64(dn_)) / (2 * h)
     wl = torch.tensor(wls0, dtype=torch.float32, device=dev, requires_grad=True)
-    layer = dl.BasisOptic(od["basis"], od["transmission"], od["coefficients"], "opd", normalise=True, device=dev)
+    layer = dl.BasisOptic(od["basis"], od["transmission"], od["coefficients"], normalise=True, effect="opd", device=dev)
     sys_ = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, 0.05, device=dev)
     psf = sys_.propagate(wl, off, w)
     (psf * torch.as_tensor(G.astype(np.float32), device=dev)).sum().backward()
@@ -663,7 +663,7 @@ def test_multi_chunk_paths(dev):
         pos = np.array([[1e-7, -2e-7], [-3e-7, 0.5e-7], [0, 0]], np.float32)
         flux = np.array([3.0, 0.25, 1.0], np.float32)
         c = torch.as_tensor(od['coefficients'], device=dev).requires_grad_(True)
-        layer = dl.BasisOptic(od['basis'], od['transmission'], c, 'opd', normalise=True, device=dev)
+        layer = dl.BasisOptic(od['basis'], od['transmission'], c, normalise=True, effect="opd", device=dev)
         s = dl.AngularOpticalSystem(64, 1.0, [('a', layer)], 32, 0.05, device=dev)
         psf = s.model(dl.PointSources(wls, pos, flux))
         psf.sum().backward()

@@ -10,7 +10,7 @@ for name in ("c1", "c2"):
     N, M = cfg["wf_npixels"], cfg["psf_npixels"] * cfg["oversample"]
     c = torch.as_tensor(cfg["coefficients"], device=dev).requires_grad_(True)
     layer = dl.BasisOptic(torch.as_tensor(cfg["basis"], device=dev), torch.as_tensor(cfg["transmission"], device=dev),
-                          c, "opd", normalise=True, device=dev)
+                          c, normalise=True, effect="opd", device=dev)
     optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("p", layer)], cfg["psf_npixels"], cfg["psf_pixel_scale"],
                                      cfg["oversample"], device=dev)
     G = torch.as_tensor(cfg["G"], device=dev)

@@ -20,7 +20,7 @@ wls = np.linspace(530e-9, 640e-9, L).astype(np.float32)
 coeffs = torch.zeros(nz, device=dev, requires_grad=True)
 pos = torch.as_tensor((rng.uniform(-1, 1, (S, 2)) * 2e-6).astype(np.float32), device=dev).requires_grad_(True)
 flux = torch.as_tensor(rng.uniform(0.5, 2.0, S).astype(np.float32), device=dev).requires_grad_(True)
-layer = dl.BasisOptic(basis, T, coeffs, "opd", normalise=True, device=dev)
+layer = dl.BasisOptic(basis, T, coeffs, normalise=True, effect="opd", device=dev)
 layer2 = dl.Optic(None, opd0, None, device=dev)
 optics = dl.AngularOpticalSystem(N, 0.125, [("mask", layer2), ("aber", layer)], M, 0.375, device=dev)
 G = torch.as_tensor(rng.standard_normal((M, M)).astype(np.float32), device=dev)

@@ -14,7 +14,7 @@ wls = np.linspace(0.9e-6, 1.1e-6, L).astype(np.float32)
 w = np.full(L, 1.0 / L, np.float32)
 pert = torch.as_tensor(rng.standard_normal((B, nz)).astype(np.float32), device=dev)
 G = torch.as_tensor(rng.standard_normal((M, M)).astype(np.float32), device=dev)
-layer = dl.BasisOptic(basis, T, pert[0], "opd", normalise=True, device=dev)
+layer = dl.BasisOptic(basis, T, pert[0], normalise=True, effect="opd", device=dev)
 optics = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, 0.05, device=dev)
 def sweep():
     grads = torch.empty((B, nz), device=dev)

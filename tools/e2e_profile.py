@@ -11,7 +11,7 @@ N, M = cfg["wf_npixels"], cfg["psf_npixels"] * cfg["oversample"]
 basis_d = torch.as_tensor(cfg["basis"], device=dev); T_d = torch.as_tensor(cfg["transmission"], device=dev)
 coeffs_h = torch.as_tensor(cfg["coefficients"]).pin_memory(); G_h = torch.as_tensor(cfg["G"]).pin_memory()
 psf_h = torch.empty((M, M)).pin_memory(); grad_h = torch.empty(len(cfg["coefficients"])).pin_memory()
-layer = dl.BasisOptic(basis_d, T_d, torch.as_tensor(cfg["coefficients"], device=dev), "opd", normalise=True, device=dev)
+layer = dl.BasisOptic(basis_d, T_d, torch.as_tensor(cfg["coefficients"], device=dev), normalise=True, effect="opd", device=dev)
 optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("pupil", layer)], cfg["psf_npixels"], cfg["psf_pixel_scale"], cfg["oversample"], device=dev)
 def step(sync=True):
     c = coeffs_h.to(dev, non_blocking=True).requires_grad_(True)

@@ -7,7 +7,7 @@ dev = torch.device("cuda:0")
 cfg = workloads.config("c2")
 N = cfg["wf_npixels"]
 c = torch.as_tensor(cfg["coefficients"], device=dev).requires_grad_(True)
-layer = dl.BasisOptic(torch.as_tensor(cfg["basis"], device=dev), torch.as_tensor(cfg["transmission"], device=dev), c, "opd", normalise=True, device=dev)
+layer = dl.BasisOptic(torch.as_tensor(cfg["basis"], device=dev), torch.as_tensor(cfg["transmission"], device=dev), c, normalise=True, effect="opd", device=dev)
 optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("p", layer)], cfg["psf_npixels"], cfg["psf_pixel_scale"], cfg["oversample"], device=dev)
 G = torch.as_tensor(cfg["G"], device=dev)
 src = dl.PointSource(cfg["wavelengths"], cfg["positions"][0], 1.0, cfg["weights"])

@@ -11,7 +11,7 @@ ref = O.MFT(x[1], 1.1e-6, 1/130, 71, 2e-7)
 print('mft err', np.linalg.norm(out[1].cpu().numpy()-ref)/np.linalg.norm(ref))
 od = _optics_dict(96, 48, 3, 1)
 c = torch.as_tensor(od['coefficients'], device=dev).requires_grad_(True)
-layer = dl.BasisOptic(od['basis'], od['transmission'], c, 'opd', normalise=True, device=dev)
+layer = dl.BasisOptic(od['basis'], od['transmission'], c, normalise=True, effect="opd", device=dev)
 s = dl.AngularOpticalSystem(96, 1.0, [('a', layer)], 48, 0.05, device=dev)
 pos = torch.as_tensor(np.array([[1e-7, -2e-7], [0, 0]], np.float32), device=dev).requires_grad_(True)
 psf = s.model(dl.PointSources(np.linspace(0.9e-6, 1.1e-6, 3).astype(np.float32), pos, np.array([1.0, 2.0], np.float32)))

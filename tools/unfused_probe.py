@@ -10,7 +10,7 @@ basis_d = torch.as_tensor(cfg["basis"], device=dev); T_d = torch.as_tensor(cfg["
 G = torch.as_tensor(cfg["G"], device=dev)
 for fused in (True, False):
     c = torch.as_tensor(cfg["coefficients"], device=dev).requires_grad_(True)
-    layer = dl.BasisOptic(basis_d, T_d, c, "opd", normalise=True, device=dev)
+    layer = dl.BasisOptic(basis_d, T_d, c, normalise=True, effect="opd", device=dev)
     optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("p", layer)], cfg["psf_npixels"], cfg["psf_pixel_scale"],
                                      cfg["oversample"], device=dev, fused=fused)
     def step():
