@@ -38,6 +38,7 @@ SIGNATURES = {
     "dlux_launch_count": (C.c_uint64, []),
     "dlux_profile_enable": (C.c_int, [C.c_int]),
     "dlux_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "dlux_tc_peak_probe": (C.c_int, [C.c_int32, C.c_int32, _P, C.POINTER(C.c_double), _P]),
     "dlux_mft_scratch_bytes": (C.c_size_t, [C.POINTER(MftDesc)]),
     "dlux_mft_c64": (C.c_int, [C.POINTER(MftDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "dlux_mft_coords": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
@@ -91,3 +92,11 @@ def profile_read():
     ms, n, fl = C.c_double(), C.c_uint64(), C.c_double()
     load().dlux_profile_read(C.byref(ms), C.byref(n), C.byref(fl))
     return ms.value, int(n.value), fl.value
+
+
+def tc_peak_probe(kind: int, n_batches: int, stream, sink=None) -> float:
+    """Enqueue the MMA-only tensor-pipe probe (kind 0 tf32, 1 bf16, 2 the GEMM's mix) on `stream`;
+    returns the real FLOPs the launch executes."""
+    fl = C.c_double()
+    check(load().dlux_tc_peak_probe(kind, n_batches, sink, C.byref(fl), stream), "dlux_tc_peak_probe")
+    return fl.value

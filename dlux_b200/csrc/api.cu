@@ -239,6 +239,10 @@ int dlux_profile_read(double* gemm_ms, uint64_t* gemm_launches, double* gemm_flo
   return DLUX_OK;
 }
 
+int dlux_tc_peak_probe(int32_t kind, int32_t n_batches, float* sink, double* flops_host, void* cuda_stream) {
+  return launch_tc_peak_probe(kind, n_batches, sink, flops_host, (cudaStream_t)cuda_stream);
+}
+
 size_t dlux_mft_scratch_bytes(const dlux_mft_desc* desc) {
   if (check_mft_desc(desc) != DLUX_OK) return 0;
   MftScratch s;

@@ -164,6 +164,7 @@ void note_cuda_error(int code);   // remembered for dlux_last_cuda_error()
 int launch_gemm_simt(const GemmParams& p, cudaStream_t st);
 int launch_gemm_tc(const GemmParams& p, cudaStream_t st);
 size_t gemm_tc_workspace_bytes();
+int launch_tc_peak_probe(int kind, int n_batches, float* sink, double* flops, cudaStream_t st);
 
 int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const float* shift_xy,
                   const float* delta_xy, int delta_stride_items, float* xin, float* uout,

@@ -901,6 +901,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   }
 }
 
+
+// ------------------------------------------------------------------ tensor-pipe peak probe
+// MMA-only microbenchmark of the instruction shapes gemm_tc_kernel issues: CTA pairs
+// (cta_group::2), M256 x N128, A operand resident in tensor memory, B operand resident in
+// shared memory -- no TMA, no generators, no epilogue.  One elected thread of every leader CTA
+// issues batches of 32 MMAs back to back and keeps two batches in flight.  bench.py times it
+// with CUDA events to MEASURE the dense tf32 / bf16 tcgen05 rate the roofline is quoted
+// against (profiles/tf32_peak.json).  kind: 0 = kind::tf32 (K = 8), 1 = kind::f16 bf16
+// (K = 16), 2 = the kernel's own mix (4 tf32 + 4 bf16 per 16-k chunk and tile).
+constexpr int PROBE_THREADS = 128;
+constexpr int PROBE_BATCH = 32;
+constexpr int PROBE_SMEM = 2 * PLANE_BYTES + 4 * BPLANE_BYTES + 1024 + 64;
+
+__global__ void __launch_bounds__(PROBE_THREADS, 1)
+tc_peak_probe_kernel(int kind, int n_batches, float* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + 2 * PLANE_BYTES + 4 * BPLANE_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 2 * PLANE_BYTES + 4 * BPLANE_BYTES + 32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // operand bits: pseudo-random finite values (idle-zero operands would understate the power draw)
+  uint32_t h = (uint32_t)(blockIdx.x * PROBE_THREADS + threadIdx.x) * 2654435761u + 12345u;
+  for (int i = threadIdx.x; i < (2 * PLANE_BYTES) / 4; i += PROBE_THREADS) {
+    h = h * 1664525u + 1013904223u;
+    reinterpret_cast<float*>(gen)[i] = tf32_hi(((float)(h >> 8) * (1.0f / 8388608.0f)) - 1.0f);
+  }
+  for (int i = threadIdx.x; i < (4 * BPLANE_BYTES) / 4; i += PROBE_THREADS) {
+    h = h * 1664525u + 1013904223u;
+    const float a = ((float)(h >> 8) * (1.0f / 8388608.0f)) - 1.0f;
+    reinterpret_cast<uint32_t*>(gen + 2 * PLANE_BYTES)[i] = pack_bf16(a, -a * 0.5f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(bar_base, 1);
+    mbar_init(bar_base + 8, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // phasor-like A operand: every warp fills its lane quarter of the two phasor stages
+  {
+    const uint32_t la = tmem_base + ((uint32_t)(warp * 32) << 16) + G_BASE_COL;
+    for (int c = 0; c < G_STAGES * G_COLS; c += 8) {
+      float v[8];
+      const bool packed = (c % G_COLS) >= GB_BASE;   // the bf16 planes of a stage hold packed pairs
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        h = h * 1664525u + 1013904223u;
+        const float a = ((float)(h >> 8) * (1.0f / 8388608.0f)) - 1.0f;
+        v[j] = packed ? __uint_as_float(pack_bf16(a, 0.25f - a)) : tf32_hi(a);
+      }
+      tmem_st8(la + c, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (cluster_ctarank() == 0 && warp == 1) {
+    const uint64_t d_rh = make_desc_sw64(base), d_ih = make_desc_sw64(base + PLANE_BYTES);
+    const uint64_t b0 = make_desc_sw32(base + 2 * PLANE_BYTES), b1 = make_desc_sw32(base + 2 * PLANE_BYTES + BPLANE_BYTES);
+    const uint64_t b2 = make_desc_sw32(base + 2 * PLANE_BYTES + 2 * BPLANE_BYTES);
+    const uint64_t b3 = make_desc_sw32(base + 2 * PLANE_BYTES + 3 * BPLANE_BYTES);
+    constexpr uint64_t KS = (UMMA_K * 4) >> 4;
+    uint32_t ph[2] = {0, 0};
+    for (int b = 0; b < n_batches; ++b) {
+      const int slot = b & 1;
+      if (b >= 2) { mbar_wait(bar_base + 8 * slot, ph[slot]); ph[slot] ^= 1; }
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int m = 0; m < PROBE_BATCH; m += 8) {
+          const uint32_t d = tmem_base + (uint32_t)(((b * (PROBE_BATCH / 8) + m / 8) % NUM_ACC) * ACC_COLS);
+          const uint32_t g0 = tmem_base + (uint32_t)(G_BASE_COL + ((m / 8) & 1) * G_COLS);
+          const uint32_t gb = g0 + GB_BASE;
+          if (kind == 0) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                umma_tf32_ts2(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);
+                umma_tf32_ts2(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);
+              }
+          } else if (kind == 1) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              umma_bf16_ts2(d, gb + 1 * GB_COLS, b0, IDESC_BF16, 1u);
+              umma_bf16_ts2(d, gb + 0 * GB_COLS, b1, IDESC_BF16, 1u);
+              umma_bf16_ts2(d, gb + 3 * GB_COLS, b2, IDESC_BF16, 1u);
+              umma_bf16_ts2(d, gb + 2 * GB_COLS, b3, IDESC_BF16, 1u);
+            }
+          } else {
+            issue_tile_chunk(d, g0, base, false);
+          }
+        }
+        umma_commit_mc2(bar_base + 8 * slot, (uint16_t)1);   // arrives on the leader's barrier
+      }
+      __syncwarp();
+    }
+    for (int b = n_batches > 2 ? n_batches - 2 : 0; b < n_batches; ++b) {   // drain the last two batches
+      const int slot = b & 1;
+      mbar_wait(bar_base + 8 * slot, ph[slot]);
+      ph[slot] ^= 1;
+    }
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (sink && blockIdx.x == 0 && warp == 0) {   // read one accumulator word so the work is observable
+    uint32_t v[16];
+    tmem_ld16(tmem_base, v);
+    tmem_ld_wait();
+    if (lane == 0) sink[0] = __uint_as_float(v[0]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -1049,6 +1182,45 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   }
   note_launch();
   return check_launch("gemm_tc");
+}
+
+
+// Launches the MMA-only probe; returns the real FLOPs it executes (0 on error) through *flops.
+int launch_tc_peak_probe(int kind, int n_batches, float* sink, double* flops, cudaStream_t st) {
+  TcState& s = tc_state();
+  if (s.rc != DLUX_OK) return s.rc;
+  if (kind < 0 || kind > 2 || n_batches < 1) return DLUX_ERR_ARG;
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once[dev & 63], [&] {
+    attr_rc = cudaFuncSetAttribute(tc_peak_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PROBE_SMEM);
+  });
+  if (attr_rc != cudaSuccess) return DLUX_ERR_CUDA;
+  const int n_clusters = s.num_sms / CLUSTER;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_clusters * CLUSTER);
+  cfg.blockDim = dim3(PROBE_THREADS);
+  cfg.dynamicSmemBytes = PROBE_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_peak_probe_kernel, kind, n_batches, sink);
+  if (e != cudaSuccess) {
+    note_cuda_error((int)e);
+    return DLUX_ERR_CUDA;
+  }
+  // per MMA: 2 * M(256) * N(128) * K real FLOPs; K = 8 (tf32) or 16 (bf16); the mix is half and half
+  const double per_mma = 2.0 * UMMA_M * BM * (kind == 0 ? 8.0 : kind == 1 ? 16.0 : 12.0);
+  if (flops) *flops = per_mma * PROBE_BATCH * (double)n_batches * n_clusters;
+  note_launch();
+  return check_launch("tc_peak_probe");
 }
 
 }  // namespace dlux

@@ -67,6 +67,14 @@ DLUX_API uint64_t dlux_launch_count(void);
 DLUX_API int dlux_profile_enable(int on);
 DLUX_API int dlux_profile_read(double* gemm_ms, uint64_t* gemm_launches, double* gemm_flops);
 
+/* Measurement aid (no reference counterpart): an MMA-only tcgen05 microbenchmark of the instruction
+ * shapes the phasor GEMM issues (cta_group::2, M256 x N128, A in tensor memory, B in shared memory,
+ * operands resident).  kind 0: kind::tf32 (K=8), 1: kind::f16 bf16 (K=16), 2: the GEMM's own mix.
+ * Each leader CTA issues n_batches x 32 MMAs; *flops_host receives the real FLOPs of the launch.
+ * bench.py times it with CUDA events to measure the tensor-pipe peak the roofline is quoted against. */
+DLUX_API int dlux_tc_peak_probe(int32_t kind, int32_t n_batches, float* sink /* 1 float, or NULL */,
+                       double* flops_host, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------
  * dlux_mft_c64: batched matrix Fourier transform.
  * Replaces dLux.utils.propagation.MFT (src/dLux/utils/propagation.py:178-256)

@@ -23,3 +23,13 @@ def rel_l2(a, b):
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_propagation.npz"))
+
+
+def check(name, err, tol):
+    """Assert err < tol and print the measured figure (pytest -s) so that tolerances can be audited."""
+    print(f"PARITY {name}: {err:.3e} (tol {tol:.0e})")
+    assert err < tol, (name, err, tol)
+
+
+def rel_scalar(a, b):
+    return abs(float(a) - float(b)) / max(abs(float(b)), 1e-300)
