@@ -24,6 +24,7 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+            name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
             cur = re.sub(r"\(.*", "", name).split("::")[-1]
             kernels[cur] = Counter()
             continue
