@@ -67,25 +67,21 @@ static std::atomic<int> g_prof_on{0};
 static PlaneSet take_planes(Bump& b, size_t n_rows, int cols) {
   PlaneSet ps;
   for (int i = 0; i < 2; ++i) ps.hi[i] = b.take<float>(n_rows * pitch4(cols));
-  for (int i = 0; i < 4; ++i) ps.b[i] = b.take<__nv_bfloat16>(n_rows * pitch8(cols));
   return ps;
 }
 static size_t plane_bytes(size_t n_rows, int cols) {
-  return n_rows * (8 * (size_t)pitch4(cols) + 8 * (size_t)pitch8(cols));
+  return n_rows * 8 * (size_t)pitch4(cols);
 }
 // the stage-1 output of the forward ([M][N]) and of the adjoint ([N][M]) share one buffer,
 // sized for the larger, and are indexed with their own pitches
 static PlaneSet take_mid_planes(Bump& b, size_t c, int N, int M) {
   PlaneSet ps;
   const size_t f4 = std::max((size_t)M * pitch4(N), (size_t)N * pitch4(M));
-  const size_t f8 = std::max((size_t)M * pitch8(N), (size_t)N * pitch8(M));
   for (int i = 0; i < 2; ++i) ps.hi[i] = b.take<float>(c * f4);
-  for (int i = 0; i < 4; ++i) ps.b[i] = b.take<__nv_bfloat16>(c * f8);
   return ps;
 }
 static size_t mid_bytes(int N, int M) {
-  return 8 * std::max((size_t)M * pitch4(N), (size_t)N * pitch4(M)) +
-         8 * std::max((size_t)M * pitch8(N), (size_t)N * pitch8(M));
+  return 8 * std::max((size_t)M * pitch4(N), (size_t)N * pitch4(M));
 }
 
 static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
@@ -287,15 +283,13 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
     rc = launch_coords(N, M, c, scale_out + b0, shift_xy ? shift_xy + 2 * (size_t)b0 : nullptr,
                        delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr, 1, s.xin, s.uout, st);
     if (rc) return rc;
-    const int exact = d->precision == DLUX_PREC_FP32;
     rc = launch_split_c64((const float2*)in + (size_t)b0 * n_src * n_src, (size_t)c * n_src, (int)n_src,
-                          s.in_pl, exact, st);
+                          s.in_pl, st);
     if (rc) return rc;
     GemmParams g{};
     fill_stage(g, adj, 0, N, M, c, s.xin, s.uout, sign2pi);
     g.a = s.in_pl;
     g.out = s.mid_pl;
-    g.exact = exact;
     g.mode = EPI_PLANES;
     g.scale = nullptr;
     rc = run_gemm(g, d->precision, st);
@@ -303,7 +297,6 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
     GemmParams h{};
     fill_stage(h, adj, 1, N, M, c, s.xin, s.uout, sign2pi);
     h.a = s.mid_pl;
-    h.exact = exact;
     h.mode = EPI_C64;
     h.scale = norm ? norm + b0 : nullptr;
     h.out_c64 = (float2*)out + (size_t)b0 * n_dst * n_dst;
@@ -382,8 +375,7 @@ static int poly_prologue(const dlux_polypsf_desc* d, const PolyScratch& s, const
   int rc = launch_power(N, T, d->normalise, s.amp_scale, st);
   if (rc) return rc;
   if (need_planes) {
-    rc = launch_pupil(N, L, T, opd, phase, wavenumber, s.amp_scale, s.p_pl,
-                      d->precision == DLUX_PREC_FP32, st);
+    rc = launch_pupil(N, L, T, opd, phase, wavenumber, s.amp_scale, s.p_pl, st);
     if (rc) return rc;
   }
   expand_items_kernel<<<(items + 255) / 256 > 1024 ? 1024 : (items + 255) / 256, 256, 0, st>>>(
@@ -411,7 +403,6 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
   rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, true, st);
   if (rc) return rc;
   const float sign2pi = (float)(-2.0 * 3.14159265358979323846);
-  const int exact = d->precision == DLUX_PREC_FP32;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
     rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
@@ -423,14 +414,12 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
     g.n_data = L;
     g.a = s.p_pl;
     g.out = s.mid_pl;
-    g.exact = exact;
     g.mode = EPI_PLANES;
     rc = run_gemm(g, d->precision, st);
     if (rc) return rc;
     GemmParams h{};
     fill_stage(h, false, 1, N, M, c, s.xin, s.uout, sign2pi);
     h.a = s.mid_pl;
-    h.exact = exact;
     h.mode = EPI_C64;
     h.scale = s.norm_item + b0;
     h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * M * M : s.fbuf;
@@ -471,7 +460,6 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   const bool need_pupil_grad =
       opd_bar || phase_bar || delta_bar || transmission_bar || scale_bar || wavenumber_bar;
   const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
-  const int exact = d->precision == DLUX_PREC_FP32;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
     // pass 0: Q = adjoint(Ebar) -> opd / phase / transmission / offset gradients.  Passes 1, 2
@@ -481,7 +469,7 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     const int n_pass = scale_bar ? 3 : 1;
     for (int pass = 0; pass < n_pass; ++pass) {
       rc = launch_cotangent(M, c, (const float2*)field + (size_t)b0 * M * M, psf_bar, weights + b0,
-                            s.ebar_pl, exact, (pass == 0 && weights_bar) ? weights_bar + b0 : nullptr,
+                            s.ebar_pl, (pass == 0 && weights_bar) ? weights_bar + b0 : nullptr,
                             pass - 1, st);
       if (rc) return rc;
       if (!need_pupil_grad) continue;
@@ -494,15 +482,13 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
       fill_stage(g, true, 0, N, M, c, s.xin, s.uout, sign2pi);
       g.a = s.ebar_pl;
       g.out = s.mid_pl;
-      g.exact = exact;
-      g.mode = EPI_PLANES;
+        g.mode = EPI_PLANES;
       rc = run_gemm(g, d->precision, st);
       if (rc) return rc;
       GemmParams h{};
       fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
       h.a = s.mid_pl;
-      h.exact = exact;
-      h.mode = EPI_C64;
+        h.mode = EPI_C64;
       h.scale = s.norm_item + b0;
       h.out_c64 = s.qbuf;
       rc = run_gemm(h, d->precision, st);

@@ -23,24 +23,24 @@ enum EpilogueMode : int {
   EPI_C64 = 1      // out_c64[item][n][m]
 };
 
-// Split representation of a complex matrix Z[n][rows][K], 16 bytes per element:
-//   hi[0], hi[1] : float32 planes [n][rows][pitch4(K)]  = tf32(Re Z), tf32(Im Z)  (rna)
-//   b[0..3]      : bfloat16 planes [n][rows][pitch8(K)] = bf16(hi_re), bf16(Re Z - hi_re),
-//                                                         bf16(hi_im), bf16(Im Z - hi_im)
-// The tensor kernel forms  z*g = hi*g_hi (tf32 MMA) + hi*g_lo + lo*g_hi (bf16 MMAs): the
-// correction terms are 2^-11 of the product, so bf16's 2^-9 leaves ~2^-20 (measured 5.6e-7
-// relative per contraction; tf32 corrections gave 6.6e-8) at 2/3 of the tensor work.
-// In `exact` mode (DLUX_PREC_FP32) hi[] hold the unrounded float32 values and b[] is unused.
+// Planar representation of a complex matrix Z[n][rows][K], 8 bytes per element: two float32 planes
+//   hi[0] = Re Z, hi[1] = Im Z      [n][rows][pitch4(K)]
+// (row pitches are multiples of 16 bytes, as TMA requires).  The values are UNSPLIT float32.
+// The tensor kernel splits them on chip: after a tile-chunk lands in shared memory, converter warps
+// round each value to tf32 ("hi", written back in place for the kind::tf32 MMA) and derive
+// bf16(hi) and bf16(z - hi) planes for the two bf16 correction MMAs,
+//   z*g = hi*g_hi (tf32) + hi*g_lo + lo*g_hi (bf16):
+// the correction terms are 2^-11 of the product, so bf16's 2^-9 leaves ~2^-20 (measured 5.6e-7
+// relative per contraction) at 2/3 of the tensor work of 3xTF32.  Round 1 kept the six split planes
+// in HBM (16 bytes per element); splitting on chip halves every operand's traffic and the
+// intermediate's epilogue.
 struct PlaneSet {
   float* hi[2];
-  __nv_bfloat16* b[4];
 };
 __host__ __device__ inline int pitch4(int k) { return (k + 3) & ~3; }
-__host__ __device__ inline int pitch8(int k) { return (k + 7) & ~7; }
 
 struct GemmParams {
   PlaneSet a;   // data operand, [n_data][rows][K]
-  int exact;    // planes hold unsplit float32 (CUDA-core path)
   int n_data;   // number of data matrices in `a`
   int rows;    // M dimension of the data matrix (rows m)
   int K;       // contraction length
@@ -53,7 +53,7 @@ struct GemmParams {
   float sign2pi;         // float32(-2*pi) forward, float32(+2*pi) inverse / adjoint-of-forward
   const float* scale;    // [n_items] or nullptr
   int mode;
-  PlaneSet out;          // EPI_PLANES: [n_items][n_out][rows] (pitch4 / pitch8 of rows)
+  PlaneSet out;          // EPI_PLANES: [n_items][n_out][rows] (pitch4 of rows)
   float2* out_c64;       // EPI_C64: [n_items][n_out][rows]
 };
 
@@ -123,21 +123,10 @@ __device__ __forceinline__ void fast_sincos_mufu(float a, int qshift, float* sn,
   *cs = __uint_as_float(co ^ (((q + 1u) & 2u) << 30));   // negate in quadrants 1, 2
 }
 
-// (re, im) -> the six operand planes at element offsets o4 (float32 pitch) / o8 (bf16 pitch)
-__device__ __forceinline__ void plane_store(const PlaneSet& ps, size_t o4, size_t o8, float re, float im,
-                                            int exact) {
-  if (exact) {
-    ps.hi[0][o4] = re;
-    ps.hi[1][o4] = im;
-    return;
-  }
-  const float rh = tf32_hi(re), ih = tf32_hi(im);
-  ps.hi[0][o4] = rh;
-  ps.hi[1][o4] = ih;
-  ps.b[0][o8] = __float2bfloat16_rn(rh);
-  ps.b[1][o8] = __float2bfloat16_rn(re - rh);
-  ps.b[2][o8] = __float2bfloat16_rn(ih);
-  ps.b[3][o8] = __float2bfloat16_rn(im - ih);
+// (re, im) -> the two operand planes at element offset o4
+__device__ __forceinline__ void plane_store(const PlaneSet& ps, size_t o4, float re, float im) {
+  ps.hi[0][o4] = re;
+  ps.hi[1][o4] = im;
 }
 
 // Shared epilogue for one output element D[m][n] = (re, im) of `item`.
@@ -149,7 +138,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
   const size_t idx = ((size_t)item * p.n_out + n) * p.rows + m;
   if (p.mode == EPI_PLANES) {
     const size_t row = (size_t)item * p.n_out + n;
-    plane_store(p.out, row * pitch4(p.rows) + m, row * pitch8(p.rows) + m, re, im, p.exact);
+    plane_store(p.out, row * pitch4(p.rows) + m, re, im);
   } else {  // EPI_C64
     p.out_c64[idx] = make_float2(re, im);
   }
@@ -170,17 +159,15 @@ int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const 
                   const float* delta_xy, int delta_stride_items, float* xin, float* uout,
                   cudaStream_t st);
 // in: [n_mat][rows][cols] c64 -> split planes
-int launch_split_c64(const float2* in, size_t n_mat_rows, int cols, const PlaneSet& out, int exact,
-                     cudaStream_t st);
+int launch_split_c64(const float2* in, size_t n_mat_rows, int cols, const PlaneSet& out, cudaStream_t st);
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
                  const float* wavenumber, const float* amp_scale /*device scalar*/,
-                 const PlaneSet& out, int exact, cudaStream_t st);
+                 const PlaneSet& out, cudaStream_t st);
 int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStream_t st);
 // `weight_axis`: -1 none; 0 / 1: multiply by the output-pixel index (col / row) minus (M-1)/2,
 // the derivative of the output coordinate w.r.t. scale_out
 int launch_cotangent(int M, int n_items, const float2* field, const float* psf_bar,
-                     const float* w, const PlaneSet& out, int exact, float* w_bar, int weight_axis,
-                     cudaStream_t st);
+                     const float* w, const PlaneSet& out, float* w_bar, int weight_axis, cudaStream_t st);
 int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coeffs,
                       const float* base, float* out, cudaStream_t st);
 int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,

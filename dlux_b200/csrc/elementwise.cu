@@ -68,24 +68,22 @@ int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const 
 }
 
 // ---------------------------------------------------------------------------
-// complex64 interleaved -> split operand planes (PlaneSet)
-__global__ void split_c64_kernel(const float2* __restrict__ in, size_t n_rows, int cols, PlaneSet out,
-                                 int exact) {
+// complex64 interleaved -> planar operand (PlaneSet)
+__global__ void split_c64_kernel(const float2* __restrict__ in, size_t n_rows, int cols, PlaneSet out) {
   const size_t n = n_rows * (size_t)cols;
-  const int p4 = pitch4(cols), p8 = pitch8(cols);
+  const int p4 = pitch4(cols);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / cols;
     const size_t c = i - r * cols;
     const float2 v = in[i];
-    plane_store(out, r * p4 + c, r * p8 + c, v.x, v.y, exact);
+    plane_store(out, r * p4 + c, v.x, v.y);
   }
 }
 
-int launch_split_c64(const float2* in, size_t n_rows, int cols, const PlaneSet& out, int exact,
-                     cudaStream_t st) {
+int launch_split_c64(const float2* in, size_t n_rows, int cols, const PlaneSet& out, cudaStream_t st) {
   if (n_rows == 0) return DLUX_OK;
-  split_c64_kernel<<<grid_for(n_rows * cols, 256), 256, 0, st>>>(in, n_rows, cols, out, exact);
+  split_c64_kernel<<<grid_for(n_rows * cols, 256), 256, 0, st>>>(in, n_rows, cols, out);
   note_launch();
   return check_launch("split_c64");
 }
@@ -139,89 +137,70 @@ int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStr
 }
 
 // ---------------------------------------------------------------------------
-// pupil phasor P_l = (1/N^2) T exp(i k_l opd) exp(i phase) * amp_scale, split to planes
-// (wavefronts.py:111-113, 349, 368; layers/optics.py:91-96)
+// pupil phasor P_l = (1/N^2) T exp(i k_l opd) exp(i phase) * amp_scale as planar float32
+// (wavefronts.py:111-113, 349, 368; layers/optics.py:91-96).  One thread = 4 consecutive pixels of one
+// row for ALL wavelengths: T / opd / phase are read once and the L planes leave as 16-byte stores.
 __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const float* __restrict__ opd,
                              const float* __restrict__ phase, const float* __restrict__ wavenumber,
-                             const float* __restrict__ amp_scale, PlaneSet out, int exact) {
-  // one thread = 4 consecutive pixels of one row: 16-byte stores to the float32 planes,
-  // 8-byte stores to the bf16 planes
-  const int p4 = pitch4(N), p8 = pitch8(N);
+                             const float* __restrict__ amp_scale, PlaneSet out) {
+  const int p4 = pitch4(N);
   const int groups_per_row = p4 / 4;
   const size_t n_groups = (size_t)N * groups_per_row;
   const float a0 = 1.0f / (float)((long long)N * N);
   const float sc = amp_scale[0];
-  const int l = blockIdx.y;
-  const float k = wavenumber[l];
+  const int l0 = blockIdx.y * (int)blockDim.y + threadIdx.y;       // wavelength slice of this thread row
+  const int lstep = gridDim.y * blockDim.y;
   for (size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_groups;
        gidx += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(gidx / groups_per_row);
     const int c = (int)(gidx - (size_t)r * groups_per_row) * 4;
-    float re[4], im[4];
+    float a[4], o[4], pc[4], ps[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      re[e] = 0.0f;
-      im[e] = 0.0f;
+      a[e] = 0.0f; o[e] = 0.0f; pc[e] = 1.0f; ps[e] = 0.0f;
       if (c + e < N) {
         const size_t i = (size_t)r * N + c + e;
-        const float a = T ? a0 * __ldg(T + i) : a0;
-        re[e] = a;
+        a[e] = T ? a0 * __ldg(T + i) : a0;
+        if (opd) o[e] = __ldg(opd + i);
+        if (phase) fast_sincos(__ldg(phase + i), &ps[e], &pc[e]);
+      }
+    }
+    for (int l = l0; l < L; l += lstep) {
+      const float k = __ldg(wavenumber + l);
+      float re[4], im[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        re[e] = a[e];
+        im[e] = 0.0f;
         if (opd) {
           float sn, cs;
-          fast_sincos(__fmul_rn(k, __ldg(opd + i)), &sn, &cs);
-          re[e] = a * cs;
-          im[e] = a * sn;
+          fast_sincos(__fmul_rn(k, o[e]), &sn, &cs);
+          re[e] = a[e] * cs;
+          im[e] = a[e] * sn;
         }
         if (phase) {
-          float sn, cs;
-          fast_sincos(__ldg(phase + i), &sn, &cs);
-          const float r2 = __fsub_rn(__fmul_rn(re[e], cs), __fmul_rn(im[e], sn));
-          const float i2 = __fadd_rn(__fmul_rn(re[e], sn), __fmul_rn(im[e], cs));
+          const float r2 = __fsub_rn(__fmul_rn(re[e], pc[e]), __fmul_rn(im[e], ps[e]));
+          const float i2 = __fadd_rn(__fmul_rn(re[e], ps[e]), __fmul_rn(im[e], pc[e]));
           re[e] = r2;
           im[e] = i2;
         }
         re[e] *= sc;
         im[e] *= sc;
       }
-    }
-    const size_t o4 = ((size_t)l * N + r) * p4 + c;
-    const size_t o8 = ((size_t)l * N + r) * p8 + c;
-    if (exact) {
+      const size_t o4 = ((size_t)l * N + r) * p4 + c;
       *reinterpret_cast<float4*>(out.hi[0] + o4) = make_float4(re[0], re[1], re[2], re[3]);
       *reinterpret_cast<float4*>(out.hi[1] + o4) = make_float4(im[0], im[1], im[2], im[3]);
-    } else {
-      float rh[4], ih[4];
-      __nv_bfloat162 b[4][2];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        rh[e] = tf32_hi(re[e]);
-        ih[e] = tf32_hi(im[e]);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        b[0][h] = __floats2bfloat162_rn(rh[2 * h], rh[2 * h + 1]);
-        b[1][h] = __floats2bfloat162_rn(re[2 * h] - rh[2 * h], re[2 * h + 1] - rh[2 * h + 1]);
-        b[2][h] = __floats2bfloat162_rn(ih[2 * h], ih[2 * h + 1]);
-        b[3][h] = __floats2bfloat162_rn(im[2 * h] - ih[2 * h], im[2 * h + 1] - ih[2 * h + 1]);
-      }
-      *reinterpret_cast<float4*>(out.hi[0] + o4) = make_float4(rh[0], rh[1], rh[2], rh[3]);
-      *reinterpret_cast<float4*>(out.hi[1] + o4) = make_float4(ih[0], ih[1], ih[2], ih[3]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint2 w;
-        w.x = *reinterpret_cast<uint32_t*>(&b[q][0]);
-        w.y = *reinterpret_cast<uint32_t*>(&b[q][1]);
-        *reinterpret_cast<uint2*>(out.b[q] + o8) = w;
-      }
     }
   }
 }
 
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
-                 const float* wavenumber, const float* amp_scale, const PlaneSet& out, int exact,
-                 cudaStream_t st) {
-  dim3 grid(grid_for((size_t)N * (pitch4(N) / 4), 256, 148 * 8), L);
-  pupil_kernel<<<grid, 256, 0, st>>>(N, L, T, opd, phase, wavenumber, amp_scale, out, exact);
+                 const float* wavenumber, const float* amp_scale, const PlaneSet& out, cudaStream_t st) {
+  // 64 x 4 threads: x runs along the pixel groups, y splits the wavelengths four ways
+  const int ly = L < 4 ? L : 4;
+  dim3 block(64, ly);
+  dim3 grid(grid_for((size_t)N * (pitch4(N) / 4), 64, 148 * 8), 1);
+  pupil_kernel<<<grid, block, 0, st>>>(N, L, T, opd, phase, wavenumber, amp_scale, out);
   note_launch();
   return check_launch("pupil");
 }
@@ -230,7 +209,7 @@ int launch_pupil(int N, int L, const float* T, const float* opd, const float* ph
 // cotangent of the field: Ebar = 2 w psf_bar .* E (planes), w_bar[item] = sum psf_bar |E|^2
 __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
                                  const float* __restrict__ psf_bar, const float* __restrict__ w,
-                                 PlaneSet out, int exact, float* __restrict__ w_bar, int weight_axis) {
+                                 PlaneSet out, float* __restrict__ w_bar, int weight_axis) {
   __shared__ float sm[256];
   const size_t n = (size_t)M * M;
   const int item = blockIdx.y;
@@ -248,7 +227,7 @@ __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
     else if (weight_axis == 1) wg *= (float)r - half;
     const float re = wg * e.x, im = wg * e.y;
     const size_t row = (size_t)item * M + r;
-    plane_store(out, row * pitch4(M) + (i - r * M), row * pitch8(M) + (i - r * M), re, im, exact);
+    plane_store(out, row * pitch4(M) + (i - r * M), re, im);
   }
   if (w_bar) {
     sm[threadIdx.x] = acc;
@@ -262,16 +241,15 @@ __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
 }
 
 int launch_cotangent(int M, int n_items, const float2* field, const float* psf_bar, const float* w,
-                     const PlaneSet& out, int exact, float* w_bar, int weight_axis, cudaStream_t st) {
+                     const PlaneSet& out, float* w_bar, int weight_axis, cudaStream_t st) {
   for (int b0 = 0; b0 < n_items; b0 += 65535) {
     int nb = n_items - b0 < 65535 ? n_items - b0 : 65535;
     const size_t off = (size_t)b0 * M * M;
     PlaneSet o = out;
     for (int i = 0; i < 2; ++i) o.hi[i] += (size_t)b0 * M * pitch4(M);
-    for (int i = 0; i < 4; ++i) if (o.b[i]) o.b[i] += (size_t)b0 * M * pitch8(M);
     dim3 grid(grid_for((size_t)M * M, 256, 64), nb);
-    cotangent_kernel<<<grid, 256, 0, st>>>(M, field + off, psf_bar, w + b0, o, exact,
-                                            w_bar ? w_bar + b0 : nullptr, weight_axis);
+    cotangent_kernel<<<grid, 256, 0, st>>>(M, field + off, psf_bar, w + b0, o, w_bar ? w_bar + b0 : nullptr,
+                                            weight_axis);
     note_launch();
   }
   return check_launch("cotangent");

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p, int t
       float re = 0.0f, im = 0.0f;
       if (m < p.rows && k < p.K) {
         const size_t o = a_off + (size_t)m * a_pitch + k;
-        re = __ldg(p.a.hi[0] + o);  // exact mode: unsplit float32
+        re = __ldg(p.a.hi[0] + o);
         im = __ldg(p.a.hi[1] + o);
       }
       As_re[kl][ml] = re;
@@ -91,7 +91,6 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p, int t
 
 int launch_gemm_simt(const GemmParams& p, cudaStream_t st) {
   if (p.n_items <= 0) return DLUX_OK;
-  if (!p.exact) return DLUX_ERR_ARG;  // this path reads unsplit float32 planes
   const int tiles_m = (p.rows + BM - 1) / BM, tiles_n = (p.n_out + BN - 1) / BN;
   const long long total = (long long)tiles_m * tiles_n * p.n_items;
   if (total > 2147483647LL) return DLUX_ERR_SHAPE;

@@ -15,12 +15,13 @@
 //       G1 = (cos | sin),   G2 = (-sin | cos)        (row 2j | row 2j+1)
 //   so that  D = G1 * Re(Data)^T + G2 * Im(Data)^T  has Re(Out[j][:]) in lane 2j and
 //   Im(Out[j][:]) in lane 2j+1: one MMA yields both complex parts.
-// * B operand = the data (PlaneSet, common.cuh): tf32 "hi" planes in float32 plus bf16 copies
-//   of hi and of the residual lo, streamed by TMA (cp.async.bulk.tensor.cta_group::2, K-major,
-//   SWIZZLE_64B for the 64-byte fp32 rows and SWIZZLE_32B for the 32-byte bf16 rows).  Each CTA
-//   holds 64 of the 128 rows of a tile: 32 KiB stages (both tiles), a 5-deep ring, completion
-//   bytes counted on the leader CTA's mbarrier.  Shared memory carries this operand and the
-//   64 KiB of epilogue staging.
+// * B operand = the data (PlaneSet, common.cuh): two planar float32 matrices (Re, Im), 8 bytes
+//   per complex element in HBM.  TMA streams them K-major into SWIZZLE_64B boxes (64 rows x
+//   16 k per CTA and tile); two CONVERTER warps per CTA then split every value on chip: hi =
+//   rna_tf32(z) is written back in place (the kind::tf32 operand) and bf16(hi), bf16(z - hi)
+//   go to SWIZZLE_32B planes next to it (the kind::f16 operands).  Each CTA holds 64 of the
+//   128 rows of a tile: 32 KiB stages (both tiles, float32 + bf16 planes), a 5-deep ring.
+//   Round 1 streamed six pre-split planes (16 bytes per element) from HBM instead.
 // * Split precision ("TF32 + 2xBF16"): per 16-k chunk and tile, 4 tcgen05.mma kind::tf32
 //   (hi*hi, K=8) + 4 kind::f16 bf16 MMAs (hi*lo and lo*hi, K=16) accumulate into the same
 //   fp32 TMEM accumulator -- 8 MMA slots instead of the 12 of 3xTF32; lo*lo is dropped.
@@ -31,15 +32,17 @@
 //   tile's epilogue warpgroup with tcgen05.ld and added, round-to-nearest, into fp32
 //   registers (Ootomo & Yokota's scheme for error-corrected TF32 GEMM).  Draining overlaps
 //   the MMAs of the other tile / next partial.
-// * Barriers: the "full" side of every ring lives in the LEADER CTA (rank 0), which alone
-//   issues MMAs: fullA (both CTAs' TMA producers), fullG (both CTAs' generator warps), tempty
+// * Barriers: rawfull (local: this CTA's TMA bytes have landed, wakes the converters); the
+//   "full" side of every ring lives in the LEADER CTA (rank 0), which alone
+//   issues MMAs: fullA (both CTAs' converter warps), fullG (both CTAs' generator warps), tempty
 //   (both CTAs' drain warpgroups) -- remote arrivals are mbarrier.arrive.relaxed.cluster.  The
 //   "empty" side is local to each CTA and signalled by tcgen05.commit ... multicast::cluster:
 //   emptyA, emptyG, tfull.
 // * Epilogues: EPI_PLANES (the intermediate of a two-stage transform) goes out through TMA
-//   stores -- every TMEM lane is one output row, so each drain thread splits and packs its
-//   own 16-column slice into the swizzled box layout of its plane and the TMA writes the six
-//   boxes of the warp asynchronously, double-buffered, clipping at the matrix edge.  EPI_C64
+//   stores -- every TMEM lane is one output row, so each drain thread drops its own
+//   16-column slice into the swizzled box layout of its plane (Re lanes -> plane 0, Im lanes
+//   -> plane 1) and the TMA writes the two boxes of the warp asynchronously, four slices in
+//   flight, clipping at the matrix edge.  EPI_C64
 //   (final complex64 result) does the same with one SWIZZLE_128B box of 16 rows x 16 complex
 //   per warp and slice (real lane -> even words, imaginary lane -> odd words); only an odd
 //   row length (global pitch not a multiple of 16 bytes) takes the load/store epilogue, which
@@ -91,17 +94,30 @@ static_assert(G_BASE_COL + G_STAGES * G_COLS <= TMEM_COLS, "TMEM budget");
 constexpr int NUM_EPI_WARPS = 8;   // warps 0..3 drain tile a (WG0), warps 4..7 tile b (WG1)
 constexpr int WARP_TMA = 8;        // WG2
 constexpr int WARP_MMA = 9;
+constexpr int RAW_BYTES = 4 * (ROWS_CTA * BK * 4);   // TMA bytes per stage and CTA: Re, Im of tiles a and b
 constexpr int FIRST_GEN_WARP = 12; // WG3 (k-step 0 of each chunk), WG4 (k-step 1)
 constexpr int NUM_GEN_WARPS = 8;
-constexpr int NUM_THREADS = 32 * (FIRST_GEN_WARP + NUM_GEN_WARPS);  // 640
-constexpr int REGS_LAUNCH = 96;    // 65536 / 640 rounded down to a multiple of 8
-constexpr int REGS_EPI = 152, REGS_CTRL = 40, REGS_GEN = 64;        // setmaxnreg budgets
-static_assert(256 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_GEN),
+constexpr int FIRST_CONV_WARP = FIRST_GEN_WARP + NUM_GEN_WARPS;      // WG5: operand converters, warp w -> (tile, plane)
+constexpr int NUM_CONV_WARPS = 4;
+constexpr int NUM_THREADS = 32 * (FIRST_CONV_WARP + NUM_CONV_WARPS);  // 768
+constexpr int REGS_LAUNCH = 80;    // 65536 / 768 rounded down to a multiple of 8
+#ifndef DLUX_REGS_EPI
+#define DLUX_REGS_EPI 152
+#define DLUX_REGS_CTRL 32
+#define DLUX_REGS_GEN 56
+#define DLUX_REGS_CONV 32
+#endif
+constexpr int REGS_EPI = DLUX_REGS_EPI, REGS_CTRL = DLUX_REGS_CTRL, REGS_GEN = DLUX_REGS_GEN,
+              REGS_CONV = DLUX_REGS_CONV;   // setmaxnreg budgets
+// setmaxnreg.inc draws from the registers the CTA was LAUNCHED with (NUM_THREADS * REGS_LAUNCH), fed by
+// the .dec of the other warpgroups -- not from unallocated registers of the SM
+static_assert(256 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_GEN) +
+                                                    128 * (REGS_LAUNCH - REGS_CONV),
               "register budget");
 constexpr int CLUSTER = 2;         // the CTA pair of a cta_group::2 MMA
 constexpr int BAR_BYTES = 1024;     // barriers + TMEM slot (keeps the staging 1 KiB aligned)
-constexpr int STG_SLICE_BYTES = 4096;                      // one 16-column slice of the six planes of a warp
-constexpr int STG_BUFS = A_STAGES >= 6 ? 1 : 2;            // a 5-stage ring leaves room to double-buffer it
+constexpr int STG_SLICE_BYTES = 2048;                      // one 16-column slice of the two planes of a warp
+constexpr int STG_BUFS = A_STAGES >= 6 ? 2 : 4;            // slices in flight per warp
 constexpr int STG_WARP_BYTES = STG_BUFS * STG_SLICE_BYTES; // epilogue staging per drain warp
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + BAR_BYTES + NUM_EPI_WARPS * STG_WARP_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory per CTA");
@@ -139,10 +155,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 #endif
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;"
-               ::"r"(cluster_addr), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -167,13 +179,31 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// pair mode: destination in my own shared memory, completion bytes counted on the LEADER's barrier
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar,
-                                                int c0, int c1, int c2) {
+// destination and completion barrier in my own shared memory (the converters of THIS CTA wait on it)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// publishes generic-proxy shared-memory writes (fenced to the async proxy by their writers) to the
+// MMA issuer of the leader CTA
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// default semantics (.release at CTA scope): the converted operand never leaves this CTA's shared memory
+// -- each SM's tensor core reads its own half -- only the signal crosses to the leader (the form CUTLASS'
+// 2-SM transform pipelines use after fence.proxy.async)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc2(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -345,69 +375,48 @@ __device__ __forceinline__ void tile_epilogue_c64_lsu(const GemmParams& p, int i
 
 // EPI_PLANES through TMA stores.  Thread = TMEM lane = one output row (coordinate j = lane / 2,
 // real or imaginary part = lane % 2) holding that row's 128 columns: no transposition is needed
-// -- each lane scales, splits and packs its own 16-column slice straight into the box layout of
-// its plane (16 rows x 16 columns; SWIZZLE_64B for the 64-byte fp32 rows, SWIZZLE_32B for the
-// 32-byte bf16 rows), and one lane hands the six boxes of the warp to the TMA, which writes
-// them asynchronously and clips what lies beyond the matrix.  Staging per warp (4 KiB):
-// [hi re 1 KiB | hi im 1 KiB | bf16 hi re, lo re, hi im, lo im 512 B each].
+// -- each lane scales its own 16-column slice straight into the box layout of its plane
+// (16 rows x 16 columns of float32, SWIZZLE_64B), and one lane hands the two boxes of the warp to
+// the TMA, which writes them asynchronously and clips what lies beyond the matrix.  Staging per
+// warp and slice (2 KiB): [Re 1 KiB | Im 1 KiB]; STG_BUFS slices in flight.
+__device__ __forceinline__ void bulk_wait_read_n(int n) {
+  if (n <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (n == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else if (n == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+}
 __device__ __forceinline__ void tile_epilogue_tma(const GemmParams& p, int item, int nq0, int m0, int lane,
-                                                  float (&tot)[BM], uint32_t stg,
-                                                  const CUtensorMap* o_hr, const CUtensorMap* o_hi,
-                                                  const CUtensorMap* o_b0, const CUtensorMap* o_b1,
-                                                  const CUtensorMap* o_b2, const CUtensorMap* o_b3) {
+                                                  float (&tot)[BM], uint32_t stg0,
+                                                  const CUtensorMap* o_re, const CUtensorMap* o_im) {
   const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
   const int mmax = p.rows - m0;
   const int j = lane >> 1, part = lane & 1;
-  const uint32_t sw64 = (uint32_t)((j >> 1) & 3), sw32 = (uint32_t)((j >> 2) & 1);
-  const uint32_t stg0 = stg;
+  const uint32_t sw64 = (uint32_t)((j >> 1) & 3);
 #pragma unroll
   for (int s = 0; s < BM / 16; ++s) {
     const int c0 = s * 16;
     if (c0 >= mmax) break;  // warp-uniform: the rest of the tile lies beyond the matrix
-    stg = stg0 + (s % STG_BUFS) * STG_SLICE_BYTES;
-    const uint32_t hi_row = stg + part * 1024 + j * 64;            // my row of the fp32 plane box
-    const uint32_t bh_row = stg + 2048 + part * 1024 + j * 32;     // ... of the bf16 hi box
-    const uint32_t bl_row = bh_row + 512;                          // ... of the bf16 lo box
+    const uint32_t stg = stg0 + (s % STG_BUFS) * STG_SLICE_BYTES;
+    const uint32_t row = stg + part * 1024 + j * 64;               // my row of my plane's box
     if (s >= STG_BUFS) {    // the TMA has read this buffer's previous slice
-      if (lane == 0) { if (STG_BUFS == 1) bulk_wait_read(); else bulk_wait_read1(); }
+      if (lane == 0) bulk_wait_read_n(STG_BUFS - 1);
       __syncwarp();
     }
-    uint32_t bh[8], bl[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {   // (the re / im lanes of a pair hit the same banks: 2-way, cheap)
-      float h[4], l[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float v = tot[c0 + 4 * c + e] * sc;
-        h[e] = tf32_hi(v);
-        l[e] = v - h[e];
-      }
-      st_shared_v4(hi_row + (((uint32_t)c ^ sw64) << 4), __float_as_uint(h[0]), __float_as_uint(h[1]),
-                   __float_as_uint(h[2]), __float_as_uint(h[3]));
-      bh[2 * c] = pack_bf16(h[0], h[1]);
-      bh[2 * c + 1] = pack_bf16(h[2], h[3]);
-      bl[2 * c] = pack_bf16(l[0], l[1]);
-      bl[2 * c + 1] = pack_bf16(l[2], l[3]);
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      st_shared_v4(bh_row + (((uint32_t)c ^ sw32) << 4), bh[4 * c], bh[4 * c + 1], bh[4 * c + 2], bh[4 * c + 3]);
-      st_shared_v4(bl_row + (((uint32_t)c ^ sw32) << 4), bl[4 * c], bl[4 * c + 1], bl[4 * c + 2], bl[4 * c + 3]);
-    }
+    for (int c = 0; c < 4; ++c)   // (the re / im lanes of a pair hit the same banks: 2-way, cheap)
+      st_shared_v4(row + (((uint32_t)c ^ sw64) << 4), __float_as_uint(tot[c0 + 4 * c] * sc),
+                   __float_as_uint(tot[c0 + 4 * c + 1] * sc), __float_as_uint(tot[c0 + 4 * c + 2] * sc),
+                   __float_as_uint(tot[c0 + 4 * c + 3] * sc));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes, before the TMA reads them
     __syncwarp();
     if (lane == 0) {
       const int col = m0 + c0;
-      tma_store_3d(o_hr, stg, col, nq0, item);
-      tma_store_3d(o_hi, stg + 1024, col, nq0, item);
-      tma_store_3d(o_b0, stg + 2048, col, nq0, item);          // bf16 hi re
-      tma_store_3d(o_b1, stg + 2048 + 512, col, nq0, item);    // bf16 lo re
-      tma_store_3d(o_b2, stg + 3072, col, nq0, item);          // bf16 hi im
-      tma_store_3d(o_b3, stg + 3072 + 512, col, nq0, item);    // bf16 lo im
+      tma_store_3d(o_re, stg, col, nq0, item);
+      tma_store_3d(o_im, stg + 1024, col, nq0, item);
       bulk_commit();
     }
   }
-  if (lane == 0) bulk_wait_read();  // the staging buffer is free again (the next user may be the C64 path)
+  if (lane == 0) bulk_wait_read();  // the staging buffers are free again (the next user may be the C64 path)
   __syncwarp();
 }
 
@@ -417,12 +426,6 @@ __device__ __forceinline__ void tile_epilogue_tma(const GemmParams& p, int item,
 // buffers per warp: up to three slices in flight.
 constexpr int C64_SLICE_BYTES = 2048;
 constexpr int C64_BUFS = STG_WARP_BYTES / C64_SLICE_BYTES;   // 4 (2 with the 6-stage ring)
-__device__ __forceinline__ void bulk_wait_read_n(int n) {
-  if (n <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  else if (n == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-  else if (n == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-  else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-}
 __device__ __forceinline__ void tile_epilogue_c64_tma(const GemmParams& p, int item, int nq0, int m0, int lane,
                                                       float (&tot)[BM], uint32_t stg0, const CUtensorMap* o_c) {
   const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
@@ -453,6 +456,57 @@ __device__ __forceinline__ void tile_epilogue_c64_tma(const GemmParams& p, int i
   }
   if (lane == 0) bulk_wait_read();
   __syncwarp();
+}
+
+// On-chip operand split.  One converter warp owns one plane (Re or Im) of one tile: this CTA's 64 rows
+// x 16 k of it, as the TMA left them (float32, SWIZZLE_64B).  Work item = (row, k-half): 8 values -> hi =
+// rna_tf32 written back in place, bf16(hi) and bf16(v - hi) as one 16-byte chunk each of the SWIZZLE_32B
+// planes.  128 items per plane = 4 per lane, loaded two at a time; every quarter-warp touches 8 distinct
+// 16-byte bank groups.
+__device__ __forceinline__ void convert_plane(uint8_t* fplane, uint8_t* bplane_hi, int lane) {
+  const uint32_t h = (uint32_t)lane & 1u;
+  const int rl = lane >> 1;
+#pragma unroll
+  for (int it2 = 0; it2 < 2; ++it2) {
+    float4 v[2][2];
+    float4* src[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = (it2 * 2 + u) * 16 + rl;
+      const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
+      uint8_t* frow = fplane + r * 64;
+      src[u][0] = reinterpret_cast<float4*>(frow + (((2u * h) ^ sw64) << 4));
+      src[u][1] = reinterpret_cast<float4*>(frow + (((2u * h + 1u) ^ sw64) << 4));
+      v[u][0] = *src[u][0];
+      v[u][1] = *src[u][1];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = (it2 * 2 + u) * 16 + rl;
+      const uint32_t sw32 = (uint32_t)((r >> 2) & 1);
+      uint4 ph, plo;
+      float4 h0, h1;
+#ifdef DLUX_CONV_TRUNC
+#define TF32_SPLIT(x) __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)   // what the MMA itself would keep
+#else
+#define TF32_SPLIT(x) tf32_hi(x)
+#endif
+      h0.x = TF32_SPLIT(v[u][0].x); h0.y = TF32_SPLIT(v[u][0].y); h0.z = TF32_SPLIT(v[u][0].z); h0.w = TF32_SPLIT(v[u][0].w);
+      h1.x = TF32_SPLIT(v[u][1].x); h1.y = TF32_SPLIT(v[u][1].y); h1.z = TF32_SPLIT(v[u][1].z); h1.w = TF32_SPLIT(v[u][1].w);
+      ph.x = pack_bf16(h0.x, h0.y); ph.y = pack_bf16(h0.z, h0.w);
+      ph.z = pack_bf16(h1.x, h1.y); ph.w = pack_bf16(h1.z, h1.w);
+      plo.x = pack_bf16(v[u][0].x - h0.x, v[u][0].y - h0.y); plo.y = pack_bf16(v[u][0].z - h0.z, v[u][0].w - h0.w);
+      plo.z = pack_bf16(v[u][1].x - h1.x, v[u][1].y - h1.y); plo.w = pack_bf16(v[u][1].z - h1.z, v[u][1].w - h1.w);
+#ifndef DLUX_CONV_TRUNC
+      *src[u][0] = h0;
+      *src[u][1] = h1;
+#endif
+      uint8_t* brow = bplane_hi + r * 32 + ((h ^ sw32) << 4);
+      *reinterpret_cast<uint4*>(brow) = ph;
+      *reinterpret_cast<uint4*>(brow + BPLANE_BYTES) = plo;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my writes, before the MMA reads them
 }
 
 // The 8 MMAs of one tile and one 16-k chunk:
@@ -518,11 +572,7 @@ struct TcParams {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-               const __grid_constant__ CUtensorMap mapb0, const __grid_constant__ CUtensorMap mapb1,
-               const __grid_constant__ CUtensorMap mapb2, const __grid_constant__ CUtensorMap mapb3,
                const __grid_constant__ CUtensorMap omap0, const __grid_constant__ CUtensorMap omap1,
-               const __grid_constant__ CUtensorMap omapb0, const __grid_constant__ CUtensorMap omapb1,
-               const __grid_constant__ CUtensorMap omapb2, const __grid_constant__ CUtensorMap omapb3,
                const __grid_constant__ CUtensorMap omapc, const TcParams tp) {
   extern __shared__ uint8_t smem_raw[];
   const GemmParams& p = tp.g;
@@ -535,33 +585,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   auto emptyG_bar = [&](int s) { return bar_base + 8u * (2 * A_STAGES + G_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * A_STAGES + 2 * G_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * A_STAGES + 2 * G_STAGES + NUM_ACC + a); };
+  auto rawfull_bar = [&](int s) { return bar_base + 8u * (2 * A_STAGES + 2 * G_STAGES + 2 * NUM_ACC + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(
-      smem_gen + RING_BYTES + 8 * (2 * A_STAGES + 2 * G_STAGES + 2 * NUM_ACC));
+      smem_gen + RING_BYTES + 8 * (3 * A_STAGES + 2 * G_STAGES + 2 * NUM_ACC));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == WARP_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map0));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map1));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb0));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb1));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb2));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapb3));
     if (tp.g.mode == EPI_PLANES) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omap0));
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omap1));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb0));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb1));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb2));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&omapb3));
     } else if (tp.c64_tma) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omapc));
     }
   }
   if (warp == WARP_MMA && lane == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
-      mbar_init(fullA_bar(s), 2);   // [leader's] arrive.expect_tx of both CTAs' TMA producers
+      mbar_init(fullA_bar(s), 2 * NUM_CONV_WARPS);   // [leader's] the converter warps of both CTAs
       mbar_init(emptyA_bar(s), 2);  // multicast tcgen05.commit of the two issuer warps
+      mbar_init(rawfull_bar(s), 1); // my TMA producer's arrive.expect_tx (+ the bytes of my four loads)
     }
     for (int s = 0; s < G_STAGES; ++s) {
       mbar_init(fullG_bar(s), 2 * NUM_GEN_WARPS);  // [leader's] one arrive per generator warp of both CTAs
@@ -601,6 +645,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
     if (warp == WARP_TMA) {
       // ===================== TMA producer =====================
+      // Four loads per chunk (Re / Im of tiles a and b, my 64 rows of each) onto my own rawfull
+      // barrier, which wakes this CTA's converter warps.
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
@@ -612,21 +658,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           mbar_wait(emptyA_bar(stage), phase ^ 1);
           if (elect_one()) {
             const uint32_t dst = smem_base + stage * A_BYTES;
-            const uint32_t bar = fullA_bar(stage);
-            // my half (64 rows) of both tiles into my own slot; the bytes are counted by the
-            // leader's barrier (rows beyond the matrix are zero-filled)
-            const uint32_t lbar = bar + lead_delta;
-            mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
+            const uint32_t bar = rawfull_bar(stage);
+            mbar_arrive_expect_tx(bar, RAW_BYTES);
 #pragma unroll
-            for (int tb2 = 0; tb2 < 2; ++tb2) {
+            for (int tb2 = 0; tb2 < 2; ++tb2) {   // (rows beyond the matrix are zero-filled)
               const uint32_t t0 = dst + tb2 * TILE_BYTES;
               const int mr = m0 + tb2 * BM + (int)crank * ROWS_CTA;
-              tma_load_3d_2sm(t0 + 0 * PLANE_BYTES, &map0, lbar, kc * BK, mr, d);   // tf32 hi: re, im
-              tma_load_3d_2sm(t0 + 1 * PLANE_BYTES, &map1, lbar, kc * BK, mr, d);
-              tma_load_3d_2sm(t0 + BPL_BASE + 0 * BPLANE_BYTES, &mapb0, lbar, kc * BK, mr, d);  // bf16
-              tma_load_3d_2sm(t0 + BPL_BASE + 1 * BPLANE_BYTES, &mapb1, lbar, kc * BK, mr, d);
-              tma_load_3d_2sm(t0 + BPL_BASE + 2 * BPLANE_BYTES, &mapb2, lbar, kc * BK, mr, d);
-              tma_load_3d_2sm(t0 + BPL_BASE + 3 * BPLANE_BYTES, &mapb3, lbar, kc * BK, mr, d);
+              tma_load_3d(t0 + 0 * PLANE_BYTES, &map0, bar, kc * BK, mr, d);   // Re
+              tma_load_3d(t0 + 1 * PLANE_BYTES, &map1, bar, kc * BK, mr, d);   // Im
             }
           }
           __syncwarp();
@@ -744,6 +783,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #endif
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
+#ifdef DLUX_DRAIN_X32
 #pragma unroll
         for (int c = 0; c < BM; c += 32) {
           uint32_t v0[16], v1[16];
@@ -756,6 +796,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             tot[c + 16 + j] += __uint_as_float(v1[j]);
           }
         }
+#else
+#pragma unroll
+        for (int c = 0; c < BM; c += 16) {
+          uint32_t v0[16];
+          tmem_ld16(t0 + c, v0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) tot[c + j] += __uint_as_float(v0[j]);
+        }
+#endif
         tc_fence_before();
         mbar_arrive_cluster(tempty_bar(buf) + lead_delta);
       }
@@ -767,7 +817,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #else
       if (m0 < p.rows) {  // warp-uniform condition
         if (p.mode == EPI_PLANES)
-          tile_epilogue_tma(p, item, nq0, m0, lane, tot, stg_addr, &omap0, &omap1, &omapb0, &omapb1, &omapb2, &omapb3);
+          tile_epilogue_tma(p, item, nq0, m0, lane, tot, stg_addr, &omap0, &omap1);
         else if (tp.c64_tma)
           tile_epilogue_c64_tma(p, item, nq0, m0, lane, tot, stg_addr, &omapc);
         else
@@ -783,6 +833,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0)
       printf("DRAIN%d: total %lld  wait tfull %lld  epilogue %lld  units %lld\n", which, clock64() - dbg_start, dbg_w,
              dbg_e, dbg_n);
+#endif
+  } else if (warp >= FIRST_CONV_WARP) {
+    // ===================== operand converters (WG5) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONV));
+    const int cw = warp - FIRST_CONV_WARP;          // tile = cw / 2, plane = cw % 2
+    const uint32_t off_f = (uint32_t)((cw >> 1) * TILE_BYTES + (cw & 1) * PLANE_BYTES);
+    const uint32_t off_b = (uint32_t)((cw >> 1) * TILE_BYTES + BPL_BASE + 2 * (cw & 1) * BPLANE_BYTES);
+    int cstage = 0;
+    uint32_t cphase = 0;
+#ifdef DLUX_DEBUG_TIMING
+    long long dbg_cw = 0, dbg_cc = 0;
+    const long long dbg_cstart = clock64();
+#endif
+    for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
+      for (int kc = 0; kc < tp.k_chunks; ++kc) {
+#ifdef DLUX_DEBUG_TIMING
+        const long long tc0_ = clock64();
+#endif
+        mbar_wait(rawfull_bar(cstage), cphase);
+#ifdef DLUX_DEBUG_TIMING
+        const long long tc1_ = clock64();
+#endif
+        uint8_t* sb = smem_gen + cstage * A_BYTES;
+        convert_plane(sb + off_f, sb + off_b, lane);
+        __syncwarp();
+#if defined(DLUX_CONV_RELAXED)
+        if (lane == 0) mbar_arrive_cluster(fullA_bar(cstage) + lead_delta);
+#elif defined(DLUX_CONV_RELEASE_CLUSTER)
+        if (lane == 0) mbar_arrive_release_cluster(fullA_bar(cstage) + lead_delta);
+#else
+        if (lane == 0) mbar_arrive_remote(fullA_bar(cstage) + lead_delta);
+#endif
+#ifdef DLUX_DEBUG_TIMING
+        dbg_cw += tc1_ - tc0_; dbg_cc += clock64() - tc1_;
+#endif
+        if (++cstage == A_STAGES) { cstage = 0; cphase ^= 1; }
+      }
+    }
+#ifdef DLUX_DEBUG_TIMING
+    if (blockIdx.x == 0 && lane == 0 && cw == 0)
+      printf("CONV: total %lld  wait rawfull %lld  convert+arrive %lld\n", clock64() - dbg_cstart, dbg_cw, dbg_cc);
 #endif
   } else {
     // ===================== phasor generators =====================
@@ -1091,22 +1182,17 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   if (p.n_items <= 0) return DLUX_OK;
   TcState& s = tc_state();
   if (s.rc != DLUX_OK) return s.rc;
-  if (p.exact) return DLUX_ERR_ARG;  // needs the split operand planes
 
   const cuuint64_t n_data = (cuuint64_t)(p.n_data > 0 ? p.n_data : p.n_items);
-  CUtensorMap maps[6];
-  for (int i = 0; i < 6; ++i) {
-    const bool bf = i >= 2;
-    const cuuint64_t esz = bf ? 2 : 4;
-    const cuuint64_t pitch = bf ? pitch8(p.K) : pitch4(p.K);  // row strides are multiples of 16 bytes
+  CUtensorMap maps[2];
+  for (int i = 0; i < 2; ++i) {
+    const cuuint64_t pitch = pitch4(p.K);  // row strides are multiples of 16 bytes
     cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.rows, n_data};
-    cuuint64_t strides[2] = {pitch * esz, pitch * esz * (cuuint64_t)p.rows};
+    cuuint64_t strides[2] = {pitch * 4, pitch * 4 * (cuuint64_t)p.rows};
     cuuint32_t box[3] = {BK, ROWS_CTA, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    void* base = bf ? (void*)p.a.b[i - 2] : (void*)p.a.hi[i];
-    CUresult r = s.encode(&maps[i], bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                          base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          bf ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+    CUresult r = s.encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.a.hi[i], dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       fprintf(stderr, "[dlux_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
@@ -1114,20 +1200,16 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
     }
   }
   // output planes of EPI_PLANES, written by TMA stores: [n_items][n_out][rows], box 16 x 16
-  CUtensorMap omaps[6];
-  for (int i = 0; i < 6; ++i) {
+  CUtensorMap omaps[2];
+  for (int i = 0; i < 2; ++i) {
     if (p.mode != EPI_PLANES) { omaps[i] = maps[i]; continue; }   // unused by the C64 epilogue
-    const bool bf = i >= 2;
-    const cuuint64_t esz = bf ? 2 : 4;
-    const cuuint64_t pitch = bf ? pitch8(p.rows) : pitch4(p.rows);
+    const cuuint64_t pitch = pitch4(p.rows);
     cuuint64_t dims[3] = {(cuuint64_t)p.rows, (cuuint64_t)p.n_out, (cuuint64_t)p.n_items};
-    cuuint64_t strides[2] = {pitch * esz, pitch * esz * (cuuint64_t)p.n_out};
+    cuuint64_t strides[2] = {pitch * 4, pitch * 4 * (cuuint64_t)p.n_out};
     cuuint32_t box[3] = {16, 16, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    void* base = bf ? (void*)p.out.b[i - 2] : (void*)p.out.hi[i];
-    CUresult r = s.encode(&omaps[i], bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                          base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          bf ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+    CUresult r = s.encode(&omaps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.out.hi[i], dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       fprintf(stderr, "[dlux_b200] cuTensorMapEncodeTiled (output plane %d) failed: %d\n", i, (int)r);
@@ -1173,8 +1255,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                     omaps[0], omaps[1], omaps[2], omaps[3], omaps[4], omaps[5], omapc, tp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], omaps[0], omaps[1], omapc, tp);
   if (e != cudaSuccess) {
     fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
     note_cuda_error((int)e);

@@ -1,11 +1,13 @@
-# usage: run_vars.sh VARIANT...   (libs prepared as dlux_b200/lib/var_<VARIANT>.so; a trailing T = timing build)
+# usage: run_vars.sh VARIANT...   (libs prepared as dlux_b200/lib/var_<VARIANT>.so; a trailing T = timing build,
+# a trailing S = also the sustained record)
 for v in "$@"; do
-  cp dlux_b200/lib/var_$v.so dlux_b200/lib/libdlux_b200.so
+  lib=${v%S}
+  cp dlux_b200/lib/var_$lib.so dlux_b200/lib/libdlux_b200.so
   echo "=== $v"
   case $v in
-    *T) timeout 60 python tools/timing_probe.py 64 2>&1 | grep "MMA\|DRAIN0\|GEN" | tail -8 ;;
-    *) timeout 100 python tools/accuracy.py 2>&1 | grep 3xtf32
-       timeout 200 python bench.py --steps 300 --warmup 10 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['gemm_ms_per_step'], d['clocks'], d['e2e']['value'])" ;;
+    *T) timeout 60 python tools/timing_probe.py 64 2>&1 | grep "MMA\|DRAIN0\|GEN\|CONV" | tail -10 ;;
+    *S) timeout 200 python bench.py --steps 50 --warmup 5 --sustained 4 2>/dev/null | tail -1 > /tmp/b.json; python tools/bench_summary.py /tmp/b.json ;;
+    *) timeout 150 python bench.py --steps 50 --warmup 5 --sustained 0 2>/dev/null | tail -1 > /tmp/b.json; python tools/bench_summary.py /tmp/b.json ;;
   esac
 done
 cp dlux_b200/lib/var_CUR.so dlux_b200/lib/libdlux_b200.so 2>/dev/null
