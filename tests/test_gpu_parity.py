@@ -421,9 +421,10 @@ def test_dynamic_apertures_fused_and_differentiable(dev):
                                   pixel_scale_rad=O.arcsec2rad(0.05), offset=off, normalise=True, dtype=np.float64)
         (ref * torch.tensor(Gc)).sum().backward()
         check(f"dynamic aperture psf [fused={fused}]", rel_l2(psf.detach().cpu().numpy(), ref.detach().numpy()), TOL)
-        # float32-input floor of the aperture producer, not of the MFT: the soft edge is two pixels wide, so
-        # d/d(radius) sums differences of float32 pixel coordinates (relative precision 6e-8 x N / softening);
-        # the same geometry evaluated in float32 on the CPU shows the same 1-2e-5 against float64
+        # a shape parameter's gradient is <T_bar, dT/d(param)> restricted to the soft-edge pixels: they carry
+        # 7 % of the norm of T_bar and the inner product cancels 11.5-fold (measured with the float64 twin), so
+        # the transmission cotangent's own 2.5e-6 (test_transmission_and_phase_gradients) shows up as 1-2e-5
+        # here.  Conditioning of the derived quantity, not a looser kernel
         check(f"radius grad [fused={fused}]", rel_scalar(radius.grad, r64.grad), 5e-5)
         check(f"rotation grad [fused={fused}]", rel_scalar(rot.grad, q64.grad), 5e-5)
 
