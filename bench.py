@@ -206,6 +206,61 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+
+def run_c4_strong(dev, world, rank, steps=3, n_stars=64):
+    """BASELINE config 4 at fixed TOTAL size (strong scaling): 2048 px binary-phase-mask pupil, `n_stars` stars x
+    64 wavelengths -> 256x256, gradients w.r.t. star positions, fluxes and the phase mask.  Stars are sharded
+    over the ranks; one NCCL all-reduce of the image forward, one flat all-reduce of the gradients backward."""
+    import torch
+    import torch.distributed as dist
+    import dlux_b200 as dl
+    from dlux_b200 import distributed as D
+    from dlux_b200 import workloads
+    cfg = workloads.config("c4")
+    N, M, L = cfg["wf_npixels"], cfg["psf_npixels"], len(cfg["wavelengths"])
+    up = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    phase = up(cfg["phase"]).requires_grad_(True)
+    pos = up(cfg["positions"][:n_stars]).requires_grad_(True)
+    flux = up(cfg["fluxes"][:n_stars]).requires_grad_(True)
+    G = up(cfg["G"])
+    layer = dl.Optic(up(cfg["transmission"]), None, phase, normalise=True, device=dev)
+    optics = dl.AngularOpticalSystem(N, cfg["diameter"], [("mask", layer)], M, cfg["psf_pixel_scale"], device=dev)
+
+    def step():
+        for t in (phase, pos, flux):
+            t.grad = None
+        psf = D.sharded_point_sources_model(optics, cfg["wavelengths"], pos, flux, cfg["weights"])
+        (psf * G).sum().backward()
+        D.all_reduce_grads([phase, pos, flux])
+        return psf
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    flops = 2 * n_stars * L * mft_flops(N, M)
+    return {"workload": f"c4-lite: 2048 px binary phase mask, {n_stars} stars x {L} wavelengths -> {M}x{M}, "
+                        "PSF + gradients w.r.t. positions, fluxes and the phase mask; TOTAL size fixed (strong scaling)",
+            "ms_per_step": ms, "star_wavelength_psf_grad_per_s": n_stars * L * 1e3 / ms,
+            "psf_grad_per_s": 1e3 / ms, "mft_tflops_algorithmic_all_gpus": flops / (ms * 1e-3) / 1e12,
+            "stars_per_gpu": n_stars / world,
+            "nccl_bytes_per_step": 0 if world == 1 else int(4 * M * M + 4 * (N * N + 3 * n_stars)),
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+
+
 # ---------------------------------------------------------------------------- CUDA arm
 def run_ours(args):
     import torch
@@ -345,6 +400,14 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = world * 1e3 / ms_e2e
 
+    # ---- the north-star multi-GPU workload at fixed total size (every rank takes part)
+    c4 = None
+    if args.c4_stars > 0:
+        try:
+            c4 = run_c4_strong(dev, world, rank, n_stars=args.c4_stars)
+        except Exception as e:                           # pragma: no cover
+            c4 = {"error": repr(e)}
+
     # clocks of the other ranks (the driver only sees rank 0's line)
     if world > 1:
         allc = [None] * world
@@ -432,6 +495,7 @@ def run_ours(args):
         "parity": parity,
         "roofline": roof,
         "sustained": sus,
+        "c4_strong": c4,
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "one full c3 PSF+grad, all 64 wavelengths (NumPy complex64 oracle transfer "
                                    "matrices + torch-CPU complex64 matmul/autograd on all host cores)"},
@@ -447,6 +511,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--c4-stars", type=int, default=64,
+                    help="stars of the fixed-size C4-lite strong-scaling record (0 = skip)")
     ap.add_argument("--sustained", type=float, default=3.0,
                     help="seconds of back-to-back steps for the `sustained` sub-record (0 = skip)")
     args = ap.parse_args()

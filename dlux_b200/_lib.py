@@ -25,6 +25,12 @@ class PolyPsfDesc(C.Structure):
                 ("save_field", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PolyPsfBatchDesc(C.Structure):
+    _fields_ = [("n_pupil", C.c_int32), ("n_psf", C.c_int32), ("n_wavels", C.c_int32),
+                ("n_batch", C.c_int32), ("n_basis", C.c_int32), ("normalise", C.c_int32),
+                ("precision", C.c_int32), ("save_field", C.c_int32)]
+
+
 class DluxError(RuntimeError):
     pass
 
@@ -45,6 +51,9 @@ SIGNATURES = {
     "dlux_polypsf_scratch_bytes": (C.c_size_t, [C.POINTER(PolyPsfDesc)]),
     "dlux_polypsf_fwd": (C.c_int, [C.POINTER(PolyPsfDesc)] + [_P] * 10 + [_P, C.c_size_t, _P]),
     "dlux_polypsf_bwd": (C.c_int, [C.POINTER(PolyPsfDesc)] + [_P] * 17 + [_P, C.c_size_t, _P]),
+    "dlux_polypsf_batch_scratch_bytes": (C.c_size_t, [C.POINTER(PolyPsfBatchDesc)]),
+    "dlux_polypsf_batch_fwd": (C.c_int, [C.POINTER(PolyPsfBatchDesc)] + [_P] * 12 + [_P, C.c_size_t, _P]),
+    "dlux_polypsf_batch_bwd": (C.c_int, [C.POINTER(PolyPsfBatchDesc)] + [_P] * 13 + [_P, C.c_size_t, _P]),
     "dlux_basis_eval": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, _P, _P]),
     "dlux_basis_reduce": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, _P]),
 }

@@ -27,17 +27,38 @@ int check_launch(const char* what) {
 
 int launch_zero(float* p, size_t n, cudaStream_t st);
 
-// per-item parameter expansion for the fused poly-PSF path: item = s * L + l
-__global__ void expand_items_kernel(int n_items, int L, const float* __restrict__ scale_out,
+// Per-item parameter expansion for the fused poly-PSF path.  The caller's arrays are source-major
+// ([S, L]: index s * L + l); items are PROCESSED wavelength-major (i = l * S + s) so that consecutive items
+// -- the stars of one wavelength -- contract the same pupil phasor P(l), which then stays L2-resident
+// instead of being re-read from HBM for every star (BASELINE config 4: 1000 stars x 64 wavelengths).
+__global__ void expand_items_kernel(int n_items, int L, int S, const float* __restrict__ scale_out,
                                     const float* __restrict__ norm, const float* __restrict__ wavenumber,
+                                    const float* __restrict__ weights, const float* __restrict__ delta_xy,
                                     int* __restrict__ item_l, float* __restrict__ s_item,
-                                    float* __restrict__ norm_item, float* __restrict__ k_item) {
+                                    float* __restrict__ norm_item, float* __restrict__ k_item,
+                                    float* __restrict__ w_item, float* __restrict__ delta_item) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
-    const int l = i % L;
+    const int l = i / S, sidx = i - l * S;
+    const int src = sidx * L + l;
     item_l[i] = l;
     s_item[i] = scale_out[l];
     norm_item[i] = norm ? norm[l] : 1.0f;
     k_item[i] = wavenumber[l];
+    if (w_item) w_item[i] = weights[src];
+    if (delta_item && delta_xy) {
+      delta_item[2 * i] = delta_xy[2 * src];
+      delta_item[2 * i + 1] = delta_xy[2 * src + 1];
+    }
+  }
+}
+
+// processing order -> the caller's [S, L] layout, `width` values per item
+__global__ void scatter_items_kernel(int n_items, int L, int S, int width, const float* __restrict__ in,
+                                     float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items * width; i += gridDim.x * blockDim.x) {
+    const int it = i / width, e = i - it * width;
+    const int l = it / S, sidx = it - l * S;
+    out[(sidx * L + l) * width + e] = in[i];
   }
 }
 
@@ -105,13 +126,13 @@ static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
   return rc;
 }
 
-// per-chunk intermediates, bytes (DLUX_B200_CHUNK_MB overrides; the tests use it to force
-// the multi-chunk paths at small sizes)
+// per-chunk intermediates, bytes: 6 GiB of a 180 GB board (DLUX_B200_CHUNK_MB overrides; the tests use it
+// to force the multi-chunk paths at small sizes).  Larger chunks = fewer, longer persistent launches
 static size_t chunk_budget() {
   static const size_t v = [] {
     const char* e = getenv("DLUX_B200_CHUNK_MB");
     const long mb = e ? atol(e) : 0;
-    return mb > 0 ? (size_t)mb << 20 : (size_t)2 << 30;
+    return mb > 0 ? (size_t)mb << 20 : (size_t)6 << 30;
   }();
   return v;
 }
@@ -185,6 +206,104 @@ static void fill_stage(GemmParams& g, bool adjoint, int stage, int N, int M, int
     g.nvec = xin + (size_t)axis * N;
     g.nvec_stride = 2 * N;
   }
+}
+
+
+// ------------------------------------------------------------------ parameter-batched poly-PSF
+// item = b * L + l; one chunk = a whole number of batch elements
+struct BatchScratch {
+  float* amp_scale;
+  float *s_item, *norm_item, *k_item, *delta_item;   // per chunk [cb * L]
+  int* item_l;
+  float *xin, *uout;
+  float* opd_c;       // [cb][N*N]
+  float* opdbar_c;    // [cb][N*N]
+  PlaneSet p_pl;      // [cb * L][N][N]
+  PlaneSet mid_pl;    // [cb * L]
+  PlaneSet ebar_pl;   // [cb * L][M][M]
+  float2* qbuf;       // [cb * L][N*N]
+  float2* fbuf;       // [cb * L][M*M]
+  int cb;
+};
+
+static int batch_chunk(const dlux_polypsf_batch_desc* d) {
+  const size_t N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
+  const size_t per_item = plane_bytes(N, (int)N) + mid_bytes((int)N, (int)M) + plane_bytes(M, (int)M) +
+                          8 * (N + M) + 8 * N * N + 8 * M * M + 64;
+  const size_t per_b = L * per_item + 8 * N * N + 4096;
+  size_t cb = kChunkBudget / per_b;
+  if (cb < 1) cb = 1;
+  if (cb * L > 32768) cb = 32768 / L > 0 ? 32768 / L : 1;     // grid.y limits of the per-item helper kernels
+  return (int)balanced_chunk((size_t)d->n_batch, cb);
+}
+
+static size_t carve_batch(const dlux_polypsf_batch_desc* d, void* scratch, size_t cap, BatchScratch* s, bool* ok) {
+  Bump b(scratch, cap);
+  const size_t N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
+  const size_t cb = batch_chunk(d), c = cb * L;
+  s->cb = (int)cb;
+  s->amp_scale = b.take<float>(4 + 512);
+  s->s_item = b.take<float>(c);
+  s->norm_item = b.take<float>(c);
+  s->k_item = b.take<float>(c);
+  s->delta_item = b.take<float>(2 * c);
+  s->item_l = b.take<int>(c);
+  s->xin = b.take<float>(c * 2 * N);
+  s->uout = b.take<float>(c * 2 * M);
+  s->opd_c = b.take<float>(cb * N * N);
+  s->opdbar_c = b.take<float>(cb * N * N);
+  s->p_pl = take_planes(b, c * N, (int)N);
+  s->mid_pl = take_mid_planes(b, c, (int)N, (int)M);
+  s->ebar_pl = take_planes(b, c * M, (int)M);
+  s->qbuf = b.take<float2>(c * N * N);
+  s->fbuf = b.take<float2>(c * M * M);
+  if (ok) *ok = b.ok;
+  return b.used();
+}
+
+static int check_batch_desc(const dlux_polypsf_batch_desc* d) {
+  if (!d) return DLUX_ERR_ARG;
+  if (d->n_pupil < 1 || d->n_psf < 1 || d->n_wavels < 1 || d->n_batch < 1 || d->n_basis < 1) return DLUX_ERR_SHAPE;
+  if (d->n_pupil > 32768 || d->n_psf > 32768 || d->n_wavels > 32768 || d->n_basis > 8192) return DLUX_ERR_SHAPE;
+  if (d->precision != DLUX_PREC_3XTF32 && d->precision != DLUX_PREC_FP32) return DLUX_ERR_ARG;
+  return DLUX_OK;
+}
+
+__global__ void expand_batch_kernel(int n_items, int L, const float* __restrict__ scale_out,
+                                    const float* __restrict__ norm, const float* __restrict__ wavenumber,
+                                    float* __restrict__ s_item, float* __restrict__ norm_item,
+                                    float* __restrict__ k_item) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int l = i % L;     // batch-major: item = b * L + l
+    s_item[i] = scale_out[l];
+    norm_item[i] = norm ? norm[l] : 1.0f;
+    k_item[i] = wavenumber[l];
+  }
+}
+
+__global__ void expand_delta_kernel(int n_items, int L, const float* __restrict__ delta_l, float* __restrict__ delta_item) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_items; i += gridDim.x * blockDim.x)
+    delta_item[i] = delta_l[2 * ((i / 2) % L) + (i & 1)];
+}
+
+// per-chunk geometry operands (the same for every chunk: items repeat the L wavelengths)
+static int batch_prologue(const dlux_polypsf_batch_desc* d, const BatchScratch& s, const float* T,
+                          const float* wavenumber, const float* scale_out, const float* norm, const float* delta_xy,
+                          cudaStream_t st) {
+  const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
+  const int c = s.cb * L;
+  int rc = launch_power(N, T, d->normalise, s.amp_scale, st);
+  if (rc) return rc;
+  expand_batch_kernel<<<(c + 255) / 256, 256, 0, st>>>(c, L, scale_out, norm, wavenumber, s.s_item, s.norm_item,
+                                                        s.k_item);
+  note_launch();
+  if (delta_xy) {
+    expand_delta_kernel<<<(2 * c + 255) / 256, 256, 0, st>>>(c, L, delta_xy, s.delta_item);
+    note_launch();
+  }
+  rc = check_launch("batch expand");
+  if (rc) return rc;
+  return launch_coords(N, M, c, s.s_item, nullptr, delta_xy ? s.delta_item : nullptr, 1, s.xin, s.uout, st);
 }
 
 }  // namespace dlux
@@ -312,6 +431,8 @@ struct PolyScratch {
   PlaneSet p_pl;     // [L][N][N]
   int* item_l;
   float *s_item, *norm_item, *k_item;
+  float *w_item, *delta_item;                          // caller's [S, L] arrays in processing order
+  float *wbar_item, *dbar_item, *sbar_item, *kbar_item; // bwd outputs in processing order
   float *xin, *uout;  // per chunk
   PlaneSet mid_pl;    // per chunk [c][M*N]
   PlaneSet ebar_pl;   // per chunk [c][M*M]  (bwd only; sized always for simplicity)
@@ -340,6 +461,12 @@ static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, 
   s->s_item = b.take<float>(items);
   s->norm_item = b.take<float>(items);
   s->k_item = b.take<float>(items);
+  s->w_item = b.take<float>(items);
+  s->delta_item = b.take<float>(2 * items);
+  s->wbar_item = b.take<float>(items);
+  s->dbar_item = b.take<float>(2 * items);
+  s->sbar_item = b.take<float>(items);
+  s->kbar_item = b.take<float>(items);
   s->xin = b.take<float>(c * 2 * N);
   s->uout = b.take<float>(c * 2 * M);
   s->mid_pl = take_mid_planes(b, c, (int)N, (int)M);
@@ -368,8 +495,8 @@ size_t dlux_polypsf_scratch_bytes(const dlux_polypsf_desc* desc) {
 
 static int poly_prologue(const dlux_polypsf_desc* d, const PolyScratch& s, const float* T,
                          const float* opd, const float* phase, const float* wavenumber,
-                         const float* scale_out, const float* norm, bool need_planes,
-                         cudaStream_t st) {
+                         const float* scale_out, const float* norm, const float* weights, const float* delta_xy,
+                         bool need_planes, cudaStream_t st) {
   const int N = d->n_pupil, L = d->n_wavels;
   const int items = d->n_sources * L;
   int rc = launch_power(N, T, d->normalise, s.amp_scale, st);
@@ -379,7 +506,8 @@ static int poly_prologue(const dlux_polypsf_desc* d, const PolyScratch& s, const
     if (rc) return rc;
   }
   expand_items_kernel<<<(items + 255) / 256 > 1024 ? 1024 : (items + 255) / 256, 256, 0, st>>>(
-      items, L, scale_out, norm, wavenumber, s.item_l, s.s_item, s.norm_item, s.k_item);
+      items, L, d->n_sources, scale_out, norm, wavenumber, weights, delta_xy, s.item_l, s.s_item, s.norm_item,
+      s.k_item, s.w_item, s.delta_item);
   note_launch();
   return check_launch("expand_items");
 }
@@ -400,12 +528,12 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
   if (!ok) return DLUX_ERR_SCRATCH;
   const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
   const int items = d->n_sources * L;
-  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, true, st);
+  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, true, st);
   if (rc) return rc;
   const float sign2pi = (float)(-2.0 * 3.14159265358979323846);
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
-    rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
+    rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? s.delta_item + 2 * (size_t)b0 : nullptr,
                        1, s.xin, s.uout, st);
     if (rc) return rc;
     GemmParams g{};
@@ -426,7 +554,7 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
     rc = run_gemm(h, d->precision, st);
     if (rc) return rc;
     // psf (+)= sum over this chunk's (source, wavelength) items of w |E|^2
-    rc = launch_psf_reduce((size_t)M * M, c, h.out_c64, weights + b0, psf, b0 > 0, st);
+    rc = launch_psf_reduce((size_t)M * M, c, h.out_c64, s.w_item + b0, psf, b0 > 0, st);
     if (rc) return rc;
   }
   return DLUX_OK;
@@ -450,8 +578,14 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
   const int items = d->n_sources * L;
   // the gradient epilogue re-evaluates the pupil phasor itself: no operand planes needed
-  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, false, st);
+  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, false, st);
   if (rc) return rc;
+  // per-item outputs are accumulated in processing order and scattered to the caller's [S, L] layout at the end
+  float* const wbar_c = weights_bar, * const dbar_c = delta_bar, * const sbar_c = scale_bar, * const kbar_c = wavenumber_bar;
+  if (weights_bar) weights_bar = s.wbar_item;
+  if (delta_bar) delta_bar = s.dbar_item;
+  if (scale_bar) scale_bar = s.sbar_item;
+  if (wavenumber_bar) wavenumber_bar = s.kbar_item;
   if (weights_bar && (rc = launch_zero(weights_bar, (size_t)items, st))) return rc;
   if (delta_bar && (rc = launch_zero(delta_bar, (size_t)items * 2, st))) return rc;
   if (scale_bar && (rc = launch_zero(scale_bar, (size_t)items, st))) return rc;
@@ -468,13 +602,13 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
     // adjoint like the offset gradient (opposite sign).
     const int n_pass = scale_bar ? 3 : 1;
     for (int pass = 0; pass < n_pass; ++pass) {
-      rc = launch_cotangent(M, c, (const float2*)field + (size_t)b0 * M * M, psf_bar, weights + b0,
+      rc = launch_cotangent(M, c, (const float2*)field + (size_t)b0 * M * M, psf_bar, s.w_item + b0,
                             s.ebar_pl, (pass == 0 && weights_bar) ? weights_bar + b0 : nullptr,
                             pass - 1, st);
       if (rc) return rc;
       if (!need_pupil_grad) continue;
       if (pass == 0) {
-        rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
+        rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? s.delta_item + 2 * (size_t)b0 : nullptr,
                            1, s.xin, s.uout, st);
         if (rc) return rc;
       }
@@ -517,11 +651,130 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
       }
     }
   }
+  {
+    const int S = d->n_sources, g = (items * 2 + 255) / 256 > 1024 ? 1024 : (items * 2 + 255) / 256;
+    if (wbar_c) { scatter_items_kernel<<<g, 256, 0, st>>>(items, L, S, 1, s.wbar_item, wbar_c); note_launch(); }
+    if (dbar_c) { scatter_items_kernel<<<g, 256, 0, st>>>(items, L, S, 2, s.dbar_item, dbar_c); note_launch(); }
+    if (sbar_c) { scatter_items_kernel<<<g, 256, 0, st>>>(items, L, S, 1, s.sbar_item, sbar_c); note_launch(); }
+    if (kbar_c) { scatter_items_kernel<<<g, 256, 0, st>>>(items, L, S, 1, s.kbar_item, kbar_c); note_launch(); }
+    if ((rc = check_launch("scatter_items"))) return rc;
+  }
   if (transmission_bar && d->normalise) {
     // amp_scale's scratch slot is followed by the 256-double work area of the power reduction
     double* work = reinterpret_cast<double*>(reinterpret_cast<char*>(s.amp_scale) + 16);
     rc = launch_tbar_finalize((size_t)N * N, T, s.amp_scale, 1.0f / (float)((long long)N * N),
                               transmission_bar, work, st);
+    if (rc) return rc;
+  }
+  return DLUX_OK;
+}
+
+
+size_t dlux_polypsf_batch_scratch_bytes(const dlux_polypsf_batch_desc* desc) {
+  if (check_batch_desc(desc) != DLUX_OK) return 0;
+  BatchScratch s;
+  return carve_batch(desc, nullptr, 0, &s, nullptr);
+}
+
+int dlux_polypsf_batch_fwd(const dlux_polypsf_batch_desc* d, const float* T, const float* base_opd,
+                           const float* phase, const float* basis, const float* coeffs, const float* wavenumber,
+                           const float* scale_out, const float* norm, const float* weights, const float* delta_xy,
+                           float* psf, void* field, void* scratch, size_t scratch_bytes, void* cuda_stream) {
+  int rc = check_batch_desc(d);
+  if (rc != DLUX_OK) return rc;
+  if (!basis || !coeffs || !wavenumber || !scale_out || !weights || !psf || !scratch) return DLUX_ERR_ARG;
+  if (d->save_field && !field) return DLUX_ERR_ARG;
+  if (((uintptr_t)psf | (uintptr_t)scratch | (uintptr_t)field) & 15) return DLUX_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  BatchScratch s;
+  bool ok = true;
+  carve_batch(d, scratch, scratch_bytes, &s, &ok);
+  if (!ok) return DLUX_ERR_SCRATCH;
+  const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels, B = d->n_batch, nz = d->n_basis;
+  const size_t npix = (size_t)N * N, mpix = (size_t)M * M;
+  rc = batch_prologue(d, s, T, wavenumber, scale_out, norm, delta_xy, st);
+  if (rc) return rc;
+  const float sign2pi = (float)(-2.0 * 3.14159265358979323846);
+  for (int b0 = 0; b0 < B; b0 += s.cb) {
+    const int cb = B - b0 < s.cb ? B - b0 : s.cb;
+    const int c = cb * L;
+    // OPD of every batch element of the chunk (utils/math.py:177-196), then its L pupil phasors
+    rc = launch_basis_eval(nz, (int64_t)npix, basis, coeffs + (size_t)b0 * nz, base_opd, s.opd_c, st, cb);
+    if (rc) return rc;
+    rc = launch_pupil(N, L, T, s.opd_c, phase, wavenumber, s.amp_scale, s.p_pl, st, cb);
+    if (rc) return rc;
+    GemmParams g{};
+    fill_stage(g, false, 0, N, M, c, s.xin, s.uout, sign2pi);
+    g.a = s.p_pl;
+    g.out = s.mid_pl;
+    g.mode = EPI_PLANES;
+    rc = run_gemm(g, d->precision, st);
+    if (rc) return rc;
+    GemmParams h{};
+    fill_stage(h, false, 1, N, M, c, s.xin, s.uout, sign2pi);
+    h.a = s.mid_pl;
+    h.mode = EPI_C64;
+    h.scale = s.norm_item;
+    h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * L * mpix : s.fbuf;
+    rc = run_gemm(h, d->precision, st);
+    if (rc) return rc;
+    // psf[b] = sum_l w_l |E_bl|^2: per-item images, no collective, nothing summed over the batch
+    rc = launch_psf_reduce(mpix, L, h.out_c64, weights, psf + (size_t)b0 * mpix, 0, st, cb);
+    if (rc) return rc;
+  }
+  return DLUX_OK;
+}
+
+int dlux_polypsf_batch_bwd(const dlux_polypsf_batch_desc* d, const float* T, const float* base_opd,
+                           const float* phase, const float* basis, const float* coeffs, const float* wavenumber,
+                           const float* scale_out, const float* norm, const float* weights, const float* delta_xy,
+                           const void* field, const float* psf_bar, float* coeff_bar, void* scratch,
+                           size_t scratch_bytes, void* cuda_stream) {
+  int rc = check_batch_desc(d);
+  if (rc != DLUX_OK) return rc;
+  if (!basis || !coeffs || !wavenumber || !scale_out || !weights || !field || !psf_bar || !coeff_bar || !scratch)
+    return DLUX_ERR_ARG;
+  if (((uintptr_t)field | (uintptr_t)scratch) & 15) return DLUX_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  BatchScratch s;
+  bool ok = true;
+  carve_batch(d, scratch, scratch_bytes, &s, &ok);
+  if (!ok) return DLUX_ERR_SCRATCH;
+  const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels, B = d->n_batch, nz = d->n_basis;
+  const size_t npix = (size_t)N * N, mpix = (size_t)M * M;
+  rc = batch_prologue(d, s, T, wavenumber, scale_out, norm, delta_xy, st);
+  if (rc) return rc;
+  const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
+  const float a0 = 1.0f / (float)((long long)N * N);
+  for (int b0 = 0; b0 < B; b0 += s.cb) {
+    const int cb = B - b0 < s.cb ? B - b0 : s.cb;
+    const int c = cb * L;
+    rc = launch_basis_eval(nz, (int64_t)npix, basis, coeffs + (size_t)b0 * nz, base_opd, s.opd_c, st, cb);
+    if (rc) return rc;
+    // Ebar_bl = 2 w_l psf_bar[b] .* E_bl
+    rc = launch_cotangent(M, c, (const float2*)field + (size_t)b0 * L * mpix, psf_bar + (size_t)b0 * mpix, weights,
+                          s.ebar_pl, nullptr, -1, st, L);
+    if (rc) return rc;
+    GemmParams g{};
+    fill_stage(g, true, 0, N, M, c, s.xin, s.uout, sign2pi);
+    g.a = s.ebar_pl;
+    g.out = s.mid_pl;
+    g.mode = EPI_PLANES;
+    rc = run_gemm(g, d->precision, st);
+    if (rc) return rc;
+    GemmParams h{};
+    fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
+    h.a = s.mid_pl;
+    h.mode = EPI_C64;
+    h.scale = s.norm_item;
+    h.out_c64 = s.qbuf;
+    rc = run_gemm(h, d->precision, st);
+    if (rc) return rc;
+    // opd_bar[b] = sum_l k_l Im(conj(P_bl) Q_bl), then its projection on the basis: coeff_bar[b]
+    rc = launch_grad_reduce(npix, L, s.qbuf, s.k_item, T, s.opd_c, phase, s.amp_scale, a0, s.opdbar_c, nullptr,
+                            nullptr, 0, st, cb);
+    if (rc) return rc;
+    rc = launch_basis_reduce(nz, (int64_t)npix, basis, s.opdbar_c, coeff_bar + (size_t)b0 * nz, st, cb);
     if (rc) return rc;
   }
   return DLUX_OK;

@@ -162,16 +162,17 @@ int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const 
 int launch_split_c64(const float2* in, size_t n_mat_rows, int cols, const PlaneSet& out, cudaStream_t st);
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
                  const float* wavenumber, const float* amp_scale /*device scalar*/,
-                 const PlaneSet& out, cudaStream_t st);
+                 const PlaneSet& out, cudaStream_t st, int n_batch = 1);
 int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStream_t st);
 // `weight_axis`: -1 none; 0 / 1: multiply by the output-pixel index (col / row) minus (M-1)/2,
 // the derivative of the output coordinate w.r.t. scale_out
 int launch_cotangent(int M, int n_items, const float2* field, const float* psf_bar,
-                     const float* w, const PlaneSet& out, float* w_bar, int weight_axis, cudaStream_t st);
+                     const float* w, const PlaneSet& out, float* w_bar, int weight_axis, cudaStream_t st,
+                     int items_per_bar = 0);
 int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coeffs,
-                      const float* base, float* out, cudaStream_t st);
+                      const float* base, float* out, cudaStream_t st, int n_batch = 1);
 int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,
-                        float* coeff_bar, cudaStream_t st);
+                        float* coeff_bar, cudaStream_t st, int n_batch = 1);
 int launch_zero(float* p, size_t n, cudaStream_t st);
 // delta_bar[item][axis] = 2 pi sum_ij x_axis(i or j) * Im(conj(P_ij) Q_ij[item])  (source-offset VJP)
 // sel 0: delta_bar[item][2] += 2 pi (sum x g, sum y g); sel 1 / 2: out[item] -= 2 pi sum x g / sum y g;
@@ -180,13 +181,14 @@ int launch_pos_grad(int N, int n_items, const float2* q, const float* k, const f
                     const float* phase, const float* amp_scale, float a0, float* out, int sel, cudaStream_t st);
 // psf[i] (+)= sum_item w[item] |field[item][i]|^2
 int launch_psf_reduce(size_t npix, int n_items, const float2* field, const float* w, float* psf,
-                      int accumulate, cudaStream_t st);
+                      int accumulate, cudaStream_t st, int n_batch = 1);
 // Gradient of the pupil phase from the adjoint field Q = MFT^H(Ebar), summed over items:
 //   g = Im(conj(P) Q),  P = a0 * amp_scale * T * exp(i (k * opd + phase))
 //   opd_bar[i] (+)= sum_item k[item] g[item][i];  phase_bar[i] (+)= sum_item g[item][i]
 int launch_grad_reduce(size_t npix, int n_items, const float2* q, const float* k, const float* T,
                        const float* opd, const float* phase, const float* amp_scale, float a0,
-                       float* opd_bar, float* phase_bar, float* t_bar, int accumulate, cudaStream_t st);
+                       float* opd_bar, float* phase_bar, float* t_bar, int accumulate, cudaStream_t st,
+                       int n_batch = 1);
 // T_bar -= (sum_i T_i T_bar_i) * amp^2 * a0^2 * T   (the power-normalisation term; `work` = 256 doubles)
 int launch_tbar_finalize(size_t npix, const float* T, const float* amp_scale, float a0, float* t_bar,
                          double* work, cudaStream_t st);

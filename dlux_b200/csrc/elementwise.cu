@@ -143,6 +143,10 @@ int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStr
 __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const float* __restrict__ opd,
                              const float* __restrict__ phase, const float* __restrict__ wavenumber,
                              const float* __restrict__ amp_scale, PlaneSet out) {
+  // blockIdx.z = element of a parameter batch: its own OPD map [N, N] and its own L planes
+  if (opd) opd += (size_t)blockIdx.z * N * N;
+  out.hi[0] += (size_t)blockIdx.z * L * N * pitch4(N);
+  out.hi[1] += (size_t)blockIdx.z * L * N * pitch4(N);
   const int p4 = pitch4(N);
   const int groups_per_row = p4 / 4;
   const size_t n_groups = (size_t)N * groups_per_row;
@@ -195,11 +199,12 @@ __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const fl
 }
 
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
-                 const float* wavenumber, const float* amp_scale, const PlaneSet& out, cudaStream_t st) {
+                 const float* wavenumber, const float* amp_scale, const PlaneSet& out, cudaStream_t st,
+                 int n_batch) {
   // 64 x 4 threads: x runs along the pixel groups, y splits the wavelengths four ways
   const int ly = L < 4 ? L : 4;
   dim3 block(64, ly);
-  dim3 grid(grid_for((size_t)N * (pitch4(N) / 4), 64, 148 * 8), 1);
+  dim3 grid(grid_for((size_t)N * (pitch4(N) / 4), 64, n_batch > 1 ? 148 * 2 : 148 * 8), 1, n_batch);
   pupil_kernel<<<grid, block, 0, st>>>(N, L, T, opd, phase, wavenumber, amp_scale, out);
   note_launch();
   return check_launch("pupil");
@@ -209,11 +214,13 @@ int launch_pupil(int N, int L, const float* T, const float* opd, const float* ph
 // cotangent of the field: Ebar = 2 w psf_bar .* E (planes), w_bar[item] = sum psf_bar |E|^2
 __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
                                  const float* __restrict__ psf_bar, const float* __restrict__ w,
-                                 PlaneSet out, float* __restrict__ w_bar, int weight_axis) {
+                                 PlaneSet out, float* __restrict__ w_bar, int weight_axis, int items_per_bar) {
   __shared__ float sm[256];
   const size_t n = (size_t)M * M;
   const int item = blockIdx.y;
-  const float w2 = 2.0f * w[item];
+  // parameter batch: item = b * L + l has its own cotangent image psf_bar[b] and the shared weight w[l]
+  if (items_per_bar > 0) psf_bar += (size_t)(item / items_per_bar) * n;
+  const float w2 = 2.0f * w[items_per_bar > 0 ? item % items_per_bar : item];
   const float half = 0.5f * (float)(M - 1);
   float acc = 0.0f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -241,15 +248,16 @@ __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
 }
 
 int launch_cotangent(int M, int n_items, const float2* field, const float* psf_bar, const float* w,
-                     const PlaneSet& out, float* w_bar, int weight_axis, cudaStream_t st) {
+                     const PlaneSet& out, float* w_bar, int weight_axis, cudaStream_t st, int items_per_bar) {
+  if (items_per_bar > 0 && n_items > 65535) return DLUX_ERR_SHAPE;   // (chunks of a batch are far smaller)
   for (int b0 = 0; b0 < n_items; b0 += 65535) {
     int nb = n_items - b0 < 65535 ? n_items - b0 : 65535;
     const size_t off = (size_t)b0 * M * M;
     PlaneSet o = out;
     for (int i = 0; i < 2; ++i) o.hi[i] += (size_t)b0 * M * pitch4(M);
     dim3 grid(grid_for((size_t)M * M, 256, 64), nb);
-    cotangent_kernel<<<grid, 256, 0, st>>>(M, field + off, psf_bar, w + b0, o, w_bar ? w_bar + b0 : nullptr,
-                                            weight_axis);
+    cotangent_kernel<<<grid, 256, 0, st>>>(M, field + off, psf_bar, items_per_bar > 0 ? w : w + b0, o,
+                                            w_bar ? w_bar + b0 : nullptr, weight_axis, items_per_bar);
     note_launch();
   }
   return check_launch("cotangent");
@@ -261,6 +269,8 @@ __global__ void basis_eval_kernel(int nz, size_t npix, const float* __restrict__
                                   const float* __restrict__ coeffs, const float* __restrict__ base,
                                   float* __restrict__ out) {
   extern __shared__ float c_sm[];
+  coeffs += (size_t)blockIdx.y * nz;          // blockIdx.y = element of a parameter batch
+  out += (size_t)blockIdx.y * npix;
   for (int z = threadIdx.x; z < nz; z += blockDim.x) c_sm[z] = coeffs[z];
   __syncthreads();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
@@ -272,9 +282,9 @@ __global__ void basis_eval_kernel(int nz, size_t npix, const float* __restrict__
 }
 
 int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coeffs,
-                      const float* base, float* out, cudaStream_t st) {
-  basis_eval_kernel<<<grid_for((size_t)npix, 256), 256, nz * sizeof(float), st>>>(
-      nz, (size_t)npix, basis, coeffs, base, out);
+                      const float* base, float* out, cudaStream_t st, int n_batch) {
+  dim3 grid(grid_for((size_t)npix, 256, n_batch > 1 ? 148 * 4 : 148 * 16), n_batch);
+  basis_eval_kernel<<<grid, 256, nz * sizeof(float), st>>>(nz, (size_t)npix, basis, coeffs, base, out);
   note_launch();
   return check_launch("basis_eval");
 }
@@ -290,6 +300,8 @@ __global__ void basis_reduce_kernel(int nz, size_t npix, const float* __restrict
   __shared__ float sm[8];
   constexpr int PER = 8;
   float g[PER];
+  out_bar += (size_t)blockIdx.y * npix;       // blockIdx.y = element of a parameter batch
+  coeff_bar += (size_t)blockIdx.y * nz;
   const size_t base_i = ((size_t)blockIdx.x * blockDim.x) * PER + threadIdx.x;
   // each block owns a contiguous chunk of PER*blockDim pixels (grid sized to cover npix)
 #pragma unroll
@@ -317,10 +329,10 @@ __global__ void basis_reduce_kernel(int nz, size_t npix, const float* __restrict
 }
 
 int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,
-                        float* coeff_bar, cudaStream_t st) {
-  zero_kernel<<<1, 256, 0, st>>>(coeff_bar, (size_t)nz);
+                        float* coeff_bar, cudaStream_t st, int n_batch) {
+  zero_kernel<<<grid_for((size_t)nz * n_batch, 256), 256, 0, st>>>(coeff_bar, (size_t)nz * n_batch);
   const size_t per_block = 256 * 8;
-  const int grid = (int)(((size_t)npix + per_block - 1) / per_block);
+  dim3 grid((unsigned)(((size_t)npix + per_block - 1) / per_block), n_batch);
   basis_reduce_kernel<<<grid, 256, 0, st>>>(nz, (size_t)npix, basis, out_bar, coeff_bar);
   note_launch(2);
   return check_launch("basis_reduce");
@@ -331,6 +343,9 @@ int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* o
 // kernels reduce them (optical_systems.py:222-223 `psf.sum(0)`, sources.py:409-411).
 __global__ void psf_reduce_kernel(size_t npix, int n_items, const float2* __restrict__ field,
                                   const float* __restrict__ w, float* __restrict__ psf, int accumulate) {
+  // blockIdx.y = element of a parameter batch: its own n_items fields and its own image, shared weights
+  field += (size_t)blockIdx.y * n_items * npix;
+  psf += (size_t)blockIdx.y * npix;
   if ((npix & 1) == 0) {  // two pixels (one float4 of field) per thread; item stride stays 16-B aligned
     const size_t npair = npix / 2;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair;
@@ -362,8 +377,9 @@ __global__ void psf_reduce_kernel(size_t npix, int n_items, const float2* __rest
 }
 
 int launch_psf_reduce(size_t npix, int n_items, const float2* field, const float* w, float* psf,
-                      int accumulate, cudaStream_t st) {
-  psf_reduce_kernel<<<grid_for(npix / 2 + 1, 128, 148 * 16), 128, 0, st>>>(npix, n_items, field, w, psf, accumulate);
+                      int accumulate, cudaStream_t st, int n_batch) {
+  dim3 grid(grid_for(npix / 2 + 1, 128, n_batch > 1 ? 148 * 4 : 148 * 16), n_batch);
+  psf_reduce_kernel<<<grid, 128, 0, st>>>(npix, n_items, field, w, psf, accumulate);
   note_launch();
   return check_launch("psf_reduce");
 }
@@ -377,6 +393,10 @@ __global__ void grad_reduce_kernel(size_t npix, int n_items, const float2* __res
                                    const float* __restrict__ amp_scale, float a0,
                                    float* __restrict__ opd_bar, float* __restrict__ phase_bar,
                                    float* __restrict__ t_bar, int accumulate) {
+  // blockIdx.y = element of a parameter batch (opd_bar only): its own OPD map, adjoint fields and output
+  q += (size_t)blockIdx.y * n_items * npix;
+  if (opd) opd += (size_t)blockIdx.y * npix;
+  if (opd_bar) opd_bar += (size_t)blockIdx.y * npix;
   const float amp = a0 * amp_scale[0];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -408,8 +428,11 @@ __global__ void grad_reduce_kernel(size_t npix, int n_items, const float2* __res
 
 int launch_grad_reduce(size_t npix, int n_items, const float2* q, const float* k, const float* T,
                        const float* opd, const float* phase, const float* amp_scale, float a0,
-                       float* opd_bar, float* phase_bar, float* t_bar, int accumulate, cudaStream_t st) {
-  grad_reduce_kernel<<<grid_for(npix, 128, 148 * 16), 128, 0, st>>>(npix, n_items, q, k, T, opd, phase,
+                       float* opd_bar, float* phase_bar, float* t_bar, int accumulate, cudaStream_t st,
+                       int n_batch) {
+  if (n_batch > 1 && (phase_bar || t_bar)) return DLUX_ERR_ARG;
+  dim3 grid(grid_for(npix, 128, n_batch > 1 ? 148 * 4 : 148 * 16), n_batch);
+  grad_reduce_kernel<<<grid, 128, 0, st>>>(npix, n_items, q, k, T, opd, phase,
                                                                     amp_scale, a0, opd_bar, phase_bar, t_bar,
                                                                     accumulate);
   note_launch();

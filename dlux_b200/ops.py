@@ -14,11 +14,11 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MftDesc, PolyPsfDesc, PREC_3XTF32, PREC_FP32, check
+from ._lib import MftDesc, PolyPsfBatchDesc, PolyPsfDesc, PREC_3XTF32, PREC_FP32, check
 
 __all__ = ["default_precision", "set_default_precision", "mft_c64", "mft_coords", "MFTFunction",
            "polypsf_fwd", "polypsf_bwd", "PolyPSFFunction", "basis_eval", "basis_reduce",
-           "BasisEvalFunction"]
+           "BasisEvalFunction", "PolyPSFBatchFunction"]
 
 _default_precision = {"3xtf32": PREC_3XTF32, "fp32": PREC_FP32}[
     os.environ.get("DLUX_B200_PRECISION", "3xtf32").lower()]
@@ -352,6 +352,67 @@ class PolyPSFFunction(torch.autograd.Function):
         if d_bar is not None:
             d_bar = d_bar.reshape(delta_xy.shape)
         return (opd_bar, phase_bar, w_bar, d_bar, t_bar, k_bar, s_bar, n_bar) + (None,) * 4
+
+
+
+# --------------------------------------------------------------------------- parameter batch
+class PolyPSFBatchFunction(torch.autograd.Function):
+    """psf[b] = sum_l w_l |MFT_l(amp T exp(i (k_l (base_opd + coeffs[b] . basis) + phase)))|^2 for a batch of
+    coefficient vectors, one fused call per direction (``dlux_polypsf_batch_fwd / _bwd``); the VJP returns
+    the per-item coefficient gradients [B, nz].  What the reference expresses as ``vmap`` of
+    ``OpticalSystem.propagate`` (and of its ``jax.grad``) over parameter sets (docs/mask_design.md:454-488).
+    Only the coefficients are differentiable here; the other operands are held fixed across the batch."""
+
+    @staticmethod
+    def forward(ctx, coeffs, basis, base_opd, phase, transmission, weights, delta_xy, wavenumber, scale_out,
+                norm, n_pupil, n_psf, normalise, precision):
+        lib = _lib.load()
+        dev = wavenumber.device
+        _need_cuda(coeffs, "coefficients")
+        B = coeffs.shape[0]
+        nz = coeffs[0].numel()
+        L = wavenumber.numel()
+        coeffs_c = coeffs.detach().reshape(B, nz).to(torch.float32).contiguous()
+        basis_c = basis.reshape(nz, n_pupil, n_pupil).contiguous()
+        need = coeffs.requires_grad
+        desc = PolyPsfBatchDesc(n_pupil, n_psf, L, B, nz, int(bool(normalise)), _prec(precision), int(need))
+        nbytes = lib.dlux_polypsf_batch_scratch_bytes(C.byref(desc))
+        scratch = _get_scratch(dev, nbytes)
+        psf = torch.empty((B, n_psf, n_psf), dtype=torch.float32, device=dev)
+        field = torch.empty((B * L, n_psf, n_psf), dtype=torch.complex64, device=dev) if need else None
+        weights_c = weights.reshape(L).contiguous()
+        delta_c = None if delta_xy is None else delta_xy.reshape(L, 2).contiguous()
+        with torch.cuda.device(dev):
+            check(lib.dlux_polypsf_batch_fwd(C.byref(desc), _ptr(transmission), _ptr(base_opd), _ptr(phase),
+                                             _ptr(basis_c), _ptr(coeffs_c), _ptr(wavenumber), _ptr(scale_out),
+                                             _ptr(norm), _ptr(weights_c), _ptr(delta_c), _ptr(psf), _ptr(field),
+                                             _ptr(scratch), scratch.numel(), _stream(dev)), "dlux_polypsf_batch_fwd")
+        ctx.saved = (coeffs_c, basis_c, base_opd, phase, transmission, weights_c, delta_c, wavenumber, scale_out,
+                     norm, field)
+        ctx.cfg = (n_pupil, n_psf, normalise, precision, coeffs.shape)
+        return psf
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, psf_bar):
+        lib = _lib.load()
+        coeffs_c, basis_c, base_opd, phase, transmission, weights_c, delta_c, wavenumber, scale_out, norm, field = ctx.saved
+        n_pupil, n_psf, normalise, precision, cshape = ctx.cfg
+        dev = wavenumber.device
+        B, nz = coeffs_c.shape
+        L = wavenumber.numel()
+        desc = PolyPsfBatchDesc(n_pupil, n_psf, L, B, nz, int(bool(normalise)), _prec(precision), 1)
+        nbytes = lib.dlux_polypsf_batch_scratch_bytes(C.byref(desc))
+        scratch = _get_scratch(dev, nbytes)
+        cbar = torch.empty((B, nz), dtype=torch.float32, device=dev)
+        psf_bar = psf_bar.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            check(lib.dlux_polypsf_batch_bwd(C.byref(desc), _ptr(transmission), _ptr(base_opd), _ptr(phase),
+                                             _ptr(basis_c), _ptr(coeffs_c), _ptr(wavenumber), _ptr(scale_out),
+                                             _ptr(norm), _ptr(weights_c), _ptr(delta_c), _ptr(field), _ptr(psf_bar),
+                                             _ptr(cbar), _ptr(scratch), scratch.numel(), _stream(dev)),
+                  "dlux_polypsf_batch_bwd")
+        return (cbar.reshape(cshape),) + (None,) * 13
 
 
 # --------------------------------------------------------------------------- basis

@@ -376,6 +376,47 @@ class ParametricLayeredOpticalSystem(ParametricOpticalSystem, LayeredOpticalSyst
                                          cont(T), k, scale_out, norm, self.wf_npixels,
                                          npix, normalise, self.precision)
 
+
+    def propagate_batch(self, coefficients, wavelengths, offset=None, weights=None, layer=None):
+        """A batch of parameter sets through one fused call: ``coefficients`` [B, nz...] are B settings of the
+        coefficients of one OPD basis layer of the stack (the only ``BasisLayer`` with effect "opd", or the
+        one named by ``layer``); returns the B polychromatic PSFs [B, M, M].  Gradients flow to
+        ``coefficients`` item by item.  This is the reference's ``vmap`` over parameter sets of
+        ``OpticalSystem.propagate`` (optical_systems.py:147-223, docs/mask_design.md:454-488)."""
+        cands = [(k, l) for k, l in self.layers.items() if isinstance(l, BasisLayer) and l.effect == "opd"]
+        if layer is not None:
+            cands = [(k, l) for k, l in cands if k == layer or l is layer]
+        if len(cands) != 1:
+            raise ValueError("propagate_batch needs exactly one OPD basis layer (name it with layer=...)")
+        blayer = cands[0][1]
+        if not self._can_fuse():
+            raise ValueError("layer stack is not pupil-only; propagate the batch in a loop with fused=False")
+        dev = self.device
+        coefficients = coefficients if torch.is_tensor(coefficients) else torch.as_tensor(
+            np.asarray(coefficients, dtype=np.float32), device=dev)
+        if tuple(coefficients.shape[1:]) != tuple(blayer.coefficients.shape):
+            raise ValueError("coefficients must be [B, *layer.coefficients.shape]")
+        saved = blayer.coefficients
+        try:                      # the other layers' (T, opd, phase): this layer contributes a zero OPD
+            blayer.coefficients = torch.zeros_like(saved)
+            T, opd, phase, normalise = self._fusable()
+        finally:
+            blayer.coefficients = saved
+        wavelengths = np.atleast_1d(_np32(wavelengths))
+        L = len(wavelengths)
+        weights = np.full(L, 1.0 / L, np.float32) if weights is None else np.atleast_1d(_np32(weights))
+        if weights.shape != wavelengths.shape:
+            raise ValueError("Wavelength and weight shape mismatch")
+        npix, scale_out, norm, k, wl_dev = self._geometry(wavelengths)
+        delta = None
+        if offset is not None:
+            off = self._upload(np.asarray(_np32(offset)).reshape(1, 2))
+            delta = ((off[:, None, :] * self.diameter) / wl_dev[None, :, None]).reshape(L, 2).contiguous()
+        cont = lambda t: None if t is None else t.contiguous()
+        return ops.PolyPSFBatchFunction.apply(coefficients, blayer.basis, cont(opd), cont(phase), cont(T),
+                                              self._upload(weights), delta, k, scale_out, norm, self.wf_npixels,
+                                              npix, normalise, self.precision)
+
     def _propagate(self, wavelengths, offset, weights, return_wf):
         if self.fused and not return_wf and self._can_fuse():
             off = offset if torch.is_tensor(offset) else _np32(offset)

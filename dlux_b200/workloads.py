@@ -80,6 +80,31 @@ def config(name: str):
         out = dict(wf_npixels=n, diameter=d, psf_npixels=128, psf_pixel_scale=0.0656, oversample=4,
                    wavelengths=np.linspace(4.1e-6, 4.5e-6, 64).astype(np.float32),
                    coefficients=rng.standard_normal(21).astype(np.float32))
+    elif name == "c4":    # Toliman-like diffractive pupil: 2048 px, binary 0/pi phase mask, 1000 stars x 64 wavelengths
+        rng = np.random.default_rng(3)
+        n, d = 2048, 0.125
+        T = _circ(n, d)
+        f = np.fft.fft2(rng.standard_normal((n, n)))
+        f[40:-40, :] = 0
+        f[:, 40:-40] = 0
+        phase = (np.pi * (np.fft.ifft2(f).real > 0)).astype(np.float32)
+        M, ps = 256, 0.7                                   # arcsec / pixel: ~ Nyquist / 1.5 at 585 nm
+        fov = M * ps * np.pi / 648000.0
+        out = dict(wf_npixels=n, diameter=d, psf_npixels=M, psf_pixel_scale=ps, oversample=1,
+                   wavelengths=np.linspace(530e-9, 640e-9, 64).astype(np.float32), phase=phase,
+                   coefficients=np.zeros(1, np.float32), n_stars=1000)
+        basis = np.zeros((1, n, n), np.float32)
+        stars_pos = (rng.uniform(-0.35, 0.35, (1000, 2)) * fov).astype(np.float32)
+        stars_flux = (10 ** rng.uniform(0, 3, 1000)).astype(np.float32)
+    elif name == "c5":    # Fisher / mask-design sweep: 1024 -> 256, 32 wavelengths, 4096 perturbed coefficient vectors
+        rng = np.random.default_rng(4)
+        n, d = 1024, 1.0
+        T = _circ(n, d)
+        basis = _zernike_opd_basis(n, d, 10, T) * np.float32(1e-9)
+        fid = (20 * rng.standard_normal(10)).astype(np.float32)
+        out = dict(wf_npixels=n, diameter=d, psf_npixels=256, psf_pixel_scale=0.05, oversample=1,
+                   wavelengths=np.linspace(0.9e-6, 1.1e-6, 32).astype(np.float32), coefficients=fid,
+                   perturbations=(fid[None, :] + 5.0 * rng.standard_normal((4096, 10))).astype(np.float32))
     elif name == "tiny":  # smoke-test size
         rng = np.random.default_rng(9)
         n, d = 128, 1.0
@@ -96,7 +121,9 @@ def config(name: str):
                weights=np.full(L, 1.0 / L, np.float32),
                positions=np.zeros((1, 2), np.float32), fluxes=np.ones(1, np.float32),
                G=rng.standard_normal((M, M)).astype(np.float32), name=name)
+    if name == "c4":
+        out.update(positions=stars_pos, fluxes=stars_flux)
     return out
 
 
-CONFIGS = ("c1", "c2", "c3", "tiny")
+CONFIGS = ("c1", "c2", "c3", "c4", "c5", "tiny")

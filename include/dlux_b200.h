@@ -133,7 +133,7 @@ typedef struct {
   int32_t n_pupil;    /* N = wf_npixels */
   int32_t n_psf;      /* M = psf_npixels * oversample */
   int32_t n_wavels;   /* L */
-  int32_t n_sources;  /* S (items are source-major: item = s * L + l) */
+  int32_t n_sources;  /* S ([S, L] operands are source-major: index s * L + l; work is ordered wavelength-major) */
   int32_t normalise;  /* Optic(normalise=True) */
   int32_t precision;  /* DLUX_PREC_* */
   int32_t save_field; /* fwd: also write E [S*L, M, M] c64 (the VJP residual) */
@@ -152,7 +152,8 @@ DLUX_API int dlux_polypsf_fwd(const dlux_polypsf_desc* desc,
                      const float* weights,      /* [S, L] flux * spectral weight */
                      const float* delta_xy,     /* [S, L, 2] fringes, or NULL */
                      float* psf,                /* [M, M] (overwritten) */
-                     void* field,               /* c64 [S*L, M, M] if save_field else NULL */
+                     void* field,               /* c64 [S*L, M, M] if save_field else NULL: opaque VJP residual
+                                                   (stored in the library's processing order) */
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
 /* VJP of dlux_polypsf_fwd w.r.t. opd (-> Zernike coefficients through
@@ -173,6 +174,54 @@ DLUX_API int dlux_polypsf_bwd(const dlux_polypsf_desc* desc,
                      float* transmission_bar,  /* [N, N] or NULL (incl. the power-normalisation term) */
                      float* scale_bar,         /* [S, L] or NULL: d/d scale_out (two extra adjoint MFTs) */
                      float* wavenumber_bar,    /* [S, L] or NULL: d/d wavenumber through exp(i k opd) only */
+                     void* scratch, size_t scratch_bytes, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------
+ * Parameter-batched fused PSF: B coefficient vectors of one OPD basis, each giving its own
+ * polychromatic PSF (and, backward, its own coefficient gradient).  This is what the reference gets
+ * from vmapping OpticalSystem.propagate / jax.grad over a batch of parameter sets
+ * (docs/mask_design.md:454-488, optical_systems.py:213-216; BASELINE config 5):
+ *   opd_b  = base_opd + sum_z coeffs[b, z] * basis[z]          (utils/math.py:177-196, fused in)
+ *   psf[b] = sum_l w[l] |norm_l A_y^T (amp T exp(i (k_l opd_b + phase))) A_x|^2
+ * Outputs are per batch element: nothing is summed over b, so a batch sharded over GPUs needs no
+ * collective.  Items are batch-major (item = b * L + l) and are processed in chunks of whole batch
+ * elements inside the caller's scratch buffer.
+ * -------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_pupil;    /* N */
+  int32_t n_psf;      /* M */
+  int32_t n_wavels;   /* L */
+  int32_t n_batch;    /* B parameter sets */
+  int32_t n_basis;    /* nz */
+  int32_t normalise;
+  int32_t precision;  /* DLUX_PREC_* */
+  int32_t save_field; /* fwd: also write E [B*L, M, M] c64 (the VJP residual) */
+} dlux_polypsf_batch_desc;
+
+DLUX_API size_t dlux_polypsf_batch_scratch_bytes(const dlux_polypsf_batch_desc* desc);
+
+DLUX_API int dlux_polypsf_batch_fwd(const dlux_polypsf_batch_desc* desc,
+                     const float* transmission, /* [N, N] or NULL */
+                     const float* base_opd,     /* [N, N] or NULL: OPD of the other layers */
+                     const float* phase,        /* [N, N] or NULL */
+                     const float* basis,        /* [nz, N, N] */
+                     const float* coeffs,       /* [B, nz] */
+                     const float* wavenumber,   /* [L] */
+                     const float* scale_out,    /* [L] */
+                     const float* norm,         /* [L] */
+                     const float* weights,      /* [L] */
+                     const float* delta_xy,     /* [L, 2] or NULL */
+                     float* psf,                /* [B, M, M] */
+                     void* field,               /* c64 [B*L, M, M] if save_field else NULL */
+                     void* scratch, size_t scratch_bytes, void* cuda_stream);
+
+DLUX_API int dlux_polypsf_batch_bwd(const dlux_polypsf_batch_desc* desc,
+                     const float* transmission, const float* base_opd, const float* phase,
+                     const float* basis, const float* coeffs, const float* wavenumber,
+                     const float* scale_out, const float* norm, const float* weights, const float* delta_xy,
+                     const void* field,         /* c64 [B*L, M, M] from fwd */
+                     const float* psf_bar,      /* [B, M, M] */
+                     float* coeff_bar,          /* [B, nz] (overwritten) */
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------
