@@ -51,6 +51,7 @@ SIGNATURES = {
     "dlux_polypsf_scratch_bytes": (C.c_size_t, [C.POINTER(PolyPsfDesc)]),
     "dlux_polypsf_fwd": (C.c_int, [C.POINTER(PolyPsfDesc)] + [_P] * 10 + [_P, C.c_size_t, _P]),
     "dlux_polypsf_bwd": (C.c_int, [C.POINTER(PolyPsfDesc)] + [_P] * 17 + [_P, C.c_size_t, _P]),
+    "dlux_polypsf_hvp": (C.c_int, [C.POINTER(PolyPsfDesc)] + [_P] * 13 + [_P, C.c_size_t, _P]),
     "dlux_polypsf_batch_scratch_bytes": (C.c_size_t, [C.POINTER(PolyPsfBatchDesc)]),
     "dlux_polypsf_batch_fwd": (C.c_int, [C.POINTER(PolyPsfBatchDesc)] + [_P] * 12 + [_P, C.c_size_t, _P]),
     "dlux_polypsf_batch_bwd": (C.c_int, [C.POINTER(PolyPsfBatchDesc)] + [_P] * 13 + [_P, C.c_size_t, _P]),

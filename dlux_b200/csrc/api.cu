@@ -670,6 +670,87 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
 }
 
 
+
+int dlux_polypsf_hvp(const dlux_polypsf_desc* d, const float* T, const float* opd, const float* phase,
+                     const float* wavenumber, const float* scale_out, const float* norm, const float* weights,
+                     const float* delta_xy, const void* field, const float* psf_bar, const float* opd_tangent,
+                     float* psf_tan, float* opd_hv, void* scratch, size_t scratch_bytes, void* cuda_stream) {
+  int rc = check_poly_desc(d);
+  if (rc != DLUX_OK) return rc;
+  if (!wavenumber || !scale_out || !weights || !field || !psf_bar || !opd_tangent || !scratch) return DLUX_ERR_ARG;
+  if (!psf_tan && !opd_hv) return DLUX_ERR_ARG;
+  if (((uintptr_t)field | (uintptr_t)scratch) & 15) return DLUX_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  PolyScratch s;
+  bool ok = true;
+  carve_poly(d, scratch, scratch_bytes, &s, &ok);
+  if (!ok) return DLUX_ERR_SCRATCH;
+  const int N = d->n_pupil, M = d->n_psf, L = d->n_wavels;
+  const int items = d->n_sources * L;
+  const size_t npix = (size_t)N * N, mpix = (size_t)M * M;
+  rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, false, st);
+  if (rc) return rc;
+  // tangent pupil planes dP_l = i k_l V P_l (they take the place of the P planes)
+  rc = launch_pupil(N, L, T, opd, phase, wavenumber, s.amp_scale, s.p_pl, st, 1, opd_tangent);
+  if (rc) return rc;
+  const float fwd2pi = (float)(-2.0 * 3.14159265358979323846), adj2pi = -fwd2pi;
+  const float a0 = 1.0f / (float)((long long)N * N);
+  for (int b0 = 0; b0 < items; b0 += s.chunk) {
+    const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
+    const float2* E = (const float2*)field + (size_t)b0 * mpix;
+    rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? s.delta_item + 2 * (size_t)b0 : nullptr, 1, s.xin,
+                       s.uout, st);
+    if (rc) return rc;
+    // dE = MFT(dP) per item
+    GemmParams g{};
+    fill_stage(g, false, 0, N, M, c, s.xin, s.uout, fwd2pi);
+    g.item_data = s.item_l + b0;
+    g.n_data = L;
+    g.a = s.p_pl;
+    g.out = s.mid_pl;
+    g.mode = EPI_PLANES;
+    rc = run_gemm(g, d->precision, st);
+    if (rc) return rc;
+    GemmParams h{};
+    fill_stage(h, false, 1, N, M, c, s.xin, s.uout, fwd2pi);
+    h.a = s.mid_pl;
+    h.mode = EPI_C64;
+    h.scale = s.norm_item + b0;
+    h.out_c64 = s.fbuf;
+    rc = run_gemm(h, d->precision, st);
+    if (rc) return rc;
+    if (psf_tan) {
+      rc = launch_psf_tangent(mpix, c, E, s.fbuf, s.w_item + b0, psf_tan, b0 > 0, st);
+      if (rc) return rc;
+    }
+    if (!opd_hv) continue;
+    // two adjoint passes: Q' = A^H(2 w G dE) and Q = A^H(2 w G E)
+    for (int pass = 0; pass < 2; ++pass) {
+      rc = launch_cotangent(M, c, pass == 0 ? s.fbuf : E, psf_bar, s.w_item + b0, s.ebar_pl, nullptr, -1, st);
+      if (rc) return rc;
+      GemmParams ga{};
+      fill_stage(ga, true, 0, N, M, c, s.xin, s.uout, adj2pi);
+      ga.a = s.ebar_pl;
+      ga.out = s.mid_pl;
+      ga.mode = EPI_PLANES;
+      rc = run_gemm(ga, d->precision, st);
+      if (rc) return rc;
+      GemmParams ha{};
+      fill_stage(ha, true, 1, N, M, c, s.xin, s.uout, adj2pi);
+      ha.a = s.mid_pl;
+      ha.mode = EPI_C64;
+      ha.scale = s.norm_item + b0;
+      ha.out_c64 = s.qbuf;
+      rc = run_gemm(ha, d->precision, st);
+      if (rc) return rc;
+      rc = launch_hv_reduce(npix, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0, opd_tangent, opd_hv, pass,
+                            (b0 > 0 || pass > 0) ? 1 : 0, st);
+      if (rc) return rc;
+    }
+  }
+  return DLUX_OK;
+}
+
 size_t dlux_polypsf_batch_scratch_bytes(const dlux_polypsf_batch_desc* desc) {
   if (check_batch_desc(desc) != DLUX_OK) return 0;
   BatchScratch s;

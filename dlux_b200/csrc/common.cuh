@@ -162,7 +162,7 @@ int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const 
 int launch_split_c64(const float2* in, size_t n_mat_rows, int cols, const PlaneSet& out, cudaStream_t st);
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
                  const float* wavenumber, const float* amp_scale /*device scalar*/,
-                 const PlaneSet& out, cudaStream_t st, int n_batch = 1);
+                 const PlaneSet& out, cudaStream_t st, int n_batch = 1, const float* tangent = nullptr);
 int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStream_t st);
 // `weight_axis`: -1 none; 0 / 1: multiply by the output-pixel index (col / row) minus (M-1)/2,
 // the derivative of the output coordinate w.r.t. scale_out
@@ -189,6 +189,11 @@ int launch_grad_reduce(size_t npix, int n_items, const float2* q, const float* k
                        const float* opd, const float* phase, const float* amp_scale, float a0,
                        float* opd_bar, float* phase_bar, float* t_bar, int accumulate, cudaStream_t st,
                        int n_batch = 1);
+int launch_psf_tangent(size_t npix, int n_items, const float2* field, const float2* dfield, const float* w,
+                       float* out, int accumulate, cudaStream_t st);
+int launch_hv_reduce(size_t npix, int n_items, const float2* q, const float* k, const float* T, const float* opd,
+                     const float* phase, const float* amp_scale, float a0, const float* V, float* out, int mode,
+                     int accumulate, cudaStream_t st);
 // T_bar -= (sum_i T_i T_bar_i) * amp^2 * a0^2 * T   (the power-normalisation term; `work` = 256 doubles)
 int launch_tbar_finalize(size_t npix, const float* T, const float* amp_scale, float a0, float* t_bar,
                          double* work, cudaStream_t st);

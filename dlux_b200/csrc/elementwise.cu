@@ -142,7 +142,7 @@ int launch_power(int N, const float* T, int normalise, float* amp_scale, cudaStr
 // row for ALL wavelengths: T / opd / phase are read once and the L planes leave as 16-byte stores.
 __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const float* __restrict__ opd,
                              const float* __restrict__ phase, const float* __restrict__ wavenumber,
-                             const float* __restrict__ amp_scale, PlaneSet out) {
+                             const float* __restrict__ amp_scale, PlaneSet out, const float* __restrict__ tangent) {
   // blockIdx.z = element of a parameter batch: its own OPD map [N, N] and its own L planes
   if (opd) opd += (size_t)blockIdx.z * N * N;
   out.hi[0] += (size_t)blockIdx.z * L * N * pitch4(N);
@@ -158,15 +158,16 @@ __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const fl
        gidx += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(gidx / groups_per_row);
     const int c = (int)(gidx - (size_t)r * groups_per_row) * 4;
-    float a[4], o[4], pc[4], ps[4];
+    float a[4], o[4], pc[4], ps[4], tv[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      a[e] = 0.0f; o[e] = 0.0f; pc[e] = 1.0f; ps[e] = 0.0f;
+      a[e] = 0.0f; o[e] = 0.0f; pc[e] = 1.0f; ps[e] = 0.0f; tv[e] = 0.0f;
       if (c + e < N) {
         const size_t i = (size_t)r * N + c + e;
         a[e] = T ? a0 * __ldg(T + i) : a0;
         if (opd) o[e] = __ldg(opd + i);
         if (phase) fast_sincos(__ldg(phase + i), &ps[e], &pc[e]);
+        if (tangent) tv[e] = __ldg(tangent + i);
       }
     }
     for (int l = l0; l < L; l += lstep) {
@@ -190,6 +191,11 @@ __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const fl
         }
         re[e] *= sc;
         im[e] *= sc;
+        if (tangent) {                    // dP = i k V P: the pupil tangent along an OPD direction V
+          const float kv = k * tv[e], r2 = -kv * im[e];
+          im[e] = kv * re[e];
+          re[e] = r2;
+        }
       }
       const size_t o4 = ((size_t)l * N + r) * p4 + c;
       *reinterpret_cast<float4*>(out.hi[0] + o4) = make_float4(re[0], re[1], re[2], re[3]);
@@ -200,12 +206,12 @@ __global__ void pupil_kernel(int N, int L, const float* __restrict__ T, const fl
 
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,
                  const float* wavenumber, const float* amp_scale, const PlaneSet& out, cudaStream_t st,
-                 int n_batch) {
+                 int n_batch, const float* tangent) {
   // 64 x 4 threads: x runs along the pixel groups, y splits the wavelengths four ways
   const int ly = L < 4 ? L : 4;
   dim3 block(64, ly);
   dim3 grid(grid_for((size_t)N * (pitch4(N) / 4), 64, n_batch > 1 ? 148 * 2 : 148 * 8), 1, n_batch);
-  pupil_kernel<<<grid, block, 0, st>>>(N, L, T, opd, phase, wavenumber, amp_scale, out);
+  pupil_kernel<<<grid, block, 0, st>>>(N, L, T, opd, phase, wavenumber, amp_scale, out, tangent);
   note_launch();
   return check_launch("pupil");
 }
@@ -437,6 +443,67 @@ int launch_grad_reduce(size_t npix, int n_items, const float2* q, const float* k
                                                                     accumulate);
   note_launch();
   return check_launch("grad_reduce");
+}
+
+
+// ---------------------------------------------------------------------------
+// Second order of the fused PSF w.r.t. the OPD (see dlux_polypsf_hvp).
+// psf_tan[i] (+)= sum_item 2 w[item] Re(conj(E[item][i]) dE[item][i])
+__global__ void psf_tangent_kernel(size_t npix, int n_items, const float2* __restrict__ field,
+                                   const float2* __restrict__ dfield, const float* __restrict__ w,
+                                   float* __restrict__ out, int accumulate) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = accumulate ? out[i] : 0.0f;
+#pragma unroll 4
+    for (int it = 0; it < n_items; ++it) {
+      const float2 e = field[(size_t)it * npix + i], d = dfield[(size_t)it * npix + i];
+      acc = fmaf(2.0f * __ldg(w + it), e.x * d.x + e.y * d.y, acc);
+    }
+    out[i] = acc;
+  }
+}
+
+int launch_psf_tangent(size_t npix, int n_items, const float2* field, const float2* dfield, const float* w,
+                       float* out, int accumulate, cudaStream_t st) {
+  psf_tangent_kernel<<<grid_for(npix, 128, 148 * 16), 128, 0, st>>>(npix, n_items, field, dfield, w, out, accumulate);
+  note_launch();
+  return check_launch("psf_tangent");
+}
+
+// mode 0: out[i] (+)= sum_item k Im(conj(P) Q[item])          (Q = adjoint of the tangent field's cotangent)
+// mode 1: out[i] (+)= -V[i] sum_item k^2 Re(conj(P) Q[item])  (Q = the first-order adjoint field)
+__global__ void hv_reduce_kernel(size_t npix, int n_items, const float2* __restrict__ q, const float* __restrict__ k,
+                                 const float* __restrict__ T, const float* __restrict__ opd,
+                                 const float* __restrict__ phase, const float* __restrict__ amp_scale, float a0,
+                                 const float* __restrict__ V, float* __restrict__ out, int mode, int accumulate) {
+  const float amp = a0 * amp_scale[0];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.0f;
+    const float t = T ? T[i] : 1.0f;
+    if (t != 0.0f) {
+      const float a = amp * t, o = opd ? opd[i] : 0.0f, ph = phase ? phase[i] : 0.0f;
+#pragma unroll 4
+      for (int it = 0; it < n_items; ++it) {
+        const float2 v = q[(size_t)it * npix + i];
+        const float kw = __ldg(k + it);
+        float sn, cs;
+        fast_sincos(__fmul_rn(kw, o) + ph, &sn, &cs);
+        if (mode == 0) acc = fmaf(kw, a * (cs * v.y - sn * v.x), acc);
+        else acc = fmaf(kw * kw, a * (cs * v.x + sn * v.y), acc);
+      }
+      if (mode == 1) acc = -V[i] * acc;
+    }
+    out[i] = accumulate ? out[i] + acc : acc;
+  }
+}
+
+int launch_hv_reduce(size_t npix, int n_items, const float2* q, const float* k, const float* T, const float* opd,
+                     const float* phase, const float* amp_scale, float a0, const float* V, float* out, int mode,
+                     int accumulate, cudaStream_t st) {
+  hv_reduce_kernel<<<grid_for(npix, 128, 148 * 16), 128, 0, st>>>(npix, n_items, q, k, T, opd, phase, amp_scale, a0, V,
+                                                                  out, mode, accumulate);
+  note_launch();
+  return check_launch("hv_reduce");
 }
 
 // Power normalisation (wavefronts.py:418-424) makes amp = (sum_j (a0 T_j)^2)^(-1/2) depend on

@@ -301,6 +301,56 @@ def polypsf_bwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, 
     return opd_bar, phase_bar, w_bar, d_bar, t_bar, s_bar, k_bar
 
 
+def polypsf_hvp(transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field, psf_bar,
+                opd_tangent, n_pupil, n_psf, normalise=True, precision=None, want_psf_tan=True, want_opd_hv=True):
+    """(psf_tan, opd_hv) of ``dlux_polypsf_hvp``: the two cotangents of (opd, psf_bar) -> opd_bar."""
+    lib = _lib.load()
+    dev = wavenumber.device
+    L = wavenumber.numel()
+    weights = weights.reshape(-1, L).contiguous()
+    S = weights.shape[0]
+    desc = _poly_desc(n_pupil, n_psf, L, S, normalise, precision, True)
+    nbytes = lib.dlux_polypsf_scratch_bytes(C.byref(desc))
+    scratch = _get_scratch(dev, nbytes)
+    psf_tan = torch.empty((n_psf, n_psf), dtype=torch.float32, device=dev) if want_psf_tan else None
+    opd_hv = torch.empty((n_pupil, n_pupil), dtype=torch.float32, device=dev) if want_opd_hv else None
+    with torch.cuda.device(dev):
+        check(lib.dlux_polypsf_hvp(C.byref(desc), _ptr(transmission), _ptr(opd), _ptr(phase), _ptr(wavenumber),
+                                   _ptr(scale_out), _ptr(norm), _ptr(weights), _ptr(delta_xy), _ptr(field),
+                                   _ptr(psf_bar.to(torch.float32).contiguous()),
+                                   _ptr(opd_tangent.to(torch.float32).contiguous()), _ptr(psf_tan), _ptr(opd_hv),
+                                   _ptr(scratch), scratch.numel(), _stream(dev)), "dlux_polypsf_hvp")
+    return psf_tan, opd_hv
+
+
+class PolyPSFGradFunction(torch.autograd.Function):
+    """opd_bar as a differentiable function of (opd, psf_bar): the node ``PolyPSFFunction.backward`` builds
+    under ``create_graph=True``.  Its own VJP is the fused second order (``dlux_polypsf_hvp``): the OPD
+    Hessian-vector product and the forward tangent of the image, so that ``torch.autograd.functional.hessian``
+    / Fisher matrices of a loss w.r.t. the basis coefficients run on the fused route (SURVEY 8f NEXT-1)."""
+
+    @staticmethod
+    def forward(ctx, opd, psf_bar, field, phase, weights, delta_xy, transmission, wavenumber, scale_out, norm,
+                n_pupil, n_psf, normalise, precision):
+        ctx.save_for_backward(opd, psf_bar)
+        ctx.consts = (field, phase, weights, delta_xy, transmission, wavenumber, scale_out, norm)
+        ctx.cfg = (n_pupil, n_psf, normalise, precision)
+        return polypsf_bwd(transmission, opd.detach(), phase, wavenumber, scale_out, norm, weights, delta_xy, field,
+                           psf_bar.detach(), n_pupil, n_psf, normalise, precision, want_opd=True)[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable     # third order is out of scope
+    def backward(ctx, v):
+        opd, psf_bar = ctx.saved_tensors
+        field, phase, weights, delta_xy, transmission, wavenumber, scale_out, norm = ctx.consts
+        n_pupil, n_psf, normalise, precision = ctx.cfg
+        want = ctx.needs_input_grad
+        psf_tan, opd_hv = polypsf_hvp(transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,
+                                      psf_bar, v, n_pupil, n_psf, normalise, precision, want_psf_tan=bool(want[1]),
+                                      want_opd_hv=bool(want[0]))
+        return (opd_hv, psf_tan) + (None,) * 12
+
+
 class PolyPSFFunction(torch.autograd.Function):
     """psf = sum_{s,l} w_sl |MFT_l(amp T exp(i(k_l opd + phase)))|^2 with gradients w.r.t.
     opd, phase, weights, the source offsets delta_xy, the transmission, the wavenumbers and the
@@ -322,13 +372,25 @@ class PolyPSFFunction(torch.autograd.Function):
         return psf
 
     @staticmethod
-    @torch.autograd.function.once_differentiable   # second order: use the layer-by-layer route (fused=False)
     def backward(ctx, psf_bar):
         it = iter(ctx.saved_tensors)
         opd, phase, weights, transmission, wavenumber, scale_out, norm, delta_xy, field = [
             next(it) if p else None for p in ctx.present]
         n_pupil, n_psf, normalise, precision, wshape = ctx.cfg
         want = ctx.needs_input_grad
+        if torch.is_grad_enabled() and (psf_bar.requires_grad or (opd is not None and opd.requires_grad)):
+            # create_graph=True: second order.  Fused for the OPD (-> basis coefficients); the other leaves
+            # take the layer-by-layer route
+            if any(want[i] for i in range(1, 8)) or opd is None:
+                raise NotImplementedError(
+                    "dlux_b200: fused second order is implemented w.r.t. the OPD / basis coefficients only; "
+                    "build the system with fused=False for Hessians w.r.t. other parameters")
+            det = lambda t: None if t is None else t.detach()
+            opd_bar = PolyPSFGradFunction.apply(opd, psf_bar, field, det(phase), det(weights), det(delta_xy),
+                                                det(transmission), det(wavenumber), det(scale_out), det(norm),
+                                                n_pupil, n_psf, normalise, precision)
+            return (opd_bar,) + (None,) * 11
+        psf_bar = psf_bar.detach()
         want_norm = bool(want[7])
         opd_bar, phase_bar, w_bar, d_bar, t_bar, s_bar, k_bar = polypsf_bwd(
             transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,

@@ -176,6 +176,25 @@ DLUX_API int dlux_polypsf_bwd(const dlux_polypsf_desc* desc,
                      float* wavenumber_bar,    /* [S, L] or NULL: d/d wavenumber through exp(i k opd) only */
                      void* scratch, size_t scratch_bytes, void* cuda_stream);
 
+/* Second order of the fused PSF w.r.t. the OPD, forward-over-reverse (what jax.hessian / zdx.hessian of a
+ * loss through OpticalSystem.propagate needs, docs/mask_design.md:480-488).  With L(opd) = <psf_bar, psf(opd)>,
+ * opd_bar(opd, psf_bar) its gradient (dlux_polypsf_bwd) and V a pupil-plane direction [N, N]:
+ *   psf_tan = (d psf / d opd) V                  = sum_{s,l} 2 w Re(conj(E) dE),   dE = MFT(i k V P)
+ *   opd_hv  = d/d opd <V, opd_bar(opd, psf_bar)> = sum_{s,l} k Im(conj(P) A^H(2 w psf_bar dE))
+ *                                                            - k^2 V Re(conj(P) A^H(2 w psf_bar E))
+ * i.e. the two cotangents of the map (opd, psf_bar) -> opd_bar: one more forward MFT and two adjoint MFTs
+ * per (source, wavelength), on the same kernels. */
+DLUX_API int dlux_polypsf_hvp(const dlux_polypsf_desc* desc,
+                     const float* transmission, const float* opd, const float* phase,
+                     const float* wavenumber, const float* scale_out, const float* norm,
+                     const float* weights, const float* delta_xy,
+                     const void* field,          /* c64 [S*L, M, M] from fwd */
+                     const float* psf_bar,       /* [M, M] */
+                     const float* opd_tangent,   /* V [N, N] */
+                     float* psf_tan,             /* [M, M] or NULL */
+                     float* opd_hv,              /* [N, N] or NULL */
+                     void* scratch, size_t scratch_bytes, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------
  * Parameter-batched fused PSF: B coefficient vectors of one OPD basis, each giving its own
  * polychromatic PSF (and, backward, its own coefficient gradient).  This is what the reference gets

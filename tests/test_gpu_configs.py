@@ -235,3 +235,64 @@ def test_geometry_gradients_float64_autograd(dev):
     out["wavelengths"] = rel_l2(wl.grad.cpu().numpy(), wl64.grad.numpy())
     print("geometry gradient errors vs float64 autograd", out)
     assert all(v < TOL for v in out.values()), out
+
+
+def test_fused_second_order_hessian(dev):
+    """NEXT-1, second order on the FUSED route: torch.autograd.functional.hessian of a nonlinear image loss w.r.t. the
+    basis coefficients through dlux_polypsf_fwd / _bwd / _hvp, against the float64 Hessian of the twin; and the same
+    Hessian from the layer-by-layer route."""
+    import dlux_b200 as dl
+    from conftest import check
+    from test_gpu_parity import _optics_dict
+    N, M, nz = 48, 24, 3
+    od = _optics_dict(N, M, nz, 21)
+    od["basis"] = od["basis"] * np.float32(4.0)
+    wls = np.array([0.95e-6, 1.05e-6], np.float32)
+    w = np.array([0.5, 0.5], np.float32)
+    off = np.array([1.0e-7, -0.5e-7], np.float32)
+    target = np.random.default_rng(22).uniform(0.5, 1.5, (M, M))
+    basis_d = torch.as_tensor(od["basis"], device=dev)
+
+    def loss_gpu(fused):
+        def f(c):
+            layer = dl.BasisOptic(basis_d, od["transmission"], c, normalise=True, effect="opd", device=dev)
+            sys_ = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, 0.05, device=dev, fused=fused)
+            psf = sys_.propagate(wls, off, w)
+            return ((psf * 1e3 - torch.as_tensor(target.astype(np.float32), device=dev)) ** 2).sum()
+        return f
+
+    def loss_ref(c):
+        psf = torch_twin.poly_psf(od["transmission"], None, wls, w, diameter=1.0, psf_npixels=M,
+                                  pixel_scale_rad=O.arcsec2rad(0.05), offset=off, basis=od["basis"], coefficients=c,
+                                  dtype=np.float64)
+        return ((psf * 1e3 - torch.tensor(target)) ** 2).sum()
+
+    c0 = torch.as_tensor(od["coefficients"], device=dev)
+    Href = torch.autograd.functional.hessian(loss_ref, torch.tensor(od["coefficients"], dtype=torch.float64)).numpy()
+    H = torch.autograd.functional.hessian(loss_gpu(True), c0).cpu().numpy().astype(np.float64)
+    check("fused hessian symmetry", rel_l2(H, H.T), TOL)
+    check("fused hessian vs float64 twin", rel_l2(H, Href), TOL)
+    H2 = torch.autograd.functional.hessian(loss_gpu(False), c0).cpu().numpy().astype(np.float64)
+    check("fused vs layer-route hessian", rel_l2(H, H2), TOL)
+    # three stars: the sum over sources inside the second order
+    import dlux_b200 as dl2
+    pos = np.array([[1e-7, -2e-7], [-3e-7, 0.5e-7], [0.0, 0.0]], np.float32)
+    flux = np.array([3.0, 0.25, 1.0], np.float32)
+
+    def loss_stars(c):
+        layer = dl.BasisOptic(basis_d, od["transmission"], c, normalise=True, effect="opd", device=dev)
+        sys_ = dl.AngularOpticalSystem(N, 1.0, [("a", layer)], M, 0.05, device=dev)
+        psf = sys_.model(dl.PointSources(wls, pos, flux, weights=w))
+        return ((psf * 1e3 - torch.as_tensor(target.astype(np.float32), device=dev)) ** 2).sum()
+
+    def loss_stars_ref(c):
+        tot = 0.0
+        for s_ in range(3):
+            tot = tot + torch_twin.poly_psf(od["transmission"], None, wls, w.astype(np.float64) * float(flux[s_]),
+                                            diameter=1.0, psf_npixels=M, pixel_scale_rad=O.arcsec2rad(0.05),
+                                            offset=pos[s_], basis=od["basis"], coefficients=c, dtype=np.float64)
+        return ((tot * 1e3 - torch.tensor(target)) ** 2).sum()
+
+    Hs = torch.autograd.functional.hessian(loss_stars, c0).cpu().numpy().astype(np.float64)
+    Hsr = torch.autograd.functional.hessian(loss_stars_ref, torch.tensor(od["coefficients"], dtype=torch.float64)).numpy()
+    check("fused hessian, three stars", rel_l2(Hs, Hsr), TOL)
