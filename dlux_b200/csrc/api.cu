@@ -531,6 +531,11 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
   rc = poly_prologue(d, s, T, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, true, st);
   if (rc) return rc;
   const float sign2pi = (float)(-2.0 * 3.14159265358979323846);
+  // Forward-only calls (no VJP residual wanted) fuse |E|^2, the spectral weights and the sum over sources
+  // and wavelengths into the last contraction's epilogue (EPI_PSF): no complex field is written or re-read.
+  // (The tensor kernel's reduce-add stores need 16-byte image rows.)
+  const bool fuse_psf = !d->save_field && (M % 4) == 0 && getenv("DLUX_B200_NO_EPI_PSF") == nullptr;
+  if (fuse_psf && (rc = launch_zero(psf, (size_t)M * M, st))) return rc;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
     rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? s.delta_item + 2 * (size_t)b0 : nullptr,
@@ -548,8 +553,16 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
     GemmParams h{};
     fill_stage(h, false, 1, N, M, c, s.xin, s.uout, sign2pi);
     h.a = s.mid_pl;
-    h.mode = EPI_C64;
     h.scale = s.norm_item + b0;
+    if (fuse_psf) {
+      h.mode = EPI_PSF;
+      h.out_psf = psf;
+      h.item_w = s.w_item + b0;
+      rc = run_gemm(h, d->precision, st);
+      if (rc) return rc;
+      continue;
+    }
+    h.mode = EPI_C64;
     h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * M * M : s.fbuf;
     rc = run_gemm(h, d->precision, st);
     if (rc) return rc;

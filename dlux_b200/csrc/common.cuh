@@ -20,7 +20,8 @@ namespace dlux {
 // ---------------------------------------------------------------------------
 enum EpilogueMode : int {
   EPI_PLANES = 0,  // out planes [item][n][m]  (feeds the next stage)
-  EPI_C64 = 1      // out_c64[item][n][m]
+  EPI_C64 = 1,     // out_c64[item][n][m]
+  EPI_PSF = 2      // out_psf[n][m] += item_w[item] * |scale[item] * D|^2   (forward-only image: no field is written)
 };
 
 // Planar representation of a complex matrix Z[n][rows][K], 8 bytes per element: two float32 planes
@@ -55,6 +56,8 @@ struct GemmParams {
   int mode;
   PlaneSet out;          // EPI_PLANES: [n_items][n_out][rows] (pitch4 of rows)
   float2* out_c64;       // EPI_C64: [n_items][n_out][rows]
+  float* out_psf;        // EPI_PSF: [n_out][rows], accumulated over the items (zeroed by the caller)
+  const float* item_w;   // EPI_PSF: [n_items] spectral weight x flux
 };
 
 // round-to-nearest (ties away from zero) to tf32's 10 mantissa bits.  Equivalent to
@@ -139,6 +142,8 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int item, in
   if (p.mode == EPI_PLANES) {
     const size_t row = (size_t)item * p.n_out + n;
     plane_store(p.out, row * pitch4(p.rows) + m, re, im);
+  } else if (p.mode == EPI_PSF) {
+    atomicAdd(p.out_psf + (size_t)n * p.rows + m, __ldg(p.item_w + item) * (re * re + im * im));
   } else {  // EPI_C64
     p.out_c64[idx] = make_float2(re, im);
   }

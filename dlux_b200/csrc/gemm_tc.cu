@@ -430,6 +430,55 @@ __device__ __forceinline__ void tile_epilogue_tma(const GemmParams& p, int item,
   __syncwarp();
 }
 
+// EPI_PSF: the image itself, psf[n][m] += w |scale D|^2, through TMA REDUCE-add stores -- no complex field
+// leaves the chip (forward-only calls need none: optical_systems.py:213-223 / wavefronts.py:279 fused into
+// the last contraction).  The Re lanes stage w re^2 in one 16 x 16 float32 box, the Im lanes w im^2 in a
+// second one, and both are added onto the same tile of the image.  The additions of different items reach
+// memory in no fixed order (float32 sums differ in the last bits from run to run).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tile_epilogue_psf(const GemmParams& p, int item, int nq0, int m0, int lane,
+                                                  float (&tot)[BM], uint32_t stg0, const CUtensorMap* o_psf) {
+  const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
+  const float w = __ldg(p.item_w + item);
+  const int mmax = p.rows - m0;
+  const int j = lane >> 1, part = lane & 1;
+  const uint32_t sw64 = (uint32_t)((j >> 1) & 3);
+#pragma unroll
+  for (int s = 0; s < BM / 16; ++s) {
+    const int c0 = s * 16;
+    if (c0 >= mmax) break;
+    const uint32_t stg = stg0 + (s % STG_BUFS) * STG_SLICE_BYTES;
+    const uint32_t row = stg + part * 1024 + j * 64;
+    if (s >= STG_BUFS) {
+      if (lane == 0) bulk_wait_read_n(STG_BUFS - 1);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = tot[c0 + 4 * c + e] * sc;
+        v[e] = w * (a * a);
+      }
+      st_shared_v4(row + (((uint32_t)c ^ sw64) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
+                   __float_as_uint(v[2]), __float_as_uint(v[3]));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tma_reduce_add_2d(o_psf, stg, m0 + c0, nq0);
+      tma_reduce_add_2d(o_psf, stg + 1024, m0 + c0, nq0);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read();
+  __syncwarp();
+}
+
 // EPI_C64 through TMA stores (needs an even row length: the global row pitch must be a multiple
 // of 16 bytes).  The box of a warp and slice is 16 rows x 16 complex = 128-byte rows, SWIZZLE_128B;
 // the real lane of a row writes the even words, the imaginary lane the odd ones.  Four 2 KiB
@@ -607,7 +656,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     if (tp.g.mode == EPI_PLANES) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omap0));
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omap1));
-    } else if (tp.c64_tma) {
+    } else if (tp.c64_tma || tp.g.mode == EPI_PSF) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omapc));
     }
   }
@@ -828,6 +877,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       if (m0 < p.rows) {  // warp-uniform condition
         if (p.mode == EPI_PLANES)
           tile_epilogue_tma(p, item, nq0, m0, lane, tot, stg_addr, &omap0, &omap1);
+        else if (p.mode == EPI_PSF)
+          tile_epilogue_psf(p, item, nq0, m0, lane, tot, stg_addr, &omapc);
         else if (tp.c64_tma)
           tile_epilogue_c64_tma(p, item, nq0, m0, lane, tot, stg_addr, &omapc);
         else
@@ -1239,6 +1290,20 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       fprintf(stderr, "[dlux_b200] cuTensorMapEncodeTiled (complex64 output) failed: %d\n", (int)r);
+      return DLUX_ERR_CUDA;
+    }
+  }
+  if (p.mode == EPI_PSF) {   // the image as a 2-d float32 tensor [n_out][rows], box 16 x 16, target of reduce-adds
+    if (!p.out_psf || !p.item_w || (p.rows % 4) != 0 || ((uintptr_t)p.out_psf & 15)) return DLUX_ERR_ARG;
+    cuuint64_t dims[2] = {(cuuint64_t)p.rows, (cuuint64_t)p.n_out};
+    cuuint64_t strides[1] = {(cuuint64_t)p.rows * 4};
+    cuuint32_t box[2] = {16, 16};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = s.encode(&omapc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.out_psf, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[dlux_b200] cuTensorMapEncodeTiled (image) failed: %d\n", (int)r);
       return DLUX_ERR_CUDA;
     }
   }

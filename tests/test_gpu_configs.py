@@ -296,3 +296,39 @@ def test_fused_second_order_hessian(dev):
     Hs = torch.autograd.functional.hessian(loss_stars, c0).cpu().numpy().astype(np.float64)
     Hsr = torch.autograd.functional.hessian(loss_stars_ref, torch.tensor(od["coefficients"], dtype=torch.float64)).numpy()
     check("fused hessian, three stars", rel_l2(Hs, Hsr), TOL)
+
+
+def test_forward_only_image_epilogue(dev):
+    """Forward-only calls fuse |E|^2, the spectral weights and the source / wavelength sum into the last contraction
+    (EPI_PSF, TMA reduce-add): same image as the path that writes the field (the VJP residual) and reduces it, at
+    C3 size and at an odd-ish small size with several stars."""
+    import os
+    import dlux_b200 as dl
+    from conftest import check
+    from dlux_b200 import _lib, workloads
+    from test_gpu_parity import _optics_dict, _system
+    cfg = workloads.config("c3")
+    optics = _angular(cfg, dev, cfg["coefficients"])
+    src = dl.PointSource(cfg["wavelengths"], np.array([1e-7, -2e-7], np.float32), 1.5, weights=cfg["weights"])
+    n0 = _lib.launch_count()
+    fused = optics.model(src)
+    n_fused = _lib.launch_count() - n0
+    os.environ["DLUX_B200_NO_EPI_PSF"] = "1"
+    try:
+        n0 = _lib.launch_count()
+        plain = optics.model(src)
+        n_plain = _lib.launch_count() - n0
+    finally:
+        del os.environ["DLUX_B200_NO_EPI_PSF"]
+    assert n_plain == n_fused           # one zero-fill instead of one reduce kernel
+    check("EPI_PSF vs field + reduce (c3)", rel_l2(fused.cpu().numpy(), plain.cpu().numpy()), 1e-6)
+    od = _optics_dict(96, 44, 4, 2)
+    sys_ = _system(od, dev)
+    wls = np.linspace(0.95e-6, 1.05e-6, 3).astype(np.float32)
+    pos = np.array([[1e-7, -2e-7], [-3e-7, 0.5e-7], [0.0, 0.0]], np.float32)
+    flux = np.array([3.0, 0.25, 1.0], np.float32)
+    psf = sys_.model(dl.PointSources(wls, pos, flux))
+    check("EPI_PSF, three stars, M = 44", rel_l2(psf.cpu().numpy(), O.point_sources_model(od, wls, pos, flux)), TOL)
+    for prec in ("fp32",):
+        psf32 = _system(od, dev, True, prec).model(dl.PointSources(wls, pos, flux))
+        check("EPI_PSF on the fp32 CUDA-core path", rel_l2(psf32.cpu().numpy(), O.point_sources_model(od, wls, pos, flux)), TOL)
