@@ -18,6 +18,7 @@ from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, Cartesian
 from .sources import (BinarySource, PointResolvedSource, PointSource, PointSources, ResolvedSource,
                       Scene)
 from .wavefronts import CoordSpec, Wavefront
+from .graphs import GraphedValueAndGrad
 
 __version__ = "0.1.0"
 __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer",
@@ -27,4 +28,4 @@ __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "Aberrated
            "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "PSF", "DetectorLayer",
            "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",
-           "LayeredDetector", "Telescope"]
+           "LayeredDetector", "Telescope", "GraphedValueAndGrad"]
