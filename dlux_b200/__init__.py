@@ -5,7 +5,7 @@ propagator layer, ``Wavefront.propagate`` and ``OpticalSystem.propagate/model``.
 Importing the package does not need a GPU; calling any operator does, and there is no
 CPU fallback (the native library is loaded lazily and its absence is an error)."""
 from . import utils
-from .apertures import (CircularAperture, CompoundAperture, CoordTransform, MultiAperture,
+from .apertures import (AberratedAperture, CircularAperture, CompoundAperture, CoordTransform, MultiAperture,
                         RectangularAperture, RegPolyAperture, Spider, SquareAperture)
 from .psfs import PSF
 from .detectors import (AddConstant, ApplyJitter, ApplyPixelResponse, ApplySaturation, DetectorLayer,
@@ -25,7 +25,7 @@ __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "Aberrated
            "Tilt", "Normalise", "Optic", "BasisOptic", "MFT", "FFT", "CoordSpec", "BaseOpticalSystem",
            "OpticalSystem", "ParametricOpticalSystem",
            "LayeredOpticalSystem", "ParametricLayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
-           "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
+           "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "AberratedAperture", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "PSF", "DetectorLayer",
            "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",
            "LayeredDetector", "Telescope", "GraphedValueAndGrad"]

@@ -6,7 +6,8 @@ SquareAperture :314-387, RectangularAperture :390-472, RegPolyAperture :475-555,
 arithmetic is differentiable torch (dlux_b200/utils/geometry.py), and in the fused route the
 transmission cotangent of ``dlux_polypsf_bwd`` flows back through it, so radii, widths,
 translations, rotations ... given as CUDA tensors with requires_grad are fitted parameters.
-Not mirrored: AberratedAperture (Zernike generation is a setup-time producer, SURVEY 8 OUT)."""
+``AberratedAperture`` (:643-800) adds a Zernike OPD / phase / amplitude basis evaluated on the aperture's own
+(transformed, normalised) coordinates; circular apertures only (the polygon "polike" bases are not mirrored)."""
 from __future__ import annotations
 
 from collections import OrderedDict
@@ -18,7 +19,7 @@ from .layers import OpticalLayer
 from .utils import geometry as G
 
 __all__ = ["CoordTransform", "CircularAperture", "SquareAperture", "RectangularAperture",
-           "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture"]
+           "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "AberratedAperture"]
 
 
 def _param(v, shape, name):
@@ -87,6 +88,71 @@ class CircularAperture(_DynamicAperture):
 
     def _shape(self, coords, clip):
         return G.soft_circle(coords, self.radius, clip, self.occulting)
+
+
+    @property
+    def extent(self):                                   # apertures.py:306-307
+        return self.radius
+
+    nsides = 0
+
+
+class AberratedAperture(OpticalLayer):
+    """apertures.py:643-800: a dynamic aperture carrying Zernike aberrations generated on its own coordinates
+    (transformed, divided by the aperture extent), so that the basis follows the aperture when its position /
+    size are fitted.  ``effect`` in {"opd", "phase", "amplitude"}; coefficients may be a CUDA tensor with
+    requires_grad.  Runs on the fused route (transmission and OPD / phase producers) and layer by layer."""
+
+    def __init__(self, aperture, noll_inds, coefficients=None, effect: str = "opd"):
+        if isinstance(aperture, (_Composite, Spider)) or not isinstance(aperture, _DynamicAperture):
+            raise TypeError("AberratedApertures cannot contain Static, Compound or Multi Apertures (or spiders).")
+        if aperture.occulting:
+            raise TypeError("AberratedApertures cannot be occulting.")
+        if getattr(aperture, "nsides", None) != 0:
+            raise NotImplementedError("dlux_b200: AberratedAperture mirrors circular apertures (Zernike basis); "
+                                      "the polygon 'polike' bases are not implemented")
+        if effect not in ("opd", "phase", "amplitude"):
+            raise ValueError("effect must be 'opd', 'phase', or 'amplitude'.")
+        self.aperture = aperture
+        self.effect = effect
+        self.noll_inds = [int(j) for j in noll_inds]
+        if coefficients is None:
+            coefficients = np.zeros(len(self.noll_inds), np.float32)
+        self.coefficients = coefficients if torch.is_tensor(coefficients) else np.asarray(coefficients, np.float32)
+        if tuple(self.coefficients.shape) != (len(self.noll_inds),):
+            raise ValueError("coefficients must have one entry per Noll index")
+
+    @property
+    def normalise(self):
+        return self.aperture.normalise
+
+    def transmission(self, coords, pixel_scale):        # :732-733
+        return self.aperture.transmission(coords, pixel_scale)
+
+    def calc_basis(self, coords):                       # :735-752
+        from .utils.zernikes import zernike_basis_torch
+        if self.aperture.transformation is not None:
+            coords = self.aperture.transformation(coords)
+        ext = self.aperture.extent
+        ext = ext.to(coords.device, coords.dtype) if torch.is_tensor(ext) else float(ext)
+        return zernike_basis_torch(self.noll_inds, coords / ext)
+
+    def eval_basis(self, coords):                       # :754-771
+        c = self.coefficients
+        c = c.to(coords.device, coords.dtype) if torch.is_tensor(c) else torch.as_tensor(c, device=coords.device,
+                                                                                          dtype=coords.dtype)
+        return torch.tensordot(c, self.calc_basis(coords), dims=1)
+
+    def __call__(self, wavefront):                      # :773-800
+        wavefront = wavefront * self.transmission(wavefront.coordinates(), wavefront.pixel_scale)
+        if self.normalise:
+            wavefront = wavefront.normalise()
+        ab = self.eval_basis(wavefront.coordinates())
+        if self.effect == "phase":
+            return wavefront.add_phase(ab)
+        if self.effect == "opd":
+            return wavefront.add_opd(ab)
+        return wavefront * (1 + ab)
 
 
 class SquareAperture(_DynamicAperture):

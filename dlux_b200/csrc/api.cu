@@ -629,13 +629,13 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
       fill_stage(g, true, 0, N, M, c, s.xin, s.uout, sign2pi);
       g.a = s.ebar_pl;
       g.out = s.mid_pl;
-        g.mode = EPI_PLANES;
+      g.mode = EPI_PLANES;
       rc = run_gemm(g, d->precision, st);
       if (rc) return rc;
       GemmParams h{};
       fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
       h.a = s.mid_pl;
-        h.mode = EPI_C64;
+      h.mode = EPI_C64;
       h.scale = s.norm_item + b0;
       h.out_c64 = s.qbuf;
       rc = run_gemm(h, d->precision, st);
@@ -647,19 +647,12 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
         if (rc) return rc;
         continue;
       }
-      if (opd_bar || phase_bar || transmission_bar) {
-        rc = launch_grad_reduce((size_t)N * N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
-                                opd_bar, phase_bar, transmission_bar, b0 > 0, st);
-        if (rc) return rc;
-      }
-      if (delta_bar) {
-        rc = launch_pos_grad(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
-                             delta_bar + 2 * (size_t)b0, 0, st);
-        if (rc) return rc;
-      }
-      if (wavenumber_bar && opd) {
-        rc = launch_pos_grad(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0,
-                             wavenumber_bar + b0, 3, st);
+      // every pupil-plane cotangent of pass 0 from ONE read of Q: opd / phase / transmission gradients summed
+      // over the items, source-offset and wavenumber gradients per item
+      if (opd_bar || phase_bar || transmission_bar || delta_bar || (wavenumber_bar && opd)) {
+        rc = launch_q_reduce(N, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0, opd_bar, phase_bar,
+                             transmission_bar, b0 > 0, delta_bar ? delta_bar + 2 * (size_t)b0 : nullptr,
+                             (wavenumber_bar && opd) ? wavenumber_bar + b0 : nullptr, st);
         if (rc) return rc;
       }
     }

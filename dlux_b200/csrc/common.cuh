@@ -199,6 +199,9 @@ int launch_psf_tangent(size_t npix, int n_items, const float2* field, const floa
 int launch_hv_reduce(size_t npix, int n_items, const float2* q, const float* k, const float* T, const float* opd,
                      const float* phase, const float* amp_scale, float a0, const float* V, float* out, int mode,
                      int accumulate, cudaStream_t st);
+int launch_q_reduce(int N, int n_items, const float2* q, const float* k, const float* T, const float* opd,
+                    const float* phase, const float* amp_scale, float a0, float* opd_bar, float* phase_bar,
+                    float* t_bar, int accumulate, float* dbar_item, float* kbar_item, cudaStream_t st);
 // T_bar -= (sum_i T_i T_bar_i) * amp^2 * a0^2 * T   (the power-normalisation term; `work` = 256 doubles)
 int launch_tbar_finalize(size_t npix, const float* T, const float* amp_scale, float a0, float* t_bar,
                          double* work, cudaStream_t st);

@@ -506,6 +506,120 @@ int launch_hv_reduce(size_t npix, int n_items, const float2* q, const float* k, 
   return check_launch("hv_reduce");
 }
 
+
+// ---------------------------------------------------------------------------
+// One pass over the adjoint fields Q for every pupil-plane cotangent of the fused backward: the phase-like
+// gradients summed over items (grad_reduce_kernel's job) AND the per-item inner products that give the
+// source-offset and wavenumber gradients (pos_grad_kernel's job).  Q is the largest array of the backward
+// pass (8 N^2 bytes per (source, wavelength): 137 GB per step at 2048 px, 64 stars x 64 wavelengths), so
+// reading it once instead of two or three times is what matters.  Items arrive wavelength-major, so the
+// pupil phasor's sincos is re-evaluated only when the wavenumber changes.
+__global__ void q_reduce_kernel(int N, int n_items, const float2* __restrict__ q, const float* __restrict__ k,
+                                const float* __restrict__ T, const float* __restrict__ opd,
+                                const float* __restrict__ phase, const float* __restrict__ amp_scale, float a0,
+                                float* __restrict__ opd_bar, float* __restrict__ phase_bar, float* __restrict__ t_bar,
+                                int accumulate, float* __restrict__ dbar_item, float* __restrict__ kbar_item) {
+  extern __shared__ float sm[];          // [n_items][3]: sum x g, sum y g, sum opd g of this block
+  const bool per_item = dbar_item != nullptr || kbar_item != nullptr;
+  if (per_item) {
+    for (int i = threadIdx.x; i < 3 * n_items; i += blockDim.x) sm[i] = 0.0f;
+    __syncthreads();
+  }
+  const size_t npix = (size_t)N * N;
+  const float amp = a0 * amp_scale[0];
+  const float half = 0.5f * (float)(N - 1), inv = 1.0f / (float)N;
+  const int lane = threadIdx.x & 31;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t rounds = (npix + stride - 1) / stride;
+  for (size_t rd = 0; rd < rounds; ++rd) {
+    const size_t i = rd * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < npix;
+    const float t = in ? (T ? T[i] : 1.0f) : 0.0f;
+    const bool live = in && (t != 0.0f || t_bar != nullptr);   // blocked pixels only matter for the transmission gradient
+    if (__ballot_sync(0xffffffffu, live) == 0u) {
+      if (in && !accumulate) {
+        if (opd_bar) opd_bar[i] = 0.0f;
+        if (phase_bar) phase_bar[i] = 0.0f;
+      }
+      continue;
+    }
+    float ao = 0.0f, ap = 0.0f, at = 0.0f;
+    if (in && accumulate) {
+      if (opd_bar) ao = opd_bar[i];
+      if (phase_bar) ap = phase_bar[i];
+      if (t_bar) at = t_bar[i];
+    }
+    const float a = amp * t;
+    const float o = (in && opd) ? opd[i] : 0.0f;
+    const float ph = (in && phase) ? phase[i] : 0.0f;
+    const int r = (int)(i / N), c = (int)(i - (size_t)r * N);
+    const float xc = ((float)c - half) * inv, yc = ((float)r - half) * inv;
+    float kprev = 0.0f, sn = 0.0f, cs = 1.0f;
+    bool have = false;
+    for (int it = 0; it < n_items; ++it) {
+      const float kw = __ldg(k + it);
+      if (!have || kw != kprev) {
+        fast_sincos(__fmul_rn(kw, o) + ph, &sn, &cs);
+        kprev = kw;
+        have = true;
+      }
+      float2 v = make_float2(0.0f, 0.0f);
+      if (live) v = q[(size_t)it * npix + i];
+      const float g = a * (cs * v.y - sn * v.x);          // Im(conj(P) Q)
+      ao = fmaf(kw, g, ao);
+      ap += g;
+      at = fmaf(amp, cs * v.x + sn * v.y, at);            // Re(conj(Q) dP/dT), direct term
+      if (per_item) {
+        float sx = xc * g, sy = yc * g, so = o * g;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, d);
+          sy += __shfl_xor_sync(0xffffffffu, sy, d);
+          so += __shfl_xor_sync(0xffffffffu, so, d);
+        }
+        if (lane == 0) {
+          atomicAdd(sm + 3 * it, sx);
+          atomicAdd(sm + 3 * it + 1, sy);
+          atomicAdd(sm + 3 * it + 2, so);
+        }
+      }
+    }
+    if (in) {
+      if (opd_bar) opd_bar[i] = ao;
+      if (phase_bar) phase_bar[i] = ap;
+      if (t_bar) t_bar[i] = at;
+    }
+  }
+  if (per_item) {
+    __syncthreads();
+    const float two_pi = 6.283185307179586f;
+    for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
+      if (dbar_item) {
+        atomicAdd(dbar_item + 2 * it, two_pi * sm[3 * it]);
+        atomicAdd(dbar_item + 2 * it + 1, two_pi * sm[3 * it + 1]);
+      }
+      if (kbar_item) atomicAdd(kbar_item + it, sm[3 * it + 2]);
+    }
+  }
+}
+
+int launch_q_reduce(int N, int n_items, const float2* q, const float* k, const float* T, const float* opd,
+                    const float* phase, const float* amp_scale, float a0, float* opd_bar, float* phase_bar,
+                    float* t_bar, int accumulate, float* dbar_item, float* kbar_item, cudaStream_t st) {
+  const size_t npix = (size_t)N * N;
+  constexpr int MAX_ITEMS = 2048;        // 24 KiB of per-item partial sums per block
+  for (int b0 = 0; b0 < n_items; b0 += MAX_ITEMS) {
+    const int nb = n_items - b0 < MAX_ITEMS ? n_items - b0 : MAX_ITEMS;
+    const bool per_item = dbar_item || kbar_item;
+    q_reduce_kernel<<<grid_for(npix, 256, 148 * 4), 256, per_item ? 3 * nb * sizeof(float) : 0, st>>>(
+        N, nb, q + (size_t)b0 * npix, k + b0, T, opd, phase, amp_scale, a0, opd_bar, phase_bar, t_bar,
+        (accumulate || b0 > 0) ? 1 : 0, dbar_item ? dbar_item + 2 * (size_t)b0 : nullptr,
+        kbar_item ? kbar_item + b0 : nullptr);
+    note_launch();
+  }
+  return check_launch("q_reduce");
+}
+
 // Power normalisation (wavefronts.py:418-424) makes amp = (sum_j (a0 T_j)^2)^(-1/2) depend on
 // T: dL/dT_j gets  -(sum_i T_i Tbar_i) * amp^2 * a0^2 * T_j  on top of the direct term.
 __global__ void tbar_partial_kernel(size_t npix, const float* __restrict__ T, const float* __restrict__ t_bar,

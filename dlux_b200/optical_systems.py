@@ -171,9 +171,9 @@ class LayeredOpticalSystem(OpticalSystem):
 
     def _batchable(self):
         from .layers import MFT as _MFTLayer, Tilt as _Tilt
-        from .apertures import _DynamicAperture
+        from .apertures import AberratedAperture, _DynamicAperture
         ok = (TransmissiveLayer, AberratedLayer, BasisLayer, Optic, BasisOptic, Normalise, _MFTLayer, _Tilt)
-        return all(type(l) in ok or isinstance(l, _DynamicAperture) for l in self.layers.values())
+        return all(type(l) in ok or isinstance(l, (_DynamicAperture, AberratedAperture)) for l in self.layers.values())
 
     def initialise_wavefront(self, wavelength, offset=None):      # optical_systems.py:363-389
         wf = Wavefront(wavelength, self.wf_npixels, self.diameter, device=self.device)
@@ -237,9 +237,14 @@ class ParametricLayeredOpticalSystem(ParametricOpticalSystem, LayeredOpticalSyst
     def _can_fuse(self) -> bool:
         """Structure-only version of ``_fusable`` (no layer is evaluated): is the stack pupil-only,
         with no transmission applied after a normalisation?"""
-        from .apertures import _DynamicAperture
+        from .apertures import AberratedAperture, _DynamicAperture
         normalise = False
         for layer in self.layers.values():
+            if isinstance(layer, AberratedAperture):
+                if normalise or (layer.effect == "amplitude" and layer.normalise):
+                    return False                       # a transmission applied after a normalisation
+                normalise = normalise or layer.normalise
+                continue
             dyn = isinstance(layer, _DynamicAperture)
             if not dyn and type(layer) not in (TransmissiveLayer, AberratedLayer, BasisLayer, Optic,
                                                 BasisOptic, Normalise):
@@ -266,8 +271,26 @@ class ParametricLayeredOpticalSystem(ParametricOpticalSystem, LayeredOpticalSyst
         def add(a, b):
             return b if a is None else (a if b is None else a + b)
 
-        from .apertures import _DynamicAperture
+        from .apertures import AberratedAperture, _DynamicAperture
         for layer in self.layers.values():
+            if isinstance(layer, AberratedAperture):
+                coords = self.__dict__.get("_pupil_coords")
+                if coords is None:
+                    from .utils.geometry import pixel_coords
+                    coords = self.__dict__["_pupil_coords"] = pixel_coords(
+                        self.wf_npixels, float(self.diameter), device=self.device)
+                ps = torch.as_tensor(np.float32(self.diameter / np.float32(self.wf_npixels)), device=self.device)
+                T = mul(T, layer.transmission(coords, ps))
+                ab = layer.eval_basis(coords)
+                if layer.effect == "opd":
+                    opd = add(opd, ab)
+                elif layer.effect == "phase":
+                    phase = add(phase, ab)
+                else:
+                    T = mul(T, 1 + ab)
+                if layer.normalise:
+                    normalise = True
+                continue
             if isinstance(layer, _DynamicAperture):
                 # a dynamic aperture evaluates its transmission on the pupil grid (torch, autograd)
                 coords = self.__dict__.get("_pupil_coords")

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-__all__ = ["noll_indices", "zernike", "zernike_basis"]
+__all__ = ["noll_indices", "zernike", "zernike_basis", "zernike_basis_torch"]
 
 
 def noll_indices(j: int):
@@ -46,3 +46,26 @@ def zernike(j: int, coordinates, diameter: float = 2.0):
 
 def zernike_basis(js, coordinates, diameter: float = 2.0):
     return np.stack([zernike(int(j), coordinates, diameter) for j in js])
+
+
+def zernike_basis_torch(js, coordinates, diameter: float = 2.0):
+    """The same basis as differentiable torch arithmetic on a (possibly transformed) coordinate tensor
+    [2, npix, npix]: what ``DynamicZernikeBasis.calculate_basis`` evaluates inside ``AberratedAperture``
+    (/root/reference/src/dLux/polynomials.py:85-115, utils/zernikes.py:179-254)."""
+    import torch
+    c = coordinates / (float(diameter) / 2)
+    rho, theta = torch.hypot(c[0], c[1]), torch.atan2(c[1], c[0])
+    inside = (rho <= 1.0).to(c.dtype)
+    out = []
+    for j in js:
+        n, m = noll_indices(int(j))
+        ma = abs(m)
+        radial = torch.zeros_like(rho)
+        for k in range((n - ma) // 2 + 1):
+            coef = ((-1) ** k * math.factorial(n - k)
+                    / (math.factorial(k) * math.factorial((n + ma) // 2 - k) * math.factorial((n - ma) // 2 - k)))
+            radial = radial + coef * rho ** (n - 2 * k)
+        norm = math.sqrt(n + 1) * (math.sqrt(2) if m != 0 else 1.0)
+        az = torch.cos(ma * theta) if m >= 0 else torch.sin(ma * theta)
+        out.append(inside * radial * norm * az)
+    return torch.stack(out)
