@@ -22,7 +22,7 @@ class MftDesc(C.Structure):
 class PolyPsfDesc(C.Structure):
     _fields_ = [("n_pupil", C.c_int32), ("n_psf", C.c_int32), ("n_wavels", C.c_int32),
                 ("n_sources", C.c_int32), ("normalise", C.c_int32), ("precision", C.c_int32),
-                ("save_field", C.c_int32), ("reserved", C.c_int32)]
+                ("save_field", C.c_int32), ("sparse", C.c_int32)]
 
 
 class PolyPsfBatchDesc(C.Structure):

@@ -433,6 +433,7 @@ struct PolyScratch {
   float *s_item, *norm_item, *k_item;
   float *w_item, *delta_item;                          // caller's [S, L] arrays in processing order
   float *wbar_item, *dbar_item, *sbar_item, *kbar_item; // bwd outputs in processing order
+  int *sp_flags, *sp_cnt, *sp_idx;                      // zero-block lists (sparse option)
   float *xin, *uout;  // per chunk
   PlaneSet mid_pl;    // per chunk [c][M*N]
   PlaneSet ebar_pl;   // per chunk [c][M*M]  (bwd only; sized always for simplicity)
@@ -467,6 +468,12 @@ static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, 
   s->dbar_item = b.take<float>(2 * items);
   s->sbar_item = b.take<float>(items);
   s->kbar_item = b.take<float>(items);
+  {
+    const size_t nblk = ((N + 127) / 128) * ((N + 15) / 16) + 64;   // >= both block grids used
+    s->sp_flags = b.take<int>(nblk);
+    s->sp_cnt = b.take<int>((N + 127) / 128 + 8);
+    s->sp_idx = b.take<int>(nblk);
+  }
   s->xin = b.take<float>(c * 2 * N);
   s->uout = b.take<float>(c * 2 * M);
   s->mid_pl = take_mid_planes(b, c, (int)N, (int)M);
@@ -536,6 +543,11 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
   // (The tensor kernel's reduce-add stores need 16-byte image rows.)
   const bool fuse_psf = !d->save_field && (M % 4) == 0 && getenv("DLUX_B200_NO_EPI_PSF") == nullptr;
   if (fuse_psf && (rc = launch_zero(psf, (size_t)M * M, st))) return rc;
+  // opt-in exact zero-block skipping: stage 1 contracts P[i][j] over j; a (256 rows x 16 k) block of P is
+  // all zeros wherever T is, and contributes exact zeros to every partial sum
+  const bool sparse = d->sparse && T && d->precision == DLUX_PREC_3XTF32;
+  if (sparse && (rc = launch_block_lists(N, T, GEMM_TC_BM2, GEMM_TC_BK, 0, s.sp_flags, s.sp_cnt, s.sp_idx, st)))
+    return rc;
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
     rc = launch_coords(N, M, c, s.s_item + b0, nullptr, delta_xy ? s.delta_item + 2 * (size_t)b0 : nullptr,
@@ -548,6 +560,10 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
     g.a = s.p_pl;
     g.out = s.mid_pl;
     g.mode = EPI_PLANES;
+    if (sparse) {
+      g.chunk_cnt = s.sp_cnt;
+      g.chunk_idx = s.sp_idx;
+    }
     rc = run_gemm(g, d->precision, st);
     if (rc) return rc;
     GemmParams h{};
@@ -606,6 +622,12 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
   if (transmission_bar && !T) return DLUX_ERR_ARG;
   const bool need_pupil_grad =
       opd_bar || phase_bar || delta_bar || transmission_bar || scale_bar || wavenumber_bar;
+  // opt-in exact zero-block skipping: the last adjoint stage writes Q[i][j]; every pupil-plane cotangent
+  // except the transmission's ignores the pixels with T == 0, so (128 x 256) output blocks that are entirely
+  // blocked are never computed
+  const bool sparse = d->sparse && T && !transmission_bar && d->precision == DLUX_PREC_3XTF32 && need_pupil_grad;
+  if (sparse && (rc = launch_block_lists(N, T, GEMM_TC_BN2, GEMM_TC_BM2, 1, s.sp_flags, s.sp_cnt, s.sp_idx, st)))
+    return rc;
   const float sign2pi = (float)(2.0 * 3.14159265358979323846);  // conj of the forward phasors
   for (int b0 = 0; b0 < items; b0 += s.chunk) {
     const int c = items - b0 < s.chunk ? items - b0 : s.chunk;
@@ -638,6 +660,10 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
       h.mode = EPI_C64;
       h.scale = s.norm_item + b0;
       h.out_c64 = s.qbuf;
+      if (sparse) {
+        h.unit_list = s.sp_idx;
+        h.unit_count = s.sp_cnt;
+      }
       rc = run_gemm(h, d->precision, st);
       if (rc) return rc;
       const float a0 = 1.0f / (float)((long long)N * N);

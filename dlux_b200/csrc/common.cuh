@@ -58,7 +58,20 @@ struct GemmParams {
   float2* out_c64;       // EPI_C64: [n_items][n_out][rows]
   float* out_psf;        // EPI_PSF: [n_out][rows], accumulated over the items (zeroed by the caller)
   const float* item_w;   // EPI_PSF: [n_items] spectral weight x flux
+  // Exact zero-block skipping (opt-in, tensor kernel only; all nullptr = dense):
+  //  chunk_cnt[tiles_mp], chunk_idx[tiles_mp][k_chunks]: for every pair of 128-row data tiles, the 16-k
+  //  chunks in which those 256 rows are not all zero (device arrays; the same for every item);
+  //  unit_list[*unit_count]: the (n-tile pair, m-tile pair) output blocks that are needed at all, as
+  //  t = np * tiles_mp + mp (the count is read on the device too: nothing is copied back to the host).
+  const int* chunk_cnt;
+  const int* chunk_idx;
+  const int* unit_list;
+  const int* unit_count;
 };
+
+constexpr int GEMM_TC_BM2 = 256;   // data rows per unit (two 128-row tiles)
+constexpr int GEMM_TC_BN2 = 128;   // output coordinates per unit (64 per CTA of the pair)
+constexpr int GEMM_TC_BK = 16;     // k per chunk
 
 // round-to-nearest (ties away from zero) to tf32's 10 mantissa bits.  Equivalent to
 // cvt.rna.tf32.f32 for finite inputs; spelled with integer ops because sm_100a expands that
@@ -179,6 +192,10 @@ int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coe
 int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,
                         float* coeff_bar, cudaStream_t st, int n_batch = 1);
 int launch_zero(float* p, size_t n, cudaStream_t st);
+// flags / cnt / idx of the non-zero (bh x bw) blocks of T [N, N]: per block row, or (rows_as_one) one list of
+// block indices br * nbc + bc
+int launch_block_lists(int N, const float* T, int bh, int bw, int rows_as_one, int* flags, int* cnt, int* idx,
+                       cudaStream_t st);
 // delta_bar[item][axis] = 2 pi sum_ij x_axis(i or j) * Im(conj(P_ij) Q_ij[item])  (source-offset VJP)
 // sel 0: delta_bar[item][2] += 2 pi (sum x g, sum y g); sel 1 / 2: out[item] -= 2 pi sum x g / sum y g;
 // sel 3: out[item] += sum opd g   (g = Im(conj(P) Q))

@@ -728,6 +728,40 @@ int launch_pos_grad(int N, int n_items, const float2* q, const float* k, const f
   return check_launch("pos_grad");
 }
 
+
+// ---------------------------------------------------------------------------
+// Exact zero-block skipping (opt-in): which blocks of the pupil hold anything but T == 0.
+// flags[br][bc] = any(T[br*bh .. +bh][bc*bw .. +bw] != 0)
+__global__ void block_mask_kernel(int N, const float* __restrict__ T, int bh, int bw, int nbc, int* __restrict__ flags) {
+  const int br = blockIdx.x / nbc, bc = blockIdx.x % nbc;
+  int any = 0;
+  for (int e = threadIdx.x; e < bh * bw; e += blockDim.x) {
+    const int r = br * bh + e / bw, c = bc * bw + e % bw;
+    if (r < N && c < N && T[(size_t)r * N + c] != 0.0f) any = 1;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flags[blockIdx.x] = any;
+}
+// row-wise compaction of the flags into index lists: idx[row][0 .. cnt[row]) = the set columns, ascending
+__global__ void compact_rows_kernel(int cols, const int* __restrict__ flags, int* __restrict__ cnt, int* __restrict__ idx) {
+  if (threadIdx.x != 0) return;
+  const int row = blockIdx.x;
+  int n = 0;
+  for (int c = 0; c < cols; ++c)
+    if (flags[row * cols + c]) idx[row * cols + n++] = c;
+  cnt[row] = n;
+}
+
+int launch_block_lists(int N, const float* T, int bh, int bw, int rows_as_one, int* flags, int* cnt, int* idx,
+                       cudaStream_t st) {
+  const int nbr = (N + bh - 1) / bh, nbc = (N + bw - 1) / bw;
+  block_mask_kernel<<<nbr * nbc, 256, 0, st>>>(N, T, bh, bw, nbc, flags);
+  if (rows_as_one) compact_rows_kernel<<<1, 32, 0, st>>>(nbr * nbc, flags, cnt, idx);
+  else compact_rows_kernel<<<nbr, 32, 0, st>>>(nbc, flags, cnt, idx);
+  note_launch(2);
+  return check_launch("block_lists");
+}
+
 int launch_zero(float* p, size_t n, cudaStream_t st) {
   if (n == 0) return DLUX_OK;
   zero_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n);

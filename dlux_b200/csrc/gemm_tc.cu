@@ -603,14 +603,19 @@ __device__ __forceinline__ void issue_tile_chunk(uint32_t d, uint32_t g0, uint32
 struct PartialSchedule {
   bool a_open, a_close, b_open, b_close;
 };
-__device__ __forceinline__ PartialSchedule partial_schedule(int kc, int k_chunks) {
-  // first partial: 3 (long K) or 2 flush periods for tile a, half a period less for tile b
 #ifndef DLUX_LONG_FIRST_MIN
 #define DLUX_LONG_FIRST_MIN (12 * FLUSH_CHUNKS)
 #endif
 #ifndef DLUX_LONG_FIRST_FACTOR
 #define DLUX_LONG_FIRST_FACTOR 3
 #endif
+// partial (= TMEM accumulation group) that k-chunk `kc` of a K loop of `k_chunks` chunks belongs to
+__device__ __forceinline__ int partial_group(int kc, int first) {
+  return kc < first ? 0 : 1 + (kc - first) / FLUSH_CHUNKS;
+}
+// Dense K loop: closed form (the MMA issuer's loop is latency-critical; this is the cheapest statement).
+//   tile a: [0,A0) [A0,A0+4) ...      tile b: [0,B0) [B0,B0+4) ...   (B0 = A0 - 2); both close at the last chunk.
+__device__ __forceinline__ PartialSchedule partial_schedule_dense(int kc, int k_chunks) {
   const int A0 = (k_chunks >= DLUX_LONG_FIRST_MIN ? DLUX_LONG_FIRST_FACTOR : 2) * FLUSH_CHUNKS,
             B0 = A0 - FLUSH_CHUNKS / 2;
   PartialSchedule ps;
@@ -622,18 +627,64 @@ __device__ __forceinline__ PartialSchedule partial_schedule(int kc, int k_chunks
   ps.b_close = last || (kc == B0 - 1) || (kc >= B0 && rb == FLUSH_CHUNKS - 1);
   return ps;
 }
+// `prev` / `next`: the k-chunks processed before / after `kc` in this unit (-1: none).  Dense K loops pass
+// kc - 1 / kc + 1; with zero-block skipping the list has holes, and because the groups are defined on the
+// ORIGINAL chunk index every partial sums exactly the chunks the dense kernel would have summed into it
+// (minus exact zeros): the result is bit-identical.
+__device__ __forceinline__ PartialSchedule partial_schedule(int prev, int kc, int next, int k_chunks) {
+  // first partial: 3 (long K) or 2 flush periods for tile a, half a period less for tile b
+  const int A0 = (k_chunks >= DLUX_LONG_FIRST_MIN ? DLUX_LONG_FIRST_FACTOR : 2) * FLUSH_CHUNKS,
+            B0 = A0 - FLUSH_CHUNKS / 2;
+  PartialSchedule ps;
+  const int ga = partial_group(kc, A0), gb = partial_group(kc, B0);
+  ps.a_open = prev < 0 || partial_group(prev, A0) != ga;
+  ps.a_close = next < 0 || partial_group(next, A0) != ga;
+  ps.b_open = prev < 0 || partial_group(prev, B0) != gb;
+  ps.b_close = next < 0 || partial_group(next, B0) != gb;
+  return ps;
+}
 
 struct TcParams {
   GemmParams g;
   int tiles_mp, tiles_np, n_units, k_chunks;  // pairs of 128-row data tiles, pairs of 64-column n-tiles
   int c64_tma;                                // EPI_C64 output goes through TMA stores (even row length)
+  int units_per_item;                         // tiles_mp * tiles_np, or the length of unit_list
 };
 
+// The K loop of one unit: dense (0 .. k_chunks-1) or, with exact zero-block skipping, the list of k-chunks
+// in which the unit's 256 data rows hold anything but zeros (GemmParams::chunk_cnt / chunk_idx).
+// (SPARSE is a compile-time switch: the dense instantiation carries none of the list logic)
+template <bool SPARSE>
+struct ChunkWalk {
+  const int* idx;
+  int n;
+  __device__ __forceinline__ ChunkWalk(const TcParams& tp, int mt) {
+    const GemmParams& p = tp.g;
+    idx = (SPARSE && p.chunk_idx) ? p.chunk_idx + (size_t)mt * tp.k_chunks : nullptr;
+    n = (SPARSE && p.chunk_cnt) ? __ldg(p.chunk_cnt + mt) : tp.k_chunks;
+  }
+  __device__ __forceinline__ int at(int ci) const { return (SPARSE && idx) ? __ldg(idx + ci) : ci; }
+  __device__ __forceinline__ int next_of(int ci) const { return ci + 1 < n ? at(ci + 1) : -1; }
+};
+// unit -> (item, tile index t): dense, or through the list of units whose output block is needed
+template <bool SPARSE>
+__device__ __forceinline__ void decode_unit(const TcParams& tp, int units_per_item, int unit, int& item, int& t) {
+  item = unit / units_per_item;
+  t = unit - item * units_per_item;
+  if (SPARSE && tp.g.unit_list) t = __ldg(tp.g.unit_list + t);
+}
+
+template <bool SPARSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                const __grid_constant__ CUtensorMap omap0, const __grid_constant__ CUtensorMap omap1,
                const __grid_constant__ CUtensorMap omapc, const TcParams tp) {
   extern __shared__ uint8_t smem_raw[];
+  int units_per_item = tp.units_per_item, n_units = tp.n_units;
+  if (SPARSE && tp.g.unit_list) {   // only the needed output blocks: the list length lives on the device
+    units_per_item = __ldg(tp.g.unit_count);
+    n_units = units_per_item * tp.g.n_items;
+  }
   const GemmParams& p = tp.g;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of the aligned base
@@ -696,7 +747,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   // cluster work unit = (item, pair of n-tiles, pair of m-tiles); CTA `crank` of the cluster
   // takes n-tile 2 * np + crank (an n-tile beyond the matrix computes on zeros and stores
   // nothing)
-  const int units_per_item = tp.tiles_mp * tp.tiles_np;
 
   // Register re-balancing between warpgroups: setmaxnreg is the first instruction of each
   // warpgroup's branch (all four warps of a warpgroup execute it).
@@ -708,12 +758,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       // barrier, which wakes this CTA's converter warps.
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
-        const int item = unit / units_per_item;
-        const int t = unit % units_per_item;
+      for (int unit = cl_id; unit < n_units; unit += n_cl) {
+        int item, t;
+        decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
         const int m0 = (t % tp.tiles_mp) * (2 * BM);
         const int d = p.item_data ? __ldg(p.item_data + item) : item;
-        for (int kc = 0; kc < tp.k_chunks; ++kc) {
+        const ChunkWalk<SPARSE> cw(tp, t % tp.tiles_mp);
+        for (int ci = 0; ci < cw.n; ++ci) {
+          const int kc = cw.at(ci);
           mbar_wait(emptyA_bar(stage), phase ^ 1);
           if (elect_one()) {
             const uint32_t dst = smem_base + stage * A_BYTES;
@@ -747,12 +799,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       const long long dbg_start = clock64();
 #endif
       // pair mode: only the leader CTA issues; its MMAs drive the tensor cores of both SMs
-      for (int unit = (crank != 0) ? tp.n_units : cl_id; unit < tp.n_units; unit += n_cl) {
-        for (int kc = 0; kc < tp.k_chunks; ++kc) {
+      for (int unit = (crank != 0) ? n_units : cl_id; unit < n_units; unit += n_cl) {
+        int n_walk = tp.k_chunks, prev = -1, kc = 0;
+        const int* widx = nullptr;
+        if (SPARSE) {
+          int item_, t_;
+          decode_unit<SPARSE>(tp, units_per_item, unit, item_, t_);
+          const ChunkWalk<SPARSE> cw(tp, t_ % tp.tiles_mp);
+          n_walk = cw.n;
+          widx = cw.idx;
+          kc = cw.n > 0 ? cw.at(0) : -1;
+        }
+        for (int ci = 0; ci < n_walk; ++ci) {
           // Partials are FLUSH_CHUNKS long; tile b's boundaries are staggered by half a partial so
           // that the three TMEM buffers are re-acquired >= 2 chunks after they were handed to a
           // drain warpgroup (see partial_schedule()).
-          const PartialSchedule ps = partial_schedule(kc, tp.k_chunks);
+          PartialSchedule ps;
+          if (SPARSE) {
+            const int next = ci + 1 < n_walk ? (widx ? __ldg(widx + ci + 1) : ci + 1) : -1;
+            ps = partial_schedule(prev, kc, next, tp.k_chunks);
+            prev = kc;
+            kc = next;
+          } else {
+            ps = partial_schedule_dense(ci, tp.k_chunks);
+          }
           bool opened = false;
           if (ps.a_open) {
             if (which == 0) { mybuf = nbuf; myphase = nphase; opened = true; }
@@ -813,16 +883,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #endif
     float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + BAR_BYTES + warp * STG_WARP_BYTES);
     const uint32_t stg_addr = smem_base + RING_BYTES + BAR_BYTES + warp * STG_WARP_BYTES;
-    for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
-      const int item = unit / units_per_item;
-      const int t = unit % units_per_item;
+    for (int unit = cl_id; unit < n_units; unit += n_cl) {
+      int item, t;
+      decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
       const int m0 = (t % tp.tiles_mp) * (2 * BM) + which * BM;
       const int nq0 = ((t / tp.tiles_mp) * CLUSTER + (int)crank) * NB + q * 16;  // first output row of this warp's lane quarter
       float tot[BM];
 #pragma unroll
       for (int j = 0; j < BM; ++j) tot[j] = 0.0f;
-      for (int kc = 0; kc < tp.k_chunks; ++kc) {
-        const PartialSchedule ps = partial_schedule(kc, tp.k_chunks);
+      const ChunkWalk<SPARSE> cw(tp, t % tp.tiles_mp);
+      int prev = -1, kc = (SPARSE && cw.n > 0) ? cw.at(0) : -1;
+      for (int ci = 0; ci < cw.n; ++ci) {
+        PartialSchedule ps;
+        if (SPARSE) {
+          const int next = cw.next_of(ci);
+          ps = partial_schedule(prev, kc, next, tp.k_chunks);
+          prev = kc;
+          kc = next;
+        } else {
+          ps = partial_schedule_dense(ci, tp.k_chunks);
+        }
         if (ps.a_open) {
           if (which == 0) { mybuf = nbuf; myphase = nphase; }
           if (++nbuf == NUM_ACC) { nbuf = 0; nphase ^= 1; }
@@ -907,8 +987,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     long long dbg_cw = 0, dbg_cc = 0;
     const long long dbg_cstart = clock64();
 #endif
-    for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
-      for (int kc = 0; kc < tp.k_chunks; ++kc) {
+    for (int unit = cl_id; unit < n_units; unit += n_cl) {
+      int n_walk = tp.k_chunks;
+      if (SPARSE) {
+        int item_, t_;
+        decode_unit<SPARSE>(tp, units_per_item, unit, item_, t_);
+        n_walk = ChunkWalk<SPARSE>(tp, t_ % tp.tiles_mp).n;
+      }
+      for (int ci = 0; ci < n_walk; ++ci) {
 #ifdef DLUX_DEBUG_TIMING
         const long long tc0_ = clock64();
 #endif
@@ -954,9 +1040,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     long long dbg_gw = 0;
     const long long dbg_gstart = clock64();
 #endif
-    for (int unit = cl_id; unit < tp.n_units; unit += n_cl) {
-      const int item = unit / units_per_item;
-      const int t = unit % units_per_item;
+    for (int unit = cl_id; unit < n_units; unit += n_cl) {
+      int item, t;
+      decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
+      const ChunkWalk<SPARSE> cw(tp, t % tp.tiles_mp);
       const int n = ((t / tp.tiles_mp) * CLUSTER + (int)crank) * NB + jcol;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
       const float u = (n < p.n_out) ? __ldg(p.nvec + (size_t)item * p.nvec_stride + n) : 0.0f;
@@ -966,12 +1053,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       const int half = lane & 1;
       const uint32_t sgn = (uint32_t)half << 31;
       float xk[4];  // my four k coordinates of this chunk, prefetched one chunk ahead
+      const int kc0 = (SPARSE && cw.n > 0) ? cw.at(0) : 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int k = ks * UMMA_K + half * 4 + j;
+        const int k = kc0 * BK + ks * UMMA_K + half * 4 + j;
         xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
       }
-      for (int kc = 0; kc < tp.k_chunks; ++kc) {
+      for (int ci = 0; ci < cw.n; ++ci) {
         // Evaluate into registers first, THEN wait for the TMEM stage: with only two phasor
         // stages the evaluation must overlap the MMAs that still read the stage.
         float g1[8], g2[8];  // (G1, G2) of my row for the 8 k of the k-step
@@ -1011,8 +1099,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           pk[3][jj] = pack_bf16(g2l2[0], g2l2[1]);
         }
 #pragma unroll
+        int knext0 = (ci + 1) * BK;     // dense: the next chunk follows
+        if (SPARSE) {
+          const int kc_next = cw.next_of(ci);
+          knext0 = kc_next < 0 ? p.K : kc_next * BK;
+        }
+#pragma unroll
         for (int j = 0; j < 4; ++j) {  // next chunk's coordinates (latency hidden behind the wait)
-          const int k = (kc + 1) * BK + ks * UMMA_K + half * 4 + j;
+          const int k = knext0 + ks * UMMA_K + half * 4 + j;
 #ifdef DLUX_DEBUG_NOXLD
           xk[j] = (float)k * 1e-3f;
 #else
@@ -1227,8 +1321,10 @@ TcState& tc_state() {
     return st;
   }
   st.encode = (EncodeTiledFn)fn;
-  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-      cudaSuccess) {
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+          cudaSuccess) {
     st.rc = DLUX_ERR_CUDA;
     return st;
   }
@@ -1312,7 +1408,8 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   tp.c64_tma = c64_tma;
   tp.tiles_mp = (p.rows + 2 * BM - 1) / (2 * BM);
   tp.tiles_np = (p.n_out + CLUSTER * NB - 1) / (CLUSTER * NB);
-  const long long total = (long long)tp.tiles_mp * tp.tiles_np * p.n_items;
+  tp.units_per_item = tp.tiles_mp * tp.tiles_np;   // (the kernel replaces both by the device-side list length)
+  const long long total = (long long)tp.units_per_item * p.n_items;
   if (total > 2147483647LL) return DLUX_ERR_SHAPE;
   tp.n_units = (int)total;
   tp.k_chunks = (p.K + BK - 1) / BK;
@@ -1330,7 +1427,10 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], omaps[0], omaps[1], omapc, tp);
+  const bool sparse = p.chunk_cnt != nullptr || p.unit_list != nullptr;
+  cudaError_t e = sparse
+      ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp)
+      : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp);
   if (e != cudaSuccess) {
     fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
     note_cuda_error((int)e);

@@ -245,19 +245,19 @@ def _mft_geometry_bar(phasor, out, g, scale_out, shift_xy, delta_xy, norm, n_out
 
 
 # --------------------------------------------------------------------------- poly-PSF
-def _poly_desc(N, M, L, S, normalise, precision, save_field):
-    return PolyPsfDesc(N, M, L, S, int(bool(normalise)), _prec(precision), int(bool(save_field)), 0)
+def _poly_desc(N, M, L, S, normalise, precision, save_field, sparse=False):
+    return PolyPsfDesc(N, M, L, S, int(bool(normalise)), _prec(precision), int(bool(save_field)), int(bool(sparse)))
 
 
 def polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, n_pupil,
-                n_psf, normalise=True, precision=None, save_field=False):
+                n_psf, normalise=True, precision=None, save_field=False, sparse=False):
     lib = _lib.load()
     dev = wavenumber.device
     _need_cuda(wavenumber, "wavenumber")
     L = wavenumber.numel()
     weights = weights.reshape(-1, L).contiguous()
     S = weights.shape[0]
-    desc = _poly_desc(n_pupil, n_psf, L, S, normalise, precision, save_field)
+    desc = _poly_desc(n_pupil, n_psf, L, S, normalise, precision, save_field, sparse)
     nbytes = lib.dlux_polypsf_scratch_bytes(C.byref(desc))
     scratch = _get_scratch(dev, nbytes)
     psf = torch.empty((n_psf, n_psf), dtype=torch.float32, device=dev)
@@ -273,13 +273,13 @@ def polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, 
 def polypsf_bwd(transmission, opd, phase, wavenumber, scale_out, norm, weights, delta_xy, field,
                 psf_bar, n_pupil, n_psf, normalise=True, precision=None, want_opd=True,
                 want_phase=False, want_weights=False, want_delta=False, want_transmission=False,
-                want_scale=False, want_wavenumber=False):
+                want_scale=False, want_wavenumber=False, sparse=False):
     lib = _lib.load()
     dev = wavenumber.device
     L = wavenumber.numel()
     weights = weights.reshape(-1, L).contiguous()
     S = weights.shape[0]
-    desc = _poly_desc(n_pupil, n_psf, L, S, normalise, precision, True)
+    desc = _poly_desc(n_pupil, n_psf, L, S, normalise, precision, True, sparse)
     nbytes = lib.dlux_polypsf_scratch_bytes(C.byref(desc))
     scratch = _get_scratch(dev, nbytes)
     mk = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
@@ -362,8 +362,12 @@ class PolyPSFFunction(torch.autograd.Function):
                 n_pupil, n_psf, normalise, precision):
         need = any(t is not None and t.requires_grad
                    for t in (opd, phase, weights, delta_xy, transmission, wavenumber, scale_out, norm))
+        sparse = False
+        if isinstance(precision, tuple):           # (precision, sparse): the opt-in zero-block skipping
+            precision, sparse = precision
+        ctx.sparse = bool(sparse)
         psf, field = polypsf_fwd(transmission, opd, phase, wavenumber, scale_out, norm, weights,
-                                 delta_xy, n_pupil, n_psf, normalise, precision, save_field=need)
+                                 delta_xy, n_pupil, n_psf, normalise, precision, save_field=need, sparse=sparse)
         ctx.save_for_backward(*(t for t in (opd, phase, weights, transmission, wavenumber, scale_out,
                                             norm, delta_xy, field) if t is not None))
         ctx.present = [t is not None for t in (opd, phase, weights, transmission, wavenumber,
@@ -398,7 +402,7 @@ class PolyPSFFunction(torch.autograd.Function):
             want_phase=bool(want[1]), want_weights=bool(want[2]) or want_norm,
             want_delta=bool(want[3]) and delta_xy is not None,
             want_transmission=bool(want[4]) and transmission is not None, want_scale=bool(want[6]),
-            want_wavenumber=bool(want[5]) and opd is not None)
+            want_wavenumber=bool(want[5]) and opd is not None, sparse=ctx.sparse)
         L = wavenumber.numel()
         n_bar = None
         if want_norm:   # psf is quadratic in norm: d/d norm_l = 2 sum_s w_sl <G, |E_sl|^2> / norm_l

@@ -137,7 +137,7 @@ typedef struct {
   int32_t normalise;  /* Optic(normalise=True) */
   int32_t precision;  /* DLUX_PREC_* */
   int32_t save_field; /* fwd: also write E [S*L, M, M] c64 (the VJP residual) */
-  int32_t reserved;
+  int32_t sparse;     /* 1: skip blocks where transmission == 0 (exact; assumes finite opd / phase there) */
 } dlux_polypsf_desc;
 
 DLUX_API size_t dlux_polypsf_scratch_bytes(const dlux_polypsf_desc* desc);

@@ -401,3 +401,44 @@ def test_aberrated_aperture(dev):
         check(f"zernike coefficient grad [fused={fused}]", rel_l2(c.grad.cpu().numpy(), c64.grad.numpy()), TOL)
         # shape parameter: edge-restricted inner product, see test_dynamic_apertures_fused_and_differentiable
         check(f"translation grad [fused={fused}]", rel_l2(t.grad.cpu().numpy(), t64.grad.numpy()), 5e-5)
+
+
+def test_sparse_zero_block_skipping_is_exact(dev):
+    """Opt-in zero-block skipping (sparse=True): blocks of the pupil where the transmission is zero are neither
+    contracted in forward stage 1 nor produced by the last adjoint stage.  The partial sums keep the dense kernel's
+    boundaries, so the image is BIT-IDENTICAL to the dense path; the gradient agrees to rounding of the reduction."""
+    import dlux_b200 as dl
+    from conftest import check
+    from dlux_b200 import workloads
+    cfg = workloads.config("c3")                      # hex NRM: ~55 % of stage-1 blocks are empty
+    G = torch.as_tensor(cfg["G"], device=dev)
+    outs = {}
+    for sparse in (False, True):
+        c = torch.as_tensor(cfg["coefficients"], device=dev).requires_grad_(True)
+        layer = dl.BasisOptic(cfg["basis"], cfg["transmission"], c, normalise=True, effect="opd", device=dev)
+        optics = dl.AngularOpticalSystem(cfg["wf_npixels"], cfg["diameter"], [("p", layer)], cfg["psf_npixels"],
+                                         cfg["psf_pixel_scale"], cfg["oversample"], device=dev, sparse=sparse)
+        pos = torch.tensor([1e-7, -2e-7], device=dev, requires_grad=True)
+        psf = optics.model(dl.PointSource(cfg["wavelengths"], pos, 1.5, weights=cfg["weights"]))
+        (psf * G).sum().backward()
+        fwd_only = optics.propagate(cfg["wavelengths"], None, cfg["weights"])        # EPI_PSF path
+        outs[sparse] = (psf.detach(), c.grad.clone(), pos.grad.clone(), fwd_only.detach())
+    assert torch.equal(outs[True][0], outs[False][0])
+    check("sparse vs dense coefficient grad", rel_l2(outs[True][1].cpu().numpy(), outs[False][1].cpu().numpy()), 1e-6)
+    check("sparse vs dense position grad", rel_l2(outs[True][2].cpu().numpy(), outs[False][2].cpu().numpy()), 1e-6)
+    check("sparse vs dense forward-only image", rel_l2(outs[True][3].cpu().numpy(), outs[False][3].cpu().numpy()), 1e-6)
+    # a circular aperture at an awkward size (edge tiles, K not a multiple of 16) and several stars
+    from test_gpu_parity import _optics_dict
+    od = _optics_dict(200, 72, 3, 5)
+    wls = np.linspace(0.95e-6, 1.05e-6, 3).astype(np.float32)
+    pos3 = np.array([[1e-7, -2e-7], [-3e-7, 0.5e-7], [0.0, 0.0]], np.float32)
+    res = []
+    for sparse in (False, True):
+        c = torch.as_tensor(od["coefficients"], device=dev).requires_grad_(True)
+        layer = dl.BasisOptic(od["basis"], od["transmission"], c, normalise=True, effect="opd", device=dev)
+        sys_ = dl.AngularOpticalSystem(200, 1.0, [("a", layer)], 72, 0.05, device=dev, sparse=sparse)
+        psf = sys_.model(dl.PointSources(wls, pos3, np.array([3.0, 0.25, 1.0], np.float32)))
+        psf.sum().backward()
+        res.append((psf.detach(), c.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    check("sparse vs dense grad (N = 200)", rel_l2(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()), 1e-6)
