@@ -21,21 +21,31 @@ class GraphedValueAndGrad:
     The parameters must keep their shapes; everything else the loss closes over (optics, sources, data) must be
     unchanged between calls -- exactly the structure of an optimisation loop."""
 
-    def __init__(self, loss_fn: Callable, params: Sequence[torch.Tensor], warmup: int = 3):
-        self.static = [p.detach().clone().requires_grad_(True) for p in params]
+    def __init__(self, loss_fn: Callable, params: Sequence[torch.Tensor], warmup: int = 3, has_aux: bool = False,
+                 argnums: Sequence[int] | None = None):
+        """``has_aux``: ``loss_fn`` returns ``(loss, aux)`` and ``aux`` (a tensor or tuple of tensors, e.g. the model
+        image) is kept as a static output; ``argnums``: the parameters to differentiate (default: all)."""
+        self.argnums = list(range(len(params))) if argnums is None else list(argnums)
+        self.static = [p.detach().clone().requires_grad_(i in self.argnums) for i, p in enumerate(params)]
+        self.has_aux = bool(has_aux)
+        self.aux = None
         dev = self.static[0].device
+        wrt = [self.static[i] for i in self.argnums]
+
+        def run():
+            out = loss_fn(*self.static)
+            loss, aux = out if self.has_aux else (out, None)
+            return loss, aux, torch.autograd.grad(loss, wrt)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):         # fills the host-side caches (uploads, scratch, geometry)
-                loss = loss_fn(*self.static)
-                torch.autograd.grad(loss, self.static)
+                run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=side):
-            self.loss = loss_fn(*self.static)
-            self.grads = torch.autograd.grad(self.loss, self.static)
+            self.loss, self.aux, self.grads = run()
         torch.cuda.synchronize(dev)
 
     def __call__(self, *params):
@@ -44,4 +54,6 @@ class GraphedValueAndGrad:
                 if p is not s:
                     s.copy_(p)
         self.graph.replay()
+        if self.has_aux:
+            return (self.loss, self.aux), self.grads
         return self.loss, self.grads
