@@ -230,19 +230,45 @@ __global__ void cotangent_kernel(int M, const float2* __restrict__ field,
   if (items_per_bar > 0) psf_bar += (size_t)(item / items_per_bar) * n;
   const float w2 = 2.0f * w[items_per_bar > 0 ? item % items_per_bar : item];
   const float half = 0.5f * (float)(M - 1);
+  const int p4 = pitch4(M);
   float acc = 0.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const float2 e = field[(size_t)item * n + i];
-    const float g = psf_bar[i];
-    acc += g * (e.x * e.x + e.y * e.y);
-    const size_t r = i / M;
-    float wg = w2 * g;
-    if (weight_axis == 0) wg *= (float)(i - r * M) - half;
-    else if (weight_axis == 1) wg *= (float)r - half;
-    const float re = wg * e.x, im = wg * e.y;
-    const size_t row = (size_t)item * M + r;
-    plane_store(out, row * pitch4(M) + (i - r * M), re, im);
+  if ((M & 3) == 0) {
+    // four consecutive pixels of one row per thread: 2 x 16-byte loads of the field, 16-byte stores to both planes
+    const size_t n4 = n / 4;
+    const int m4 = M / 4;
+    const float4* f4 = reinterpret_cast<const float4*>(field + (size_t)item * n);
+    const float4* g4 = reinterpret_cast<const float4*>(psf_bar);
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+      const float4 e0 = f4[2 * q], e1 = f4[2 * q + 1];
+      const float4 g = g4[q];
+      const int r = (int)(q / m4), c0 = (int)(q - (size_t)r * m4) * 4;
+      acc += g.x * (e0.x * e0.x + e0.y * e0.y) + g.y * (e0.z * e0.z + e0.w * e0.w) +
+             g.z * (e1.x * e1.x + e1.y * e1.y) + g.w * (e1.z * e1.z + e1.w * e1.w);
+      float wg[4] = {w2 * g.x, w2 * g.y, w2 * g.z, w2 * g.w};
+      if (weight_axis == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wg[e] *= (float)(c0 + e) - half;
+      } else if (weight_axis == 1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wg[e] *= (float)r - half;
+      }
+      const size_t o = ((size_t)item * M + r) * p4 + c0;
+      *reinterpret_cast<float4*>(out.hi[0] + o) = make_float4(wg[0] * e0.x, wg[1] * e0.z, wg[2] * e1.x, wg[3] * e1.z);
+      *reinterpret_cast<float4*>(out.hi[1] + o) = make_float4(wg[0] * e0.y, wg[1] * e0.w, wg[2] * e1.y, wg[3] * e1.w);
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+      const float2 e = field[(size_t)item * n + i];
+      const float g = psf_bar[i];
+      acc += g * (e.x * e.x + e.y * e.y);
+      const size_t r = i / M;
+      float wg = w2 * g;
+      if (weight_axis == 0) wg *= (float)(i - r * M) - half;
+      else if (weight_axis == 1) wg *= (float)r - half;
+      const size_t row = (size_t)item * M + r;
+      plane_store(out, row * p4 + (i - r * M), wg * e.x, wg * e.y);
+    }
   }
   if (w_bar) {
     sm[threadIdx.x] = acc;
@@ -305,7 +331,7 @@ __global__ void zero_kernel(float* p, size_t n) {
 
 __global__ void basis_reduce_kernel(int nz, size_t npix, const float* __restrict__ basis,
                                     const float* __restrict__ out_bar, float* __restrict__ coeff_bar) {
-  __shared__ float sm[8];
+  __shared__ float sm[4][8];
   constexpr int PER = 8;
   float g[PER];
   out_bar += (size_t)blockIdx.y * npix;       // blockIdx.y = element of a parameter batch
@@ -317,20 +343,28 @@ __global__ void basis_reduce_kernel(int nz, size_t npix, const float* __restrict
     const size_t i = base_i + (size_t)j * blockDim.x;
     g[j] = i < npix ? out_bar[i] : 0.0f;
   }
-  for (int z = 0; z < nz; ++z) {
-    float acc = 0.0f;
+  for (int z0 = 0; z0 < nz; z0 += 4) {        // four modes per round: 32 independent loads in flight per thread
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const size_t i = base_i + (size_t)j * blockDim.x;
-      if (i < npix) acc = fmaf(g[j], __ldg(basis + (size_t)z * npix + i), acc);
+    for (int zz = 0; zz < 4; ++zz) {
+      if (z0 + zz < nz) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const size_t i = base_i + (size_t)j * blockDim.x;
+          if (i < npix) acc[zz] = fmaf(g[j], __ldg(basis + (size_t)(z0 + zz) * npix + i), acc[zz]);
+        }
+      }
     }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+#pragma unroll
+    for (int zz = 0; zz < 4; ++zz) {
+      for (int o = 16; o > 0; o >>= 1) acc[zz] += __shfl_xor_sync(0xffffffffu, acc[zz], o);
+      if ((threadIdx.x & 31) == 0) sm[zz][threadIdx.x >> 5] = acc[zz];
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 4 && z0 + threadIdx.x < nz) {
       float s = 0.0f;
-      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += sm[wv];
-      atomicAdd(coeff_bar + z, s);
+      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += sm[threadIdx.x][wv];
+      atomicAdd(coeff_bar + z0 + threadIdx.x, s);
     }
     __syncthreads();
   }
