@@ -16,7 +16,8 @@ PREC_FP32 = 1
 
 class MftDesc(C.Structure):
     _fields_ = [("n_in", C.c_int32), ("n_out", C.c_int32), ("batch", C.c_int32),
-                ("inverse", C.c_int32), ("adjoint", C.c_int32), ("precision", C.c_int32)]
+                ("inverse", C.c_int32), ("adjoint", C.c_int32), ("precision", C.c_int32),
+                ("dft_period", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PolyPsfDesc(C.Structure):
@@ -76,7 +77,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.dlux_abi_version() != 1:
+    if lib.dlux_abi_version() != 2:
         raise ImportError("dlux_b200: ABI version mismatch, rebuild the library")
     _lib = lib
     return lib

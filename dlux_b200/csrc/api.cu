@@ -176,6 +176,10 @@ static int check_mft_desc(const dlux_mft_desc* d) {
   if (d->n_in < 1 || d->n_out < 1 || d->batch < 0) return DLUX_ERR_SHAPE;
   if (d->n_in > 32768 || d->n_out > 32768) return DLUX_ERR_SHAPE;
   if (d->precision != DLUX_PREC_3XTF32 && d->precision != DLUX_PREC_FP32) return DLUX_ERR_ARG;
+  if (d->dft_period < 0) return DLUX_ERR_ARG;
+  // exact-DFT mode: the integer products (j - j0)(b - b0) must be exact in float32
+  if (d->dft_period > 0 && (double)(d->n_in + d->dft_period) * (double)(d->n_out + d->dft_period) >= 16777216.0)
+    return DLUX_ERR_SHAPE;
   return DLUX_OK;
 }
 
@@ -400,7 +404,7 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
   for (int b0 = 0; b0 < d->batch; b0 += chunk) {
     const int c = d->batch - b0 < chunk ? d->batch - b0 : chunk;
     rc = launch_coords(N, M, c, scale_out + b0, shift_xy ? shift_xy + 2 * (size_t)b0 : nullptr,
-                       delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr, 1, s.xin, s.uout, st);
+                       delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr, 1, s.xin, s.uout, st, d->dft_period > 0);
     if (rc) return rc;
     rc = launch_split_c64((const float2*)in + (size_t)b0 * n_src * n_src, (size_t)c * n_src, (int)n_src,
                           s.in_pl, st);
@@ -411,6 +415,7 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
     g.out = s.mid_pl;
     g.mode = EPI_PLANES;
     g.scale = nullptr;
+    g.dft_period = (float)d->dft_period;
     rc = run_gemm(g, d->precision, st);
     if (rc) return rc;
     GemmParams h{};
@@ -418,6 +423,7 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
     h.a = s.mid_pl;
     h.mode = EPI_C64;
     h.scale = norm ? norm + b0 : nullptr;
+    h.dft_period = (float)d->dft_period;
     h.out_c64 = (float2*)out + (size_t)b0 * n_dst * n_dst;
     rc = run_gemm(h, d->precision, st);
     if (rc) return rc;

@@ -67,6 +67,8 @@ struct GemmParams {
   const int* chunk_idx;
   const int* unit_list;
   const int* unit_count;
+  // Exact-DFT mode (dlu.FFT): kvec / nvec hold integer index offsets and the phase is +-2 pi ((k n) mod P) / P
+  float dft_period;      // P = padded size, 0 = the MFT's float32 phase form
 };
 
 constexpr int GEMM_TC_BM2 = 256;   // data rows per unit (two 128-row tiles)
@@ -83,6 +85,16 @@ __device__ __forceinline__ float tf32_hi(float x) {
 // Reference phase argument: two float32 multiplies, no fused contraction.
 __device__ __forceinline__ float phase_arg(float sign2pi, float x, float u) {
   return __fmul_rn(sign2pi, __fmul_rn(x, u));
+}
+// Exact-DFT phase argument (dlu.FFT through these kernels): x and u are integer index offsets, the phase is
+// +-2 pi ((x u) mod P) / P.  x u is an exact integer in float32 (|x u| < 2^24 is checked on the host), the
+// reduction is exact, and only the final scaling rounds -- the float32 MFT form fl(2 pi fl(x u / P)) would carry
+// ~1e-4 rad of rounding at N_pad = 2048, which the reference's FFT (an FFT, not a phasor matrix) does not have.
+__device__ __forceinline__ float dft_arg(float sign2pi, float x, float u, float period, float inv_period) {
+  const float pf = x * u;
+  const float q = rintf(pf * inv_period);
+  const float r = fmaf(-q, period, pf);          // exact: |r| <= period
+  return sign2pi * (r * inv_period);
 }
 
 // sin/cos of a float32 argument, ~1.5 ulp: Cody-Waite reduction by pi/2 in three parts
@@ -175,7 +187,7 @@ int launch_tc_peak_probe(int kind, int n_batches, float* sink, double* flops, cu
 
 int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const float* shift_xy,
                   const float* delta_xy, int delta_stride_items, float* xin, float* uout,
-                  cudaStream_t st);
+                  cudaStream_t st, int dft = 0);
 // in: [n_mat][rows][cols] c64 -> split planes
 int launch_split_c64(const float2* in, size_t n_mat_rows, int cols, const PlaneSet& out, cudaStream_t st);
 int launch_pupil(int N, int L, const float* T, const float* opd, const float* phase,

@@ -24,8 +24,16 @@ __device__ __forceinline__ float lerp_linspace(float start, float stop, int i, i
 // propagation.py:113-121 via utils/coordinates.py:329-332), float32 bit-exact.
 __global__ void coords_kernel(int n_in, int n_out, int batch, const float* __restrict__ scale_out,
                               const float* __restrict__ shift_xy, const float* __restrict__ delta_xy,
-                              float* __restrict__ xin, float* __restrict__ uout) {
+                              float* __restrict__ xin, float* __restrict__ uout, int dft) {
   const int item = blockIdx.y, axis = blockIdx.z;
+  if (dft) {   // exact-DFT mode: integer index offsets from the origins shift_xy (input) and delta_xy (output)
+    const float j0 = shift_xy ? shift_xy[item * 2 + axis] : 0.0f, b0 = delta_xy ? delta_xy[item * 2 + axis] : 0.0f;
+    float* xi = xin + ((size_t)item * 2 + axis) * n_in;
+    float* uo = uout + ((size_t)item * 2 + axis) * n_out;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) xi[i] = (float)i - j0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) uo[i] = (float)i - b0;
+    return;
+  }
   const float shift = shift_xy ? shift_xy[item * 2 + axis] : 0.0f;
   const float delta = delta_xy ? delta_xy[item * 2 + axis] : 0.0f;
   const float s = scale_out[item];
@@ -52,7 +60,7 @@ __global__ void coords_kernel(int n_in, int n_out, int batch, const float* __res
 }
 
 int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const float* shift_xy,
-                  const float* delta_xy, int, float* xin, float* uout, cudaStream_t st) {
+                  const float* delta_xy, int, float* xin, float* uout, cudaStream_t st, int dft) {
   if (batch <= 0) return DLUX_OK;
   int mx = n_in > n_out ? n_in : n_out;
   for (int b0 = 0; b0 < batch; b0 += 65535) {
@@ -61,7 +69,7 @@ int launch_coords(int n_in, int n_out, int batch, const float* scale_out, const 
     coords_kernel<<<grid, 256, 0, st>>>(n_in, n_out, nb, scale_out + b0,
                                          shift_xy ? shift_xy + 2 * (size_t)b0 : nullptr,
                                          delta_xy ? delta_xy + 2 * (size_t)b0 : nullptr,
-                                         xin + (size_t)b0 * 2 * n_in, uout + (size_t)b0 * 2 * n_out);
+                                         xin + (size_t)b0 * 2 * n_in, uout + (size_t)b0 * 2 * n_out, dft);
     note_launch();
   }
   return check_launch("coords");

@@ -49,7 +49,12 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p, int t
       const int kl = idx / BN, nl = idx % BN;
       const int n = n0 + nl, k = k0 + kl;
       float s = 0.0f, c = 0.0f;
-      if (n < p.n_out && k < p.K) sincosf(phase_arg(p.sign2pi, __ldg(kv + k), __ldg(nv + n)), &s, &c);
+      if (n < p.n_out && k < p.K) {
+        const float arg = p.dft_period > 0.0f
+                              ? dft_arg(p.sign2pi, __ldg(kv + k), __ldg(nv + n), p.dft_period, 1.0f / p.dft_period)
+                              : phase_arg(p.sign2pi, __ldg(kv + k), __ldg(nv + n));
+        sincosf(arg, &s, &c);
+      }
       Gs_re[kl][nl] = c;
       Gs_im[kl][nl] = s;
     }

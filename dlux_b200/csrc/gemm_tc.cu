@@ -674,7 +674,7 @@ __device__ __forceinline__ void decode_unit(const TcParams& tp, int units_per_it
   if (SPARSE && tp.g.unit_list) t = __ldg(tp.g.unit_list + t);
 }
 
-template <bool SPARSE>
+template <bool SPARSE, bool DFT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                const __grid_constant__ CUtensorMap omap0, const __grid_constant__ CUtensorMap omap1,
@@ -1031,6 +1031,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GEN));
     const int q = warp & 3;                          // TMEM lane quarter
     const int ks = (warp - FIRST_GEN_WARP) >> 2;     // which k-step of the chunk
+    const float dft_inv = DFT ? 1.0f / p.dft_period : 0.0f;
     const int qshift = (lane & 1) ? -1 : 0;          // odd lane = imaginary row of the phasor column
     const int jcol = (q * 32 + lane) >> 1;           // phasor column within the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -1069,7 +1070,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #ifdef DLUX_DEBUG_NOGEN
           sn = xk[j]; cs = u;
 #else
-          fast_sincos_mufu(phase_arg(p.sign2pi, xk[j], u), qshift, &sn, &cs);
+          fast_sincos_mufu(DFT ? dft_arg(p.sign2pi, xk[j], u, p.dft_period, dft_inv) : phase_arg(p.sign2pi, xk[j], u),
+                           qshift, &sn, &cs);
 #endif
           // mine: (G1, G2) = (cs, -sn).  The other lane's: even -> odd (sin, cos) = (sn, cs);
           // odd -> even (cos, -sin) = (-sn, -cs) in terms of my quarter-turn-shifted values.
@@ -1321,9 +1323,11 @@ TcState& tc_state() {
     return st;
   }
   st.encode = (EncodeTiledFn)fn;
-  if (cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
           cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+      cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
           cudaSuccess) {
     st.rc = DLUX_ERR_CUDA;
     return st;
@@ -1428,9 +1432,13 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const bool sparse = p.chunk_cnt != nullptr || p.unit_list != nullptr;
-  cudaError_t e = sparse
-      ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp)
-      : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp);
+  const bool dft = p.dft_period > 0.0f;
+  if (dft && sparse) return DLUX_ERR_ARG;
+  cudaError_t e = dft
+      ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp)
+      : sparse
+          ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, false>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp)
+          : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, false>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp);
   if (e != cudaSuccess) {
     fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
     note_cuda_error((int)e);

@@ -93,7 +93,8 @@ def mft_coords(n_in: int, n_out: int, scale_out, shift_xy=None, delta_xy=None):
 
 
 def mft_c64(phasor: torch.Tensor, scale_out, n_out_or_in: int, shift_xy=None, delta_xy=None,
-            norm=None, inverse: bool = False, adjoint: bool = False, precision=None) -> torch.Tensor:
+            norm=None, inverse: bool = False, adjoint: bool = False, precision=None,
+            dft_period: int = 0) -> torch.Tensor:
     """Batched MFT through ``dlux_mft_c64``.  ``phasor``: complex64 [..., n, n].
     forward: n = n_in, ``n_out_or_in`` = n_out; adjoint: n = n_out, ``n_out_or_in`` = n_in."""
     lib = _lib.load()
@@ -123,7 +124,7 @@ def mft_c64(phasor: torch.Tensor, scale_out, n_out_or_in: int, shift_xy=None, de
     shift_xy = per_item(shift_xy, 2)
     delta_xy = per_item(delta_xy, 2)
     norm = None if norm is None else per_item(norm, 1)
-    desc = MftDesc(n_in, n_out, batch, int(bool(inverse)), int(bool(adjoint)), _prec(precision))
+    desc = MftDesc(n_in, n_out, batch, int(bool(inverse)), int(bool(adjoint)), _prec(precision), int(dft_period), 0)
     nbytes = lib.dlux_mft_scratch_bytes(C.byref(desc))
     scratch = _get_scratch(dev, nbytes)
     out = torch.empty((batch, n_dst, n_dst), dtype=torch.complex64, device=dev)
@@ -158,9 +159,12 @@ class MFTFunction(torch.autograd.Function):
         ctx.n_self = phasor.shape[-1]
         ctx.n_other = n_other
         ctx.args = (scale_out, shift_xy, delta_xy, norm, inverse, precision, bool(adjoint))
-        out = mft_c64(phasor, scale_out, n_other, shift_xy, delta_xy, norm, inverse, bool(adjoint), precision)
+        prec, period = precision if isinstance(precision, tuple) else (precision, 0)   # (precision, dft_period)
+        out = mft_c64(phasor, scale_out, n_other, shift_xy, delta_xy, norm, inverse, bool(adjoint), prec, period)
         geo = [t for t in (scale_out, shift_xy, delta_xy, norm) if torch.is_tensor(t) and t.requires_grad]
         ctx.geo = bool(geo)
+        if ctx.geo and period:
+            raise NotImplementedError("dlux_b200: the exact-DFT (FFT) transform has no differentiable geometry operands")
         if ctx.geo:
             if adjoint:
                 raise NotImplementedError("dlux_b200: geometry gradients of the adjoint MFT (second order "

@@ -128,10 +128,11 @@ def FFT(phasor, wavelength, pixel_scale, focal_length=None, pad: int = 2, invers
     ``(phasor, new_pixel_scale)``.
 
     The padded, centred DFT is evaluated by the same phasor-GEMM kernels as the MFT (SURVEY 8f
-    NEXT-2): with N_pad output samples it is exactly an MFT at ``scale_out = N / N_pad`` whose
-    input / output index origins sit at ``N_pad//2 - npad`` and ``N_pad//2`` (numpy's
-    fftshift convention) and whose normalisation is ``1 / N_pad``.  This costs O(N^2 N_pad)
-    instead of O(N_pad^2 log N_pad) but runs on the tensor cores and shares the adjoint."""
+    NEXT-2) in their exact-DFT mode: integer index offsets from the origins ``N_pad//2 - npad``
+    (input) and ``N_pad//2`` (output; numpy's fftshift convention), phases
+    ``2 pi ((j - j0)(b - b0) mod N_pad) / N_pad`` reduced exactly before the sincos, normalisation
+    ``1 / N_pad``.  This costs O(N^2 N_pad) instead of O(N_pad^2 log N_pad) but runs on the tensor
+    cores and shares the adjoint; ``tools/fft_probe.py`` times it against cuFFT."""
     if not torch.is_tensor(phasor):
         raise TypeError("phasor must be a torch CUDA tensor")
     n = phasor.shape[-1]
@@ -143,15 +144,17 @@ def FFT(phasor, wavelength, pixel_scale, focal_length=None, pad: int = 2, invers
         new_pixel_scale = new_pixel_scale * fl
     npad = (n * (pad - 1)) // 2
     n_out = n + 2 * npad
-    s = np.float32(n) / np.float32(n_out)
-    sh_in = np.float32(n_out // 2 - npad - (n - 1) / 2)        # input origin: padded index N_pad//2
-    sh_out = np.float32(n_out // 2 - (n_out - 1) / 2)          # output origin: index N_pad//2
+    # exact-DFT mode of the kernels: integer index offsets from the fftshift origins (input index N_pad//2 - npad,
+    # output index N_pad//2) and phases 2 pi ((j - j0)(b - b0) mod N_pad) / N_pad -- no float32 phase rounding
+    j0 = float(n_out // 2 - npad)
+    b0 = float(n_out // 2)
     dev = phasor.device
     batch = int(np.prod(phasor.shape[:-2])) if phasor.dim() > 2 else 1
     f = lambda v, w: torch.full((batch, w), float(v), dtype=torch.float32, device=dev)
-    out = ops.MFTFunction.apply(phasor, f(s, 1).reshape(batch), n_out, f(sh_in, 2),
-                                f((sh_out - sh_in) * s, 2), f(np.float32(1.0) / np.float32(n_out), 1),
-                                bool(inverse), precision, False)
+    # dlu.FFT scales the forward transform by 1/N_pad and the inverse (ifft2 = 1/N_pad^2 inside) by N_pad:
+    # both are 1/N_pad on the unnormalised DFT sum
+    out = ops.MFTFunction.apply(phasor, f(1.0, 1).reshape(batch), n_out, f(j0, 2), f(b0, 2),
+                                f(np.float32(1.0) / np.float32(n_out), 1), bool(inverse), (precision, n_out), False)
     return out, new_pixel_scale
 
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLUX_B200_ABI_VERSION 1
+#define DLUX_B200_ABI_VERSION 2
 
 enum {
   DLUX_OK = 0,
@@ -96,6 +96,10 @@ typedef struct {
   int32_t inverse;   /* propagation.py:125-126: sign flip of the exponent */
   int32_t adjoint;   /* 0: forward operator, 1: its conjugate transpose */
   int32_t precision; /* DLUX_PREC_* */
+  int32_t dft_period; /* 0: MFT.  P > 0: exact DFT of period P (dlu.FFT, propagation.py:8-64, evaluated as a
+                         centred, zero-padded DFT): phasors exp(-/+ 2 pi i ((j - j0)(b - b0) mod P) / P) with the
+                         integer origins j0 = shift_xy, b0 = delta_xy (scale_out is ignored) */
+  int32_t reserved;
 } dlux_mft_desc;
 
 DLUX_API size_t dlux_mft_scratch_bytes(const dlux_mft_desc* desc);

@@ -663,6 +663,19 @@ def test_fft_golden_reference_vectors(dev, golden, prec):
         assert abs(float(gps) - ps) <= 1e-6 * abs(ps)
 
 
+def test_fft_large_sizes_against_numpy_fft(dev):
+    # the reference's FFT is an FFT: no float32 phase-matrix rounding.  The exact-DFT mode of the kernels must hold
+    # 1e-5 at sizes where the MFT's float32 phase form would not (1e-4 at N_pad = 2048)
+    import dlux_b200 as dl
+    rng = np.random.default_rng(3)
+    for n, pad, inverse in ((1024, 2, False), (512, 3, True), (200, 2, False), (129, 3, False)):
+        x = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+        out, ps = dl.utils.FFT(torch.as_tensor(x, device=dev), np.float32(1e-6), np.float32(0.01), None, pad, inverse)
+        ref, ps_ref = O.FFT(x.astype(np.complex128), 1e-6, 0.01, None, pad, inverse, dtype=np.float64)
+        check(f"FFT n={n} pad={pad} inverse={inverse}", rel_l2(out.cpu().numpy(), ref), TOL)
+        assert abs(float(ps) - float(ps_ref)) < 1e-6 * float(ps_ref)
+
+
 def test_fft_roundtrip_and_layer(dev):
     # /root/reference/tests/utils/test_propagation.py:74-92 and tests/layers/test_propagators.py:48-63
     import dlux_b200 as dl

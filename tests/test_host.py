@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
     nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (dlux_\w+)", nm))
     assert declared <= exported, declared - exported
-    assert lib.dlux_abi_version() == 1
+    assert lib.dlux_abi_version() == 2
     assert lib.dlux_error_string(-3) == b"scratch buffer too small"
 
 
