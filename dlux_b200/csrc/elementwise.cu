@@ -600,31 +600,42 @@ __global__ void q_reduce_kernel(int N, int n_items, const float2* __restrict__ q
     const float xc = ((float)c - half) * inv, yc = ((float)r - half) * inv;
     float kprev = 0.0f, sn = 0.0f, cs = 1.0f;
     bool have = false;
-    for (int it = 0; it < n_items; ++it) {
-      const float kw = __ldg(k + it);
-      if (!have || kw != kprev) {
-        fast_sincos(__fmul_rn(kw, o) + ph, &sn, &cs);
-        kprev = kw;
-        have = true;
-      }
-      float2 v = make_float2(0.0f, 0.0f);
-      if (live) v = q[(size_t)it * npix + i];
-      const float g = a * (cs * v.y - sn * v.x);          // Im(conj(P) Q)
-      ao = fmaf(kw, g, ao);
-      ap += g;
-      at = fmaf(amp, cs * v.x + sn * v.y, at);            // Re(conj(Q) dP/dT), direct term
-      if (per_item) {
-        float sx = xc * g, sy = yc * g, so = o * g;
+    constexpr int UN = 4;                     // four independent loads of Q in flight per thread
+    for (int it0 = 0; it0 < n_items; it0 += UN) {
+      float2 vv[UN];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          sx += __shfl_xor_sync(0xffffffffu, sx, d);
-          sy += __shfl_xor_sync(0xffffffffu, sy, d);
-          so += __shfl_xor_sync(0xffffffffu, so, d);
+      for (int u = 0; u < UN; ++u) {
+        vv[u] = make_float2(0.0f, 0.0f);
+        if (live && it0 + u < n_items) vv[u] = q[(size_t)(it0 + u) * npix + i];
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int it = it0 + u;
+        if (it >= n_items) break;
+        const float kw = __ldg(k + it);
+        if (!have || kw != kprev) {
+          fast_sincos(__fmul_rn(kw, o) + ph, &sn, &cs);
+          kprev = kw;
+          have = true;
         }
-        if (lane == 0) {
-          atomicAdd(sm + 3 * it, sx);
-          atomicAdd(sm + 3 * it + 1, sy);
-          atomicAdd(sm + 3 * it + 2, so);
+        const float2 v = vv[u];
+        const float g = a * (cs * v.y - sn * v.x);          // Im(conj(P) Q)
+        ao = fmaf(kw, g, ao);
+        ap += g;
+        at = fmaf(amp, cs * v.x + sn * v.y, at);            // Re(conj(Q) dP/dT), direct term
+        if (per_item) {
+          float sx = xc * g, sy = yc * g, so = o * g;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, d);
+            sy += __shfl_xor_sync(0xffffffffu, sy, d);
+            so += __shfl_xor_sync(0xffffffffu, so, d);
+          }
+          if (lane == 0) {
+            atomicAdd(sm + 3 * it, sx);
+            atomicAdd(sm + 3 * it + 1, sy);
+            atomicAdd(sm + 3 * it + 2, so);
+          }
         }
       }
     }
@@ -655,7 +666,10 @@ int launch_q_reduce(int N, int n_items, const float2* q, const float* k, const f
   for (int b0 = 0; b0 < n_items; b0 += MAX_ITEMS) {
     const int nb = n_items - b0 < MAX_ITEMS ? n_items - b0 : MAX_ITEMS;
     const bool per_item = dbar_item || kbar_item;
-    q_reduce_kernel<<<grid_for(npix, 256, 148 * 4), 256, per_item ? 3 * nb * sizeof(float) : 0, st>>>(
+    // per-item sums want few, fat blocks (one flush of the shared partials each); the pixel-only case wants many
+    const int threads = per_item ? 256 : 128;
+    q_reduce_kernel<<<grid_for(npix, threads, per_item ? 148 * 4 : 148 * 16), threads,
+                      per_item ? 3 * nb * sizeof(float) : 0, st>>>(
         N, nb, q + (size_t)b0 * npix, k + b0, T, opd, phase, amp_scale, a0, opd_bar, phase_bar, t_bar,
         (accumulate || b0 > 0) ? 1 : 0, dbar_item ? dbar_item + 2 * (size_t)b0 : nullptr,
         kbar_item ? kbar_item + b0 : nullptr);
