@@ -105,10 +105,19 @@ __global__ void power_partial_kernel(int N, const float* __restrict__ T, double*
   const size_t n = (size_t)N * N;
   const float a0 = 1.0f / (float)((long long)N * N);
   double acc = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const float v = T ? a0 * T[i] : a0;
-    acc += (double)(v * v);
+  if (T && (n & 3) == 0) {      // 16-byte loads; the float32 products are summed in float64 in a fixed order
+    const float4* T4 = reinterpret_cast<const float4*>(T);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
+      const float4 t = T4[i];
+      const float v0 = a0 * t.x, v1 = a0 * t.y, v2 = a0 * t.z, v3 = a0 * t.w;
+      acc += ((double)(v0 * v0) + (double)(v1 * v1)) + ((double)(v2 * v2) + (double)(v3 * v3));
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+      const float v = T ? a0 * T[i] : a0;
+      acc += (double)(v * v);
+    }
   }
   sm[threadIdx.x] = acc;
   __syncthreads();
@@ -318,6 +327,7 @@ __global__ void basis_eval_kernel(int nz, size_t npix, const float* __restrict__
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (size_t)gridDim.x * blockDim.x) {
     float acc = 0.0f;
+#pragma unroll 8
     for (int z = 0; z < nz; ++z) acc = fmaf(c_sm[z], __ldg(basis + (size_t)z * npix + i), acc);
     out[i] = base ? base[i] + acc : acc;
   }
@@ -340,7 +350,7 @@ __global__ void zero_kernel(float* p, size_t n) {
 __global__ void basis_reduce_kernel(int nz, size_t npix, const float* __restrict__ basis,
                                     const float* __restrict__ out_bar, float* __restrict__ coeff_bar) {
   __shared__ float sm[4][8];
-  constexpr int PER = 8;
+  constexpr int PER = 4;
   float g[PER];
   out_bar += (size_t)blockIdx.y * npix;       // blockIdx.y = element of a parameter batch
   coeff_bar += (size_t)blockIdx.y * nz;
@@ -381,7 +391,7 @@ __global__ void basis_reduce_kernel(int nz, size_t npix, const float* __restrict
 int launch_basis_reduce(int nz, int64_t npix, const float* basis, const float* out_bar,
                         float* coeff_bar, cudaStream_t st, int n_batch) {
   zero_kernel<<<grid_for((size_t)nz * n_batch, 256), 256, 0, st>>>(coeff_bar, (size_t)nz * n_batch);
-  const size_t per_block = 256 * 8;
+  const size_t per_block = 256 * 4;           // PER of basis_reduce_kernel
   dim3 grid((unsigned)(((size_t)npix + per_block - 1) / per_block), n_batch);
   basis_reduce_kernel<<<grid, 256, 0, st>>>(nz, (size_t)npix, basis, out_bar, coeff_bar);
   note_launch(2);
