@@ -126,6 +126,38 @@ static int run_gemm(const GemmParams& p, int precision, cudaStream_t st) {
   return rc;
 }
 
+// Stage 1 + stage 2 of the same items: ONE persistent launch with the intermediate in an L2-resident ring
+// (gemm_tc.cu, FUSED) when the tensor path applies, else two launches through the full intermediate.
+static int run_gemm_pair(const GemmParams& g1, const GemmParams& g2, int* sync_ws, int precision, cudaStream_t st) {
+  static const bool no_fuse = getenv("DLUX_B200_NO_FUSE") != nullptr;
+  if (precision == DLUX_PREC_3XTF32 && sync_ws && !no_fuse && g1.dft_period == 0.0f && !g1.chunk_cnt && !g1.unit_list &&
+      !g2.chunk_cnt && !g2.unit_list) {
+    int lag = 0;
+    const int ring = gemm_tc_fused_ring(g1, g2, g1.n_items, &lag);
+    if (ring > 0) {
+      ProfRec r{};
+      const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
+      if (prof) {
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        r.flops = 8.0 * (double)g1.rows * g1.K * (double)g1.n_out * g1.n_items +
+                  8.0 * (double)g2.rows * g2.K * (double)g2.n_out * g2.n_items;
+        cudaEventRecord(r.a, st);
+      }
+      const int rc = launch_gemm_tc_fused(g1, g2, ring, lag, sync_ws, st);
+      if (prof) {
+        cudaEventRecord(r.b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(r);
+      }
+      return rc;
+    }
+  }
+  int rc = run_gemm(g1, precision, st);
+  if (rc) return rc;
+  return run_gemm(g2, precision, st);
+}
+
 // per-chunk intermediates, bytes: 6 GiB of a 180 GB board (DLUX_B200_CHUNK_MB overrides; the tests use it
 // to force the multi-chunk paths at small sizes).  Larger chunks = fewer, longer persistent launches
 static size_t chunk_budget() {
@@ -156,6 +188,7 @@ static int mft_chunk(const dlux_mft_desc* d) {
 struct MftScratch {
   float *xin, *uout;
   PlaneSet in_pl, mid_pl;
+  int* sync_ws;     // 2 ints per item of a chunk: the fused launch's ready / consumed counters
 };
 
 static size_t carve_mft(const dlux_mft_desc* d, void* scratch, size_t cap, MftScratch* s, bool* ok) {
@@ -166,6 +199,7 @@ static size_t carve_mft(const dlux_mft_desc* d, void* scratch, size_t cap, MftSc
   s->uout = b.take<float>(c * 2 * d->n_out);
   s->in_pl = take_planes(b, c * n_src, (int)n_src);
   s->mid_pl = take_mid_planes(b, c, d->n_in, d->n_out);
+  s->sync_ws = b.take<int>(2 * c);
   b.take<float>(gemm_tc_workspace_bytes() / sizeof(float) + 1);
   if (ok) *ok = b.ok;
   return b.used();
@@ -219,6 +253,7 @@ struct BatchScratch {
   float* amp_scale;
   float *s_item, *norm_item, *k_item, *delta_item;   // per chunk [cb * L]
   int* item_l;
+  int* sync_ws;       // fused launch counters, 2 per item of a chunk
   float *xin, *uout;
   float* opd_c;       // [cb][N*N]
   float* opdbar_c;    // [cb][N*N]
@@ -252,6 +287,7 @@ static size_t carve_batch(const dlux_polypsf_batch_desc* d, void* scratch, size_
   s->k_item = b.take<float>(c);
   s->delta_item = b.take<float>(2 * c);
   s->item_l = b.take<int>(c);
+  s->sync_ws = b.take<int>(2 * c);
   s->xin = b.take<float>(c * 2 * N);
   s->uout = b.take<float>(c * 2 * M);
   s->opd_c = b.take<float>(cb * N * N);
@@ -416,8 +452,6 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
     g.mode = EPI_PLANES;
     g.scale = nullptr;
     g.dft_period = (float)d->dft_period;
-    rc = run_gemm(g, d->precision, st);
-    if (rc) return rc;
     GemmParams h{};
     fill_stage(h, adj, 1, N, M, c, s.xin, s.uout, sign2pi);
     h.a = s.mid_pl;
@@ -425,7 +459,7 @@ int dlux_mft_c64(const dlux_mft_desc* d, const void* in, const float* scale_out,
     h.scale = norm ? norm + b0 : nullptr;
     h.dft_period = (float)d->dft_period;
     h.out_c64 = (float2*)out + (size_t)b0 * n_dst * n_dst;
-    rc = run_gemm(h, d->precision, st);
+    rc = run_gemm_pair(g, h, s.sync_ws, d->precision, st);
     if (rc) return rc;
   }
   return DLUX_OK;
@@ -440,6 +474,7 @@ struct PolyScratch {
   float *w_item, *delta_item;                          // caller's [S, L] arrays in processing order
   float *wbar_item, *dbar_item, *sbar_item, *kbar_item; // bwd outputs in processing order
   int *sp_flags, *sp_cnt, *sp_idx;                      // zero-block lists (sparse option)
+  int* sync_ws;                                         // fused launch counters, 2 per item of a chunk
   float *xin, *uout;  // per chunk
   PlaneSet mid_pl;    // per chunk [c][M*N]
   PlaneSet ebar_pl;   // per chunk [c][M*M]  (bwd only; sized always for simplicity)
@@ -482,6 +517,7 @@ static size_t carve_poly(const dlux_polypsf_desc* d, void* scratch, size_t cap, 
   }
   s->xin = b.take<float>(c * 2 * N);
   s->uout = b.take<float>(c * 2 * M);
+  s->sync_ws = b.take<int>(2 * c);
   s->mid_pl = take_mid_planes(b, c, (int)N, (int)M);
   s->ebar_pl = take_planes(b, c * M, (int)M);
   s->qbuf = b.take<float2>(c * N * N);
@@ -570,8 +606,6 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
       g.chunk_cnt = s.sp_cnt;
       g.chunk_idx = s.sp_idx;
     }
-    rc = run_gemm(g, d->precision, st);
-    if (rc) return rc;
     GemmParams h{};
     fill_stage(h, false, 1, N, M, c, s.xin, s.uout, sign2pi);
     h.a = s.mid_pl;
@@ -580,13 +614,13 @@ int dlux_polypsf_fwd(const dlux_polypsf_desc* d, const float* T, const float* op
       h.mode = EPI_PSF;
       h.out_psf = psf;
       h.item_w = s.w_item + b0;
-      rc = run_gemm(h, d->precision, st);
+      rc = run_gemm_pair(g, h, s.sync_ws, d->precision, st);
       if (rc) return rc;
       continue;
     }
     h.mode = EPI_C64;
     h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * M * M : s.fbuf;
-    rc = run_gemm(h, d->precision, st);
+    rc = run_gemm_pair(g, h, s.sync_ws, d->precision, st);
     if (rc) return rc;
     // psf (+)= sum over this chunk's (source, wavelength) items of w |E|^2
     rc = launch_psf_reduce((size_t)M * M, c, h.out_c64, s.w_item + b0, psf, b0 > 0, st);
@@ -658,8 +692,6 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
       g.a = s.ebar_pl;
       g.out = s.mid_pl;
       g.mode = EPI_PLANES;
-      rc = run_gemm(g, d->precision, st);
-      if (rc) return rc;
       GemmParams h{};
       fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
       h.a = s.mid_pl;
@@ -670,7 +702,7 @@ int dlux_polypsf_bwd(const dlux_polypsf_desc* d, const float* T, const float* op
         h.unit_list = s.sp_idx;
         h.unit_count = s.sp_cnt;
       }
-      rc = run_gemm(h, d->precision, st);
+      rc = run_gemm_pair(g, h, s.sync_ws, d->precision, st);
       if (rc) return rc;
       const float a0 = 1.0f / (float)((long long)N * N);
       if (pass > 0) {
@@ -747,15 +779,13 @@ int dlux_polypsf_hvp(const dlux_polypsf_desc* d, const float* T, const float* op
     g.a = s.p_pl;
     g.out = s.mid_pl;
     g.mode = EPI_PLANES;
-    rc = run_gemm(g, d->precision, st);
-    if (rc) return rc;
     GemmParams h{};
     fill_stage(h, false, 1, N, M, c, s.xin, s.uout, fwd2pi);
     h.a = s.mid_pl;
     h.mode = EPI_C64;
     h.scale = s.norm_item + b0;
     h.out_c64 = s.fbuf;
-    rc = run_gemm(h, d->precision, st);
+    rc = run_gemm_pair(g, h, s.sync_ws, d->precision, st);
     if (rc) return rc;
     if (psf_tan) {
       rc = launch_psf_tangent(mpix, c, E, s.fbuf, s.w_item + b0, psf_tan, b0 > 0, st);
@@ -771,15 +801,13 @@ int dlux_polypsf_hvp(const dlux_polypsf_desc* d, const float* T, const float* op
       ga.a = s.ebar_pl;
       ga.out = s.mid_pl;
       ga.mode = EPI_PLANES;
-      rc = run_gemm(ga, d->precision, st);
-      if (rc) return rc;
       GemmParams ha{};
       fill_stage(ha, true, 1, N, M, c, s.xin, s.uout, adj2pi);
       ha.a = s.mid_pl;
       ha.mode = EPI_C64;
       ha.scale = s.norm_item + b0;
       ha.out_c64 = s.qbuf;
-      rc = run_gemm(ha, d->precision, st);
+      rc = run_gemm_pair(ga, ha, s.sync_ws, d->precision, st);
       if (rc) return rc;
       rc = launch_hv_reduce(npix, c, s.qbuf, s.k_item + b0, T, opd, phase, s.amp_scale, a0, opd_tangent, opd_hv, pass,
                             (b0 > 0 || pass > 0) ? 1 : 0, st);
@@ -827,15 +855,13 @@ int dlux_polypsf_batch_fwd(const dlux_polypsf_batch_desc* d, const float* T, con
     g.a = s.p_pl;
     g.out = s.mid_pl;
     g.mode = EPI_PLANES;
-    rc = run_gemm(g, d->precision, st);
-    if (rc) return rc;
     GemmParams h{};
     fill_stage(h, false, 1, N, M, c, s.xin, s.uout, sign2pi);
     h.a = s.mid_pl;
     h.mode = EPI_C64;
     h.scale = s.norm_item;
     h.out_c64 = d->save_field ? (float2*)field + (size_t)b0 * L * mpix : s.fbuf;
-    rc = run_gemm(h, d->precision, st);
+    rc = run_gemm_pair(g, h, s.sync_ws, d->precision, st);
     if (rc) return rc;
     // psf[b] = sum_l w_l |E_bl|^2: per-item images, no collective, nothing summed over the batch
     rc = launch_psf_reduce(mpix, L, h.out_c64, weights, psf + (size_t)b0 * mpix, 0, st, cb);
@@ -879,15 +905,13 @@ int dlux_polypsf_batch_bwd(const dlux_polypsf_batch_desc* d, const float* T, con
     g.a = s.ebar_pl;
     g.out = s.mid_pl;
     g.mode = EPI_PLANES;
-    rc = run_gemm(g, d->precision, st);
-    if (rc) return rc;
     GemmParams h{};
     fill_stage(h, true, 1, N, M, c, s.xin, s.uout, sign2pi);
     h.a = s.mid_pl;
     h.mode = EPI_C64;
     h.scale = s.norm_item;
     h.out_c64 = s.qbuf;
-    rc = run_gemm(h, d->precision, st);
+    rc = run_gemm_pair(g, h, s.sync_ws, d->precision, st);
     if (rc) return rc;
     // opd_bar[b] = sum_l k_l Im(conj(P_bl) Q_bl), then its projection on the basis: coeff_bar[b]
     rc = launch_grad_reduce(npix, L, s.qbuf, s.k_item, T, s.opd_c, phase, s.amp_scale, a0, s.opdbar_c, nullptr,

@@ -182,6 +182,9 @@ void note_cuda_error(int code);   // remembered for dlux_last_cuda_error()
 // kernels' host launchers
 int launch_gemm_simt(const GemmParams& p, cudaStream_t st);
 int launch_gemm_tc(const GemmParams& p, cudaStream_t st);
+// fused two-stage launch (see gemm_tc.cu): ring slots it would use (0 = not applicable) and the launch itself
+int gemm_tc_fused_ring(const GemmParams& g1, const GemmParams& g2, int max_ring, int* lag_out);
+int launch_gemm_tc_fused(const GemmParams& g1, const GemmParams& g2, int ring, int lag, int* sync_ws, cudaStream_t st);
 size_t gemm_tc_workspace_bytes();
 int launch_tc_peak_probe(int kind, int n_batches, float* sink, double* flops, cudaStream_t st);
 

@@ -56,6 +56,7 @@
 // G2_lo as packed bf16 (16 k -> 8 columns each).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include "common.cuh"
 
@@ -197,6 +198,24 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       " [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// the same with an L2 cache policy (createpolicy): the fused launch keeps its ring of intermediates resident
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                 int c0, int c1, int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -223,6 +242,11 @@ __device__ __forceinline__ void umma_commit_mc2(uint32_t bar, uint16_t cta_mask)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -395,13 +419,15 @@ __device__ __forceinline__ void bulk_wait_read_n(int n) {
   else if (n == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
   else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
 }
-__device__ __forceinline__ void tile_epilogue_tma(const GemmParams& p, int item, int nq0, int m0, int lane,
+__device__ __forceinline__ void tile_epilogue_tma(const GemmParams& p, int item, int out_idx, int nq0, int m0, int lane,
                                                   float (&tot)[BM], uint32_t stg0,
-                                                  const CUtensorMap* o_re, const CUtensorMap* o_im) {
+                                                  const CUtensorMap* o_re, const CUtensorMap* o_im,
+                                                  bool keep_in_l2 = false) {
   const float sc = p.scale ? __ldg(p.scale + item) : 1.0f;
   const int mmax = p.rows - m0;
   const int j = lane >> 1, part = lane & 1;
   const uint32_t sw64 = (uint32_t)((j >> 1) & 3);
+  const uint64_t pol = keep_in_l2 ? l2_policy_evict_last() : 0;
 #pragma unroll
   for (int s = 0; s < BM / 16; ++s) {
     const int c0 = s * 16;
@@ -421,8 +447,13 @@ __device__ __forceinline__ void tile_epilogue_tma(const GemmParams& p, int item,
     __syncwarp();
     if (lane == 0) {
       const int col = m0 + c0;
-      tma_store_3d(o_re, stg, col, nq0, item);
-      tma_store_3d(o_im, stg + 1024, col, nq0, item);
+      if (keep_in_l2) {
+        tma_store_3d_hint(o_re, stg, col, nq0, out_idx, pol);
+        tma_store_3d_hint(o_im, stg + 1024, col, nq0, out_idx, pol);
+      } else {
+        tma_store_3d(o_re, stg, col, nq0, out_idx);
+        tma_store_3d(o_im, stg + 1024, col, nq0, out_idx);
+      }
       bulk_commit();
     }
   }
@@ -674,13 +705,60 @@ __device__ __forceinline__ void decode_unit(const TcParams& tp, int units_per_it
   if (SPARSE && tp.g.unit_list) t = __ldg(tp.g.unit_list + t);
 }
 
-template <bool SPARSE, bool DFT>
+// Two chained stages in ONE persistent launch (FUSED): the stage-1 -> stage-2 intermediate of an item lives in a
+// ring of `ring` slots that are rewritten every `ring` items, so it stays L2-resident and never needs HBM.
+// Work list (every cluster walks it in order, unit = cluster + i * #clusters):
+//   S1(0) .. S1(lag-1) | S1(lag) S2(0) | S1(lag+1) S2(1) | ... | S2(n-lag) .. S2(n-1)        (S = all units of an item)
+// Dependencies are per item and point BACKWARDS in the list only (lag < ring), so in-order persistent clusters
+// cannot deadlock:  S2(i) loads after ready[i] == all S1(i) stores completed;  S1(i) stores after
+// consumed[i - ring] == all S2(i - ring) units finished.
+struct FusedTc {
+  TcParams s[2];
+  int fused;                 // 0: a single stage, s[0]
+  int n_items, lag, ring, n_units_total;
+  int* ready;                // [n_items], zeroed before the launch
+  int* consumed;             // [n_items]
+  int ready_target, consumed_target;
+};
+__device__ __forceinline__ void decode_fused(const FusedTc& f, int unit, int& stage, int& item, int& t) {
+  const int n1 = f.s[0].units_per_item, n2 = f.s[1].units_per_item;
+  const int head = f.lag * n1;
+  if (unit < head) {
+    stage = 0; item = unit / n1; t = unit - item * n1;
+    return;
+  }
+  int u = unit - head;
+  const int grp = n1 + n2, n_mid = f.n_items - f.lag, mid = n_mid * grp;
+  if (u < mid) {
+    const int g = u / grp, r = u - g * grp;
+    if (r < n1) { stage = 0; item = f.lag + g; t = r; }
+    else { stage = 1; item = g; t = r - n1; }
+    return;
+  }
+  u -= mid;
+  stage = 1; item = n_mid + u / n2; t = u % n2;
+}
+__device__ __forceinline__ void wait_counter(const int* ctr, int target) {
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v < target) __nanosleep(100);
+  } while (v < target);
+}
+__device__ __forceinline__ void publish_counter(int* ctr) {
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+
+template <bool SPARSE, bool DFT, bool FUSED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                const __grid_constant__ CUtensorMap omap0, const __grid_constant__ CUtensorMap omap1,
-               const __grid_constant__ CUtensorMap omapc, const TcParams tp) {
+               const __grid_constant__ CUtensorMap omapc, const __grid_constant__ CUtensorMap map2,
+               const __grid_constant__ CUtensorMap map3, const FusedTc ftp) {
   extern __shared__ uint8_t smem_raw[];
-  int units_per_item = tp.units_per_item, n_units = tp.n_units;
+  const TcParams& tp = ftp.s[0];     // (FUSED: every unit loop re-binds tp / p to its unit's stage)
+  int units_per_item = tp.units_per_item, n_units = FUSED ? ftp.n_units_total : tp.n_units;
   if (SPARSE && tp.g.unit_list) {   // only the needed output blocks: the list length lives on the device
     units_per_item = __ldg(tp.g.unit_count);
     n_units = units_per_item * tp.g.n_items;
@@ -704,10 +782,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   if (warp == WARP_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map0));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map1));
+    if (FUSED) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map2));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map3));
+    }
     if (tp.g.mode == EPI_PLANES) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omap0));
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omap1));
-    } else if (tp.c64_tma || tp.g.mode == EPI_PSF) {
+    }
+    if (FUSED || tp.c64_tma || tp.g.mode == EPI_PSF) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&omapc));
     }
   }
@@ -758,11 +841,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       // barrier, which wakes this CTA's converter warps.
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_ring = FUSED ? l2_policy_evict_last() : 0;
       for (int unit = cl_id; unit < n_units; unit += n_cl) {
-        int item, t;
-        decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
+        int ustage = 0, item, t;
+        if (FUSED) decode_fused(ftp, unit, ustage, item, t);
+        else decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
+        const TcParams& tp = ftp.s[FUSED ? ustage : 0];
+        const GemmParams& p = tp.g;
+        const CUtensorMap* m_re = (FUSED && ustage) ? &map2 : &map0;
+        const CUtensorMap* m_im = (FUSED && ustage) ? &map3 : &map1;
         const int m0 = (t % tp.tiles_mp) * (2 * BM);
-        const int d = p.item_data ? __ldg(p.item_data + item) : item;
+        int d = p.item_data ? __ldg(p.item_data + item) : item;
+        if (FUSED && ustage) {
+          d = item % ftp.ring;                          // my data = the ring slot stage 1 filled for this item
+          wait_counter(ftp.ready + item, ftp.ready_target);
+          asm volatile("fence.proxy.async;" ::: "memory");   // the acquire above, before my async-proxy (TMA) reads
+        }
         const ChunkWalk<SPARSE> cw(tp, t % tp.tiles_mp);
         for (int ci = 0; ci < cw.n; ++ci) {
           const int kc = cw.at(ci);
@@ -775,8 +869,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             for (int tb2 = 0; tb2 < 2; ++tb2) {   // (rows beyond the matrix are zero-filled)
               const uint32_t t0 = dst + tb2 * TILE_BYTES;
               const int mr = m0 + tb2 * BM + (int)crank * ROWS_CTA;
-              tma_load_3d(t0 + 0 * PLANE_BYTES, &map0, bar, kc * BK, mr, d);   // Re
-              tma_load_3d(t0 + 1 * PLANE_BYTES, &map1, bar, kc * BK, mr, d);   // Im
+              if (FUSED && ustage) {   // the ring: keep it in L2 until its slot is rewritten
+                tma_load_3d_hint(t0 + 0 * PLANE_BYTES, m_re, bar, kc * BK, mr, d, pol_ring);
+                tma_load_3d_hint(t0 + 1 * PLANE_BYTES, m_im, bar, kc * BK, mr, d, pol_ring);
+              } else {
+                tma_load_3d(t0 + 0 * PLANE_BYTES, m_re, bar, kc * BK, mr, d);   // Re
+                tma_load_3d(t0 + 1 * PLANE_BYTES, m_im, bar, kc * BK, mr, d);   // Im
+              }
             }
           }
           __syncwarp();
@@ -802,6 +901,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       for (int unit = (crank != 0) ? n_units : cl_id; unit < n_units; unit += n_cl) {
         int n_walk = tp.k_chunks, prev = -1, kc = 0;
         const int* widx = nullptr;
+        int k_chunks_u = tp.k_chunks;
+        if (FUSED) {
+          int ustage, item_, t_;
+          decode_fused(ftp, unit, ustage, item_, t_);
+          n_walk = k_chunks_u = ftp.s[ustage].k_chunks;
+        }
         if (SPARSE) {
           int item_, t_;
           decode_unit<SPARSE>(tp, units_per_item, unit, item_, t_);
@@ -821,7 +926,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             prev = kc;
             kc = next;
           } else {
-            ps = partial_schedule_dense(ci, tp.k_chunks);
+            ps = partial_schedule_dense(ci, k_chunks_u);
           }
           bool opened = false;
           if (ps.a_open) {
@@ -884,14 +989,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     float* stg = reinterpret_cast<float*>(smem_gen + RING_BYTES + BAR_BYTES + warp * STG_WARP_BYTES);
     const uint32_t stg_addr = smem_base + RING_BYTES + BAR_BYTES + warp * STG_WARP_BYTES;
     for (int unit = cl_id; unit < n_units; unit += n_cl) {
-      int item, t;
-      decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
+      int ustage = 0, item, t;
+      if (FUSED) decode_fused(ftp, unit, ustage, item, t);
+      else decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
+      const TcParams& tp = ftp.s[FUSED ? ustage : 0];
+      const GemmParams& p = tp.g;
       const int m0 = (t % tp.tiles_mp) * (2 * BM) + which * BM;
       const int nq0 = ((t / tp.tiles_mp) * CLUSTER + (int)crank) * NB + q * 16;  // first output row of this warp's lane quarter
       float tot[BM];
 #pragma unroll
       for (int j = 0; j < BM; ++j) tot[j] = 0.0f;
-      const ChunkWalk<SPARSE> cw(tp, t % tp.tiles_mp);
+      const ChunkWalk<SPARSE> cw(tp, t % tp.tiles_mp);     // (tp = this unit's stage)
       int prev = -1, kc = (SPARSE && cw.n > 0) ? cw.at(0) : -1;
       for (int ci = 0; ci < cw.n; ++ci) {
         PartialSchedule ps;
@@ -954,9 +1062,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #ifdef DLUX_DEBUG_NOEPI
       if (m0 < p.rows && tot[5] == 123.456f) tile_epilogue_c64_lsu(p, item, nq0, m0, lane, tot, stg);
 #else
+      if (FUSED && ustage == 0 && item >= ftp.ring) {   // the ring slot's previous tenant has been consumed
+        if (lane == 0) wait_counter(ftp.consumed + (item - ftp.ring), ftp.consumed_target);
+        __syncwarp();
+      }
       if (m0 < p.rows) {  // warp-uniform condition
         if (p.mode == EPI_PLANES)
-          tile_epilogue_tma(p, item, nq0, m0, lane, tot, stg_addr, &omap0, &omap1);
+          tile_epilogue_tma(p, item, FUSED ? item % ftp.ring : item, nq0, m0, lane, tot, stg_addr, &omap0, &omap1,
+                            FUSED);
         else if (p.mode == EPI_PSF)
           tile_epilogue_psf(p, item, nq0, m0, lane, tot, stg_addr, &omapc);
         else if (tp.c64_tma)
@@ -965,6 +1078,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           tile_epilogue_c64_lsu(p, item, nq0, m0, lane, tot, stg);
       }
 #endif
+      if (FUSED && lane == 0) {
+        if (ustage == 0) {      // my share of the intermediate is in memory: one of the ready[item] arrivals
+          bulk_wait_all();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          publish_counter(ftp.ready + item);
+        } else {                // this unit no longer reads its ring slot
+          publish_counter(ftp.consumed + item);
+        }
+      }
 #ifdef DLUX_DEBUG_TIMING
       dbg_e += clock64() - te0_; ++dbg_n;
 #endif
@@ -989,6 +1111,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #endif
     for (int unit = cl_id; unit < n_units; unit += n_cl) {
       int n_walk = tp.k_chunks;
+      if (FUSED) {
+        int ustage, item_, t_;
+        decode_fused(ftp, unit, ustage, item_, t_);
+        n_walk = ftp.s[ustage].k_chunks;
+      }
       if (SPARSE) {
         int item_, t_;
         decode_unit<SPARSE>(tp, units_per_item, unit, item_, t_);
@@ -1042,8 +1169,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     const long long dbg_gstart = clock64();
 #endif
     for (int unit = cl_id; unit < n_units; unit += n_cl) {
-      int item, t;
-      decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
+      int ustage = 0, item, t;
+      if (FUSED) decode_fused(ftp, unit, ustage, item, t);
+      else decode_unit<SPARSE>(tp, units_per_item, unit, item, t);
+      const TcParams& tp = ftp.s[FUSED ? ustage : 0];
+      const GemmParams& p = tp.g;
       const ChunkWalk<SPARSE> cw(tp, t % tp.tiles_mp);
       const int n = ((t / tp.tiles_mp) * CLUSTER + (int)crank) * NB + jcol;
       const float* kv = p.kvec + (size_t)item * p.kvec_stride;
@@ -1323,12 +1453,14 @@ TcState& tc_state() {
     return st;
   }
   st.encode = (EncodeTiledFn)fn;
-  if (cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-          cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-          cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-          cudaSuccess) {
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SMEM_BYTES) != cudaSuccess) {
     st.rc = DLUX_ERR_CUDA;
     return st;
   }
@@ -1339,20 +1471,16 @@ TcState& tc_state() {
 
 size_t gemm_tc_workspace_bytes() { return 0; }
 
-int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
-  if (p.n_items <= 0) return DLUX_OK;
-  TcState& s = tc_state();
-  if (s.rc != DLUX_OK) return s.rc;
-
-  const cuuint64_t n_data = (cuuint64_t)(p.n_data > 0 ? p.n_data : p.n_items);
-  CUtensorMap maps[2];
+namespace {
+// data operand planes [n][rows][K] as TMA-load tensors (box 16 k x 64 rows, SWIZZLE_64B)
+int encode_in_maps(TcState& s, float* const hi[2], int K, int rows, cuuint64_t n, CUtensorMap maps[2]) {
   for (int i = 0; i < 2; ++i) {
-    const cuuint64_t pitch = pitch4(p.K);  // row strides are multiples of 16 bytes
-    cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.rows, n_data};
-    cuuint64_t strides[2] = {pitch * 4, pitch * 4 * (cuuint64_t)p.rows};
+    const cuuint64_t pitch = pitch4(K);  // row strides are multiples of 16 bytes
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, n};
+    cuuint64_t strides[2] = {pitch * 4, pitch * 4 * (cuuint64_t)rows};
     cuuint32_t box[3] = {BK, ROWS_CTA, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = s.encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.a.hi[i], dims, strides, box, estr,
+    CUresult r = s.encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)hi[i], dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1360,16 +1488,17 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
       return DLUX_ERR_CUDA;
     }
   }
-  // output planes of EPI_PLANES, written by TMA stores: [n_items][n_out][rows], box 16 x 16
-  CUtensorMap omaps[2];
+  return DLUX_OK;
+}
+// output planes of EPI_PLANES, written by TMA stores: [n][n_out][rows], box 16 x 16
+int encode_plane_out_maps(TcState& s, float* const hi[2], int rows, int n_out, cuuint64_t n, CUtensorMap omaps[2]) {
   for (int i = 0; i < 2; ++i) {
-    if (p.mode != EPI_PLANES) { omaps[i] = maps[i]; continue; }   // unused by the C64 epilogue
-    const cuuint64_t pitch = pitch4(p.rows);
-    cuuint64_t dims[3] = {(cuuint64_t)p.rows, (cuuint64_t)p.n_out, (cuuint64_t)p.n_items};
-    cuuint64_t strides[2] = {pitch * 4, pitch * 4 * (cuuint64_t)p.n_out};
+    const cuuint64_t pitch = pitch4(rows);
+    cuuint64_t dims[3] = {(cuuint64_t)rows, (cuuint64_t)n_out, n};
+    cuuint64_t strides[2] = {pitch * 4, pitch * 4 * (cuuint64_t)n_out};
     cuuint32_t box[3] = {16, 16, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = s.encode(&omaps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.out.hi[i], dims, strides, box, estr,
+    CUresult r = s.encode(&omaps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)hi[i], dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1377,15 +1506,18 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
       return DLUX_ERR_CUDA;
     }
   }
-  // complex64 result of EPI_C64 as a float32 tensor [n_items][n_out][2 * rows], box 32 x 16
-  CUtensorMap omapc = maps[0];
-  const int c64_tma = (p.mode == EPI_C64 && (p.rows % 2) == 0 && ((uintptr_t)p.out_c64 & 15) == 0) ? 1 : 0;
-  if (c64_tma) {
+  return DLUX_OK;
+}
+// the final result of a stage: EPI_C64 as a float32 tensor [n_items][n_out][2 * rows] (box 32 x 16), or EPI_PSF as
+// the 2-d image [n_out][rows] that receives reduce-adds
+int encode_result_map(TcState& s, const GemmParams& p, CUtensorMap* omapc, int* c64_tma) {
+  *c64_tma = (p.mode == EPI_C64 && (p.rows % 2) == 0 && ((uintptr_t)p.out_c64 & 15) == 0) ? 1 : 0;
+  if (*c64_tma) {
     cuuint64_t dims[3] = {(cuuint64_t)2 * p.rows, (cuuint64_t)p.n_out, (cuuint64_t)p.n_items};
     cuuint64_t strides[2] = {(cuuint64_t)p.rows * 8, (cuuint64_t)p.rows * 8 * (cuuint64_t)p.n_out};
     cuuint32_t box[3] = {32, 16, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = s.encode(&omapc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.out_c64, dims, strides, box, estr,
+    CUresult r = s.encode(omapc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.out_c64, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1393,13 +1525,13 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
       return DLUX_ERR_CUDA;
     }
   }
-  if (p.mode == EPI_PSF) {   // the image as a 2-d float32 tensor [n_out][rows], box 16 x 16, target of reduce-adds
+  if (p.mode == EPI_PSF) {
     if (!p.out_psf || !p.item_w || (p.rows % 4) != 0 || ((uintptr_t)p.out_psf & 15)) return DLUX_ERR_ARG;
     cuuint64_t dims[2] = {(cuuint64_t)p.rows, (cuuint64_t)p.n_out};
     cuuint64_t strides[1] = {(cuuint64_t)p.rows * 4};
     cuuint32_t box[2] = {16, 16};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = s.encode(&omapc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.out_psf, dims, strides, box, estr,
+    CUresult r = s.encode(omapc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.out_psf, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1407,18 +1539,24 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
       return DLUX_ERR_CUDA;
     }
   }
-  TcParams tp;
-  tp.g = p;
-  tp.c64_tma = c64_tma;
-  tp.tiles_mp = (p.rows + 2 * BM - 1) / (2 * BM);
-  tp.tiles_np = (p.n_out + CLUSTER * NB - 1) / (CLUSTER * NB);
-  tp.units_per_item = tp.tiles_mp * tp.tiles_np;   // (the kernel replaces both by the device-side list length)
-  const long long total = (long long)tp.units_per_item * p.n_items;
-  if (total > 2147483647LL) return DLUX_ERR_SHAPE;
-  tp.n_units = (int)total;
-  tp.k_chunks = (p.K + BK - 1) / BK;
+  return DLUX_OK;
+}
+int fill_tc_params(const GemmParams& p, int c64_tma, TcParams* tp) {
+  tp->g = p;
+  tp->c64_tma = c64_tma;
+  tp->tiles_mp = (p.rows + 2 * BM - 1) / (2 * BM);
+  tp->tiles_np = (p.n_out + CLUSTER * NB - 1) / (CLUSTER * NB);
+  tp->units_per_item = tp->tiles_mp * tp->tiles_np;   // (sparse: the kernel replaces it by the device-side list length)
+  const long long total = (long long)tp->units_per_item * p.n_items;
+  if (total > 1073741823LL) return DLUX_ERR_SHAPE;
+  tp->n_units = (int)total;
+  tp->k_chunks = (p.K + BK - 1) / BK;
+  return DLUX_OK;
+}
+template <class Kernel>
+int launch_tc(TcState& s, Kernel kernel, int n_units, cudaStream_t st, const CUtensorMap (&m)[7], const FusedTc& f) {
   const int max_clusters = s.num_sms / CLUSTER;
-  const int n_clusters = tp.n_units < max_clusters ? tp.n_units : max_clusters;
+  const int n_clusters = n_units < max_clusters ? n_units : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_clusters * CLUSTER);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -1431,14 +1569,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const bool sparse = p.chunk_cnt != nullptr || p.unit_list != nullptr;
-  const bool dft = p.dft_period > 0.0f;
-  if (dft && sparse) return DLUX_ERR_ARG;
-  cudaError_t e = dft
-      ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp)
-      : sparse
-          ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, false>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp)
-          : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, false>, maps[0], maps[1], omaps[0], omaps[1], omapc, tp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, m[0], m[1], m[2], m[3], m[4], m[5], m[6], f);
   if (e != cudaSuccess) {
     fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
     note_cuda_error((int)e);
@@ -1447,7 +1578,91 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   note_launch();
   return check_launch("gemm_tc");
 }
+}  // namespace
 
+int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
+  if (p.n_items <= 0) return DLUX_OK;
+  TcState& s = tc_state();
+  if (s.rc != DLUX_OK) return s.rc;
+  CUtensorMap m[7];
+  int rc = encode_in_maps(s, p.a.hi, p.K, p.rows, (cuuint64_t)(p.n_data > 0 ? p.n_data : p.n_items), &m[0]);
+  if (rc) return rc;
+  m[2] = m[0]; m[3] = m[1];     // unused by the C64 / PSF epilogues
+  if (p.mode == EPI_PLANES && (rc = encode_plane_out_maps(s, p.out.hi, p.rows, p.n_out, (cuuint64_t)p.n_items, &m[2])))
+    return rc;
+  m[4] = m[0];
+  int c64_tma = 0;
+  if ((rc = encode_result_map(s, p, &m[4], &c64_tma))) return rc;
+  m[5] = m[0]; m[6] = m[1];     // stage-2 operand of the fused launch: unused
+  FusedTc f{};
+  if ((rc = fill_tc_params(p, c64_tma, &f.s[0]))) return rc;
+  f.s[1] = f.s[0];
+  const bool sparse = p.chunk_cnt != nullptr || p.unit_list != nullptr;
+  const bool dft = p.dft_period > 0.0f;
+  if (dft && sparse) return DLUX_ERR_ARG;
+  const int n_units = f.s[0].n_units;
+  if (dft) return launch_tc(s, gemm_tc_kernel<false, true, false>, n_units, st, m, f);
+  if (sparse) return launch_tc(s, gemm_tc_kernel<true, false, false>, n_units, st, m, f);
+  return launch_tc(s, gemm_tc_kernel<false, false, false>, n_units, st, m, f);
+}
+
+int gemm_tc_fused_ring(const GemmParams& g1, const GemmParams& g2, int max_ring, int* lag_out) {
+  TcState& s = tc_state();
+  if (s.rc != DLUX_OK) return 0;
+  TcParams a, b;
+  if (fill_tc_params(g1, 0, &a) || fill_tc_params(g2, 0, &b)) return 0;
+  const int n_cl = s.num_sms / CLUSTER;
+  // stage 2 of an item starts >= two "waves" of units after its stage 1, so that its operand is complete
+  // by the time the clusters get there (waits are then the exception, not the rule)
+  static const double waves = [] {
+    const char* e = getenv("DLUX_B200_FUSE_WAVES");
+    const double v = e ? atof(e) : 0.0;
+    return v > 0.0 ? v : 2.0;
+  }();
+  const int per_item = a.units_per_item + b.units_per_item;
+  int lag = (int)((waves * n_cl + per_item - 1) / per_item) + 1;
+  if (lag > g1.n_items) lag = g1.n_items;
+  int ring = lag + 2;
+  if (ring > g1.n_items) ring = g1.n_items;
+  if (ring > max_ring) return 0;          // (lag < ring must hold unless the ring covers every item)
+  if (lag_out) *lag_out = lag;
+  return ring;
+}
+
+// Stage 1 (EPI_PLANES into a ring of `ring` item slots at g1.out) and stage 2 (whose data operand g2.a is that ring)
+// of the same items in one persistent launch.  sync_ws: 2 * n_items ints (zeroed here).
+int launch_gemm_tc_fused(const GemmParams& g1, const GemmParams& g2, int ring, int lag, int* sync_ws, cudaStream_t st) {
+  if (g1.n_items <= 0) return DLUX_OK;
+  TcState& s = tc_state();
+  if (s.rc != DLUX_OK) return s.rc;
+  if (g1.mode != EPI_PLANES || g2.mode == EPI_PLANES || g1.n_items != g2.n_items || g2.K != g1.rows ||
+      g2.rows != g1.n_out || g1.sign2pi != g2.sign2pi || g1.dft_period > 0.0f || g1.chunk_cnt || g1.unit_list ||
+      g2.chunk_cnt || g2.unit_list || ring < 1 || lag < 1 || (lag >= ring && ring < g1.n_items))
+    return DLUX_ERR_ARG;
+  CUtensorMap m[7];
+  int rc = encode_in_maps(s, g1.a.hi, g1.K, g1.rows, (cuuint64_t)(g1.n_data > 0 ? g1.n_data : g1.n_items), &m[0]);
+  if (rc) return rc;
+  if ((rc = encode_plane_out_maps(s, g1.out.hi, g1.rows, g1.n_out, (cuuint64_t)ring, &m[2]))) return rc;
+  m[4] = m[0];
+  int c64_tma = 0;
+  if ((rc = encode_result_map(s, g2, &m[4], &c64_tma))) return rc;
+  if ((rc = encode_in_maps(s, g1.out.hi, g2.K, g2.rows, (cuuint64_t)ring, &m[5]))) return rc;
+  FusedTc f{};
+  if ((rc = fill_tc_params(g1, 0, &f.s[0])) || (rc = fill_tc_params(g2, c64_tma, &f.s[1]))) return rc;
+  f.fused = 1;
+  f.n_items = g1.n_items;
+  f.lag = lag;
+  f.ring = ring;
+  const long long total = (long long)f.s[0].n_units + f.s[1].n_units;
+  if (total > 2147483647LL) return DLUX_ERR_SHAPE;
+  f.n_units_total = (int)total;
+  f.ready = sync_ws;
+  f.consumed = sync_ws + g1.n_items;
+  f.ready_target = f.s[0].units_per_item * CLUSTER * NUM_EPI_WARPS;
+  f.consumed_target = f.s[1].units_per_item * CLUSTER * NUM_EPI_WARPS;
+  if ((rc = launch_zero(reinterpret_cast<float*>(sync_ws), 2 * (size_t)g1.n_items, st))) return rc;
+  return launch_tc(s, gemm_tc_kernel<false, false, true>, f.n_units_total, st, m, f);
+}
 
 // Launches the MMA-only probe; returns the real FLOPs it executes (0 on error) through *flops.
 int launch_tc_peak_probe(int kind, int n_batches, float* sink, double* flops, cudaStream_t st) {
