@@ -322,7 +322,8 @@ __global__ void basis_eval_kernel(int nz, size_t npix, const float* __restrict__
   extern __shared__ float c_sm[];
   coeffs += (size_t)blockIdx.y * nz;          // blockIdx.y = element of a parameter batch
   out += (size_t)blockIdx.y * npix;
-  for (int z = threadIdx.x; z < nz; z += blockDim.x) c_sm[z] = coeffs[z];
+  // (the buffer is padded to a multiple of 8 coefficients: the unrolled loop below may read them in 16-byte pieces)
+  for (int z = threadIdx.x; z < ((nz + 7) & ~7); z += blockDim.x) c_sm[z] = z < nz ? coeffs[z] : 0.0f;
   __syncthreads();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -336,7 +337,7 @@ __global__ void basis_eval_kernel(int nz, size_t npix, const float* __restrict__
 int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coeffs,
                       const float* base, float* out, cudaStream_t st, int n_batch) {
   dim3 grid(grid_for((size_t)npix, 256, n_batch > 1 ? 148 * 4 : 148 * 16), n_batch);
-  basis_eval_kernel<<<grid, 256, nz * sizeof(float), st>>>(nz, (size_t)npix, basis, coeffs, base, out);
+  basis_eval_kernel<<<grid, 256, ((nz + 7) & ~7) * sizeof(float), st>>>(nz, (size_t)npix, basis, coeffs, base, out);
   note_launch();
   return check_launch("basis_eval");
 }
