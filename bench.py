@@ -126,9 +126,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Statistics of the samples received in [t0, t1] (perf_counter; default: all of them).  nvidia-smi needs
+        ~0.1-0.2 s to deliver its first line, so the sampler is started well before the window it is asked about."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -138,7 +140,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r[1:] for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1 + 0.03)]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 try:
@@ -233,31 +236,6 @@ def run_c4_strong(dev, world, rank, steps=3, n_stars=64):
         (psf * G).sum().backward()
         D.all_reduce_grads([phase, pos, flux])
         return psf
-
-    # the same step captured once into a CUDA graph through the public API (dl.GraphedValueAndGrad, the role
-    # jax.jit plays for the reference's value_and_grad loop); single GPU only (no NCCL inside the capture)
-    gstep = None
-    if world == 1:
-        stars = dl.PointSources(cfg["wavelengths"], all_positions, all_fluxes, weights=cfg["weights"])
-
-        def loss_fn(c, G):
-            e2e_layer.coefficients = c
-            psf = stars.model(optics)
-            return (psf * G).sum(), psf
-        try:
-            gstep = dl.GraphedValueAndGrad(loss_fn, [coeffs_d, G_d], has_aux=True, argnums=[0])
-        except Exception as e:                          # pragma: no cover
-            print("bench: CUDA-graph capture of the e2e step failed:", repr(e), file=sys.stderr)
-            gstep = None
-
-    def step_e2e_graph():
-        gstep.static[0].detach().copy_(coeffs_h, non_blocking=True)
-        gstep.static[1].copy_(G_h, non_blocking=True)
-        gstep.graph.replay()
-        psf_h.copy_(gstep.aux.detach(), non_blocking=True)
-        grad_h.copy_(gstep.grads[0], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(psf_h[0, 0])
 
     def barrier():
         if world > 1:
@@ -412,14 +390,19 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local)                      # every rank samples its own board
+    sampler.start()                                    # (early: nvidia-smi's first line takes ~0.2 s)
+    t_w = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         step_device()
-    sampler = ClockSampler(local)                      # every rank samples its own board
-    sampler.start()
+    torch.cuda.synchronize()
+    while time.perf_counter() - t_w < 0.4 and not sampler.rows:   # untimed: wait for the sampler to be alive
+        step_device()
+        torch.cuda.synchronize()
     launches0 = _lib.launch_count()
+    t_c0 = time.perf_counter()
     ms_total = timed(step_device, args.steps)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = world * 1e3 / ms_step                      # PSF+grad per second, all ranks
 
@@ -427,7 +410,11 @@ def run_ours(args):
     _lib.profile_enable(True)
     timed(step_device, args.steps)
     _lib.profile_enable(False)
+    t_c1 = time.perf_counter()
     gemm_ms, gemm_launches, gemm_flops = _lib.profile_read()
+    # clocks over the timed region + the identical roofline pass right after it (>= 0.1 s even at 20 steps)
+    clocks = sampler.stop(t_c0, t_c1)
+    clocks["window_s"] = t_c1 - t_c0
 
     # ---- sustained regime: the same step back to back for >= 3 s (power-capped clocks)
     sus = None

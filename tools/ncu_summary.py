@@ -38,6 +38,8 @@ def main():
     if g:
         out["dram_bytes_per_gemm_launch"] = g["dram_bytes_per_launch"]
     out["dram_bytes_total"] = sum(k["dram_read"] + k["dram_write"] for k in ker.values())
+    if not steps:   # one pupil_kernel launch per PSF + gradient step
+        steps = float(next((v["launches"] for k, v in out["kernels"].items() if k.startswith("pupil_kernel")), 0))
     if steps:
         out["steps_in_capture"] = steps
         out["dram_bytes_per_step"] = out["dram_bytes_total"] / steps
