@@ -151,6 +151,19 @@ __device__ __forceinline__ void fast_sincos_mufu(float a, int qshift, float* sn,
   *cs = __uint_as_float(co ^ (((q + 1u) & 2u) << 30));   // negate in quadrants 1, 2
 }
 
+// Leanest variant, for the tensor-core kernel's generator warps (their instruction count bounds the kernel):
+// ONE reduction modulo 2 pi (the same Cody-Waite constants x 4; the third term is < 4e-10 rad for |a| < 1e5 and
+// is dropped), then MUFU.SIN / MUFU.COS on |r| <= pi, where the unit's absolute error is the same ~3e-7 as on
+// the first quadrant -- no quadrant swap / sign logic at all (9 instructions instead of 19 per phasor).
+__device__ __forceinline__ void fast_sincos_turn(float a, float* sn, float* cs) {
+  float j = fmaf(a, 0.159154937f, 12582912.0f);
+  j -= 12582912.0f;
+  float r = fmaf(j, -4.0f * 1.57079601e+00f, a);
+  r = fmaf(j, -4.0f * 3.13916473e-07f, r);
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+}
+
 // (re, im) -> the two operand planes at element offset o4
 __device__ __forceinline__ void plane_store(const PlaneSet& ps, size_t o4, float re, float im) {
   ps.hi[0][o4] = re;

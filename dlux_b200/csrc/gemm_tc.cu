@@ -616,11 +616,16 @@ __device__ __forceinline__ void issue_tile_chunk(uint32_t d, uint32_t g0, uint32
   umma_bf16_ts2(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);                // G1_hi * Re_lo
   umma_bf16_ts2(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);                // G2_lo * Im_hi
   umma_bf16_ts2(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);                // G2_hi * Im_lo
+#ifdef DLUX_EXP_F16X3   // timing experiment only (wrong numbers): hi*hi at the kind::f16 rate
+  umma_bf16_ts2(d, gb + 0 * GB_COLS, b_rh, IDESC_BF16, 1u);
+  umma_bf16_ts2(d, gb + 2 * GB_COLS, b_ih, IDESC_BF16, 1u);
+#else
 #pragma unroll
   for (int ks = 0; ks < BK / UMMA_K; ++ks) {
     umma_tf32_ts2(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);        // G1_hi * Re_hi
     umma_tf32_ts2(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);   // G2_hi * Im_hi
   }
+#endif
 }
 
 // Where the TMEM partial accumulators of the two tiles open and close along the k-chunks of
@@ -680,6 +685,7 @@ struct TcParams {
   int tiles_mp, tiles_np, n_units, k_chunks;  // pairs of 128-row data tiles, pairs of 64-column n-tiles
   int c64_tma;                                // EPI_C64 output goes through TMA stores (even row length)
   int units_per_item;                         // tiles_mp * tiles_np, or the length of unit_list
+  int kvec_vec4;                              // kvec rows can be read four coordinates (16 bytes) at a time
 };
 
 // The K loop of one unit: dense (0 .. k_chunks-1) or, with exact zero-block skipping, the list of k-chunks
@@ -750,6 +756,27 @@ __device__ __forceinline__ void publish_counter(int* ctr) {
   asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 
+// one generator warp's share of a phasor stage: k-step KS of the two tf32 planes and of the four packed-bf16 planes
+template <int KS>
+__device__ __forceinline__ void store_phasors(uint32_t g0, const float (&g1h)[8], const float (&g2h)[8],
+                                              const uint32_t (&pk)[4][4]) {
+  tmem_st8(g0 + KS * UMMA_K, g1h);        // tf32 G1_hi: columns [0,16)
+  tmem_st8(g0 + BK + KS * UMMA_K, g2h);   // tf32 G2_hi: columns [16,32)
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) tmem_st4u(g0 + GB_BASE + q4 * GB_COLS + KS * (UMMA_K / 2), pk[q4]);
+}
+
+// four consecutive coordinates kv[k .. k+3] (zero past K)
+__device__ __forceinline__ void load_k4(const float* __restrict__ kv, int k, int K, bool vec4, float (&x)[4]) {
+  if (vec4) {
+    const float4 v = (k < K) ? __ldg(reinterpret_cast<const float4*>(kv + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = (k + j < K) ? __ldg(kv + k + j) : 0.0f;
+  }
+}
+
 template <bool SPARSE, bool DFT, bool FUSED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
@@ -777,7 +804,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(
       smem_gen + RING_BYTES + 8 * (3 * A_STAGES + 2 * G_STAGES + 2 * NUM_ACC));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the broadcast tells ptxas that `warp` is warp-uniform: role dispatch, tensor-memory addresses and barrier
+  // addresses derived from it then live in uniform registers)
+  const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (warp == WARP_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map0));
@@ -1182,14 +1211,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       // evaluates 4 of them (even lane k 0..3 of the k-step, odd lane k 4..7) and passes the
       // other lane what it needs with one shuffle per value.
       const int half = lane & 1;
-      const uint32_t sgn = (uint32_t)half << 31;
+      // four consecutive k per lane: one 16-byte load when the coordinate rows allow it (K and the row pitch
+      // multiples of 4, checked on the host), scalar loads otherwise
+      const bool kv4 = tp.kvec_vec4 != 0;
+      const int kofs = ks * UMMA_K + half * 4;
       float xk[4];  // my four k coordinates of this chunk, prefetched one chunk ahead
       const int kc0 = (SPARSE && cw.n > 0) ? cw.at(0) : 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kc0 * BK + ks * UMMA_K + half * 4 + j;
-        xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
-      }
+      load_k4(kv, kc0 * BK + kofs, p.K, kv4, xk);
       for (int ci = 0; ci < cw.n; ++ci) {
         // Evaluate into registers first, THEN wait for the TMEM stage: with only two phasor
         // stages the evaluation must overlap the MMAs that still read the stage.
@@ -1200,17 +1228,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #ifdef DLUX_DEBUG_NOGEN
           sn = xk[j]; cs = u;
 #else
-          fast_sincos_mufu(DFT ? dft_arg(p.sign2pi, xk[j], u, p.dft_period, dft_inv) : phase_arg(p.sign2pi, xk[j], u),
-                           qshift, &sn, &cs);
+          fast_sincos_turn(DFT ? dft_arg(p.sign2pi, xk[j], u, p.dft_period, dft_inv) : phase_arg(p.sign2pi, xk[j], u),
+                           &sn, &cs);
 #endif
-          // mine: (G1, G2) = (cs, -sn).  The other lane's: even -> odd (sin, cos) = (sn, cs);
-          // odd -> even (cos, -sin) = (-sn, -cs) in terms of my quarter-turn-shifted values.
-          const float r1 = __shfl_xor_sync(0xFFFFFFFFu, __uint_as_float(__float_as_uint(sn) ^ sgn), 1);
-          const float r2 = __shfl_xor_sync(0xFFFFFFFFu, __uint_as_float(__float_as_uint(cs) ^ sgn), 1);
-          g1[j] = half ? r1 : cs;
-          g1[4 + j] = half ? cs : r1;
-          g2[j] = half ? r2 : -sn;
-          g2[4 + j] = half ? -sn : r2;
+          // even lane (Re row): (G1, G2) = (cos, -sin), k 0..3 mine, k 4..7 the partner's;
+          // odd lane (Im row):  (G1, G2) = (sin,  cos), k 4..7 mine, k 0..3 the partner's
+          const float ps = __shfl_xor_sync(0xFFFFFFFFu, sn, 1);
+          const float pc = __shfl_xor_sync(0xFFFFFFFFu, cs, 1);
+          g1[j] = half ? ps : cs;
+          g1[4 + j] = half ? sn : pc;
+          g2[j] = half ? pc : -sn;
+          g2[4 + j] = half ? cs : -ps;
         }
         float g1h[8], g2h[8];
         uint32_t pk[4][4];  // packed bf16: G1_hi, G1_lo, G2_hi, G2_lo, 8 k -> 4 columns each
@@ -1230,21 +1258,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           pk[2][jj] = pack_bf16(g2h[2 * jj], g2h[2 * jj + 1]);
           pk[3][jj] = pack_bf16(g2l2[0], g2l2[1]);
         }
-#pragma unroll
         int knext0 = (ci + 1) * BK;     // dense: the next chunk follows
         if (SPARSE) {
           const int kc_next = cw.next_of(ci);
           knext0 = kc_next < 0 ? p.K : kc_next * BK;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {  // next chunk's coordinates (latency hidden behind the wait)
-          const int k = knext0 + ks * UMMA_K + half * 4 + j;
-#ifdef DLUX_DEBUG_NOXLD
-          xk[j] = (float)k * 1e-3f;
-#else
-          xk[j] = (k < p.K) ? __ldg(kv + k) : 0.0f;
-#endif
-        }
+        load_k4(kv, knext0 + kofs, p.K, kv4, xk);   // next chunk's coordinates (latency hidden behind the wait)
 #ifdef DLUX_DEBUG_TIMING
         const long long tg1_ = clock64();
         mbar_wait(emptyG_bar(stage), phase ^ 1);
@@ -1254,14 +1273,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #endif
         tc_fence_after();
         const uint32_t g0 = tmem_base + lane_addr + (uint32_t)(G_BASE_COL + stage * G_COLS);
-        tmem_st8(g0 + ks * UMMA_K, g1h);        // tf32 G1_hi: columns [0,16)
-        tmem_st8(g0 + BK + ks * UMMA_K, g2h);   // tf32 G2_hi: columns [16,32)
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) tmem_st4u(g0 + GB_BASE + q4 * GB_COLS + ks * (UMMA_K / 2), pk[q4]);
+        // (a warp-uniform branch: every column offset of the six stores is then a compile-time constant)
+        if (ks == 0) store_phasors<0>(g0, g1h, g2h, pk);
+        else store_phasors<1>(g0, g1h, g2h, pk);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(fullG_bar(stage) + lead_delta);
+        if (elect_one()) mbar_arrive_cluster(fullG_bar(stage) + lead_delta);
         if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -1551,6 +1569,7 @@ int fill_tc_params(const GemmParams& p, int c64_tma, TcParams* tp) {
   if (total > 1073741823LL) return DLUX_ERR_SHAPE;
   tp->n_units = (int)total;
   tp->k_chunks = (p.K + BK - 1) / BK;
+  tp->kvec_vec4 = (p.K % 4 == 0 && p.kvec_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(p.kvec) & 15) == 0) ? 1 : 0;
   return DLUX_OK;
 }
 template <class Kernel>
