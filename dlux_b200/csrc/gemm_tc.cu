@@ -616,16 +616,11 @@ __device__ __forceinline__ void issue_tile_chunk(uint32_t d, uint32_t g0, uint32
   umma_bf16_ts2(d, gb + 0 * GB_COLS, b_rl, IDESC_BF16, 1u);                // G1_hi * Re_lo
   umma_bf16_ts2(d, gb + 3 * GB_COLS, b_ih, IDESC_BF16, 1u);                // G2_lo * Im_hi
   umma_bf16_ts2(d, gb + 2 * GB_COLS, b_il, IDESC_BF16, 1u);                // G2_hi * Im_lo
-#ifdef DLUX_EXP_F16X3   // timing experiment only (wrong numbers): hi*hi at the kind::f16 rate
-  umma_bf16_ts2(d, gb + 0 * GB_COLS, b_rh, IDESC_BF16, 1u);
-  umma_bf16_ts2(d, gb + 2 * GB_COLS, b_ih, IDESC_BF16, 1u);
-#else
 #pragma unroll
   for (int ks = 0; ks < BK / UMMA_K; ++ks) {
     umma_tf32_ts2(d, g0 + ks * UMMA_K, d_rh + ks * KS, IDESC, 1u);        // G1_hi * Re_hi
     umma_tf32_ts2(d, g0 + BK + ks * UMMA_K, d_ih + ks * KS, IDESC, 1u);   // G2_hi * Im_hi
   }
-#endif
 }
 
 // Where the TMEM partial accumulators of the two tiles open and close along the k-chunks of
