@@ -158,13 +158,9 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-#ifdef DLUX_ARRIVE_RELEASE
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-#else
   // relaxed: what the arrival publishes lives in tensor memory and is ordered by the
   // tcgen05 fences around it, not by the generic-proxy release
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-#endif
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -211,28 +207,15 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// publishes generic-proxy shared-memory writes (fenced to the async proxy by their writers) to the
-// MMA issuer of the leader CTA
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// default semantics (.release at CTA scope): the converted operand never leaves this CTA's shared memory
+// The converters' arrival on the leader's fullA barrier (their generic-proxy writes are fenced to the async proxy
+// first).  Default semantics, .release at CTA scope: the converted operand never leaves this CTA's shared memory
 // -- each SM's tensor core reads its own half -- only the signal crosses to the leader (the form CUTLASS'
-// 2-SM transform pipelines use after fence.proxy.async)
+// 2-SM transform pipelines use after fence.proxy.async; a .release.cluster arrival cost ~700 cycles per chunk)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void ld_shared_v4(uint32_t addr, float (&v)[4]) {
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc2(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -250,7 +233,6 @@ __device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, uint32
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -294,10 +276,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-               ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
 __device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t (&v)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
@@ -576,21 +554,14 @@ __device__ __forceinline__ void convert_plane(uint8_t* fplane, uint8_t* bplane_h
       const uint32_t sw32 = (uint32_t)((r >> 2) & 1);
       uint4 ph, plo;
       float4 h0, h1;
-#ifdef DLUX_CONV_TRUNC
-#define TF32_SPLIT(x) __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)   // what the MMA itself would keep
-#else
-#define TF32_SPLIT(x) tf32_hi(x)
-#endif
-      h0.x = TF32_SPLIT(v[u][0].x); h0.y = TF32_SPLIT(v[u][0].y); h0.z = TF32_SPLIT(v[u][0].z); h0.w = TF32_SPLIT(v[u][0].w);
-      h1.x = TF32_SPLIT(v[u][1].x); h1.y = TF32_SPLIT(v[u][1].y); h1.z = TF32_SPLIT(v[u][1].z); h1.w = TF32_SPLIT(v[u][1].w);
+      h0.x = tf32_hi(v[u][0].x); h0.y = tf32_hi(v[u][0].y); h0.z = tf32_hi(v[u][0].z); h0.w = tf32_hi(v[u][0].w);
+      h1.x = tf32_hi(v[u][1].x); h1.y = tf32_hi(v[u][1].y); h1.z = tf32_hi(v[u][1].z); h1.w = tf32_hi(v[u][1].w);
       ph.x = pack_bf16(h0.x, h0.y); ph.y = pack_bf16(h0.z, h0.w);
       ph.z = pack_bf16(h1.x, h1.y); ph.w = pack_bf16(h1.z, h1.w);
       plo.x = pack_bf16(v[u][0].x - h0.x, v[u][0].y - h0.y); plo.y = pack_bf16(v[u][0].z - h0.z, v[u][0].w - h0.w);
       plo.z = pack_bf16(v[u][1].x - h1.x, v[u][1].y - h1.y); plo.w = pack_bf16(v[u][1].z - h1.z, v[u][1].w - h1.w);
-#ifndef DLUX_CONV_TRUNC
       *src[u][0] = h0;
       *src[u][1] = h1;
-#endif
       uint8_t* brow = bplane_hi + r * 32 + ((h ^ sw32) << 4);
       *reinterpret_cast<uint4*>(brow) = ph;
       *reinterpret_cast<uint4*>(brow + BPLANE_BYTES) = plo;
@@ -963,9 +934,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           }
 #ifdef DLUX_DEBUG_TIMING
           const long long t0_ = clock64();
-#ifndef DLUX_DEBUG_NOGWAIT
           mbar_wait_cluster(fullG_bar(sg), pg);
-#endif
           const long long t1_ = clock64();
           mbar_wait_cluster(fullA_bar(sa), pa);
           const long long t2_ = clock64();
@@ -1054,20 +1023,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #endif
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
-#ifdef DLUX_DRAIN_X32
-#pragma unroll
-        for (int c = 0; c < BM; c += 32) {
-          uint32_t v0[16], v1[16];
-          tmem_ld16(t0 + c, v0);
-          tmem_ld16(t0 + c + 16, v1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            tot[c + j] += __uint_as_float(v0[j]);
-            tot[c + 16 + j] += __uint_as_float(v1[j]);
-          }
-        }
-#else
 #pragma unroll
         for (int c = 0; c < BM; c += 16) {
           uint32_t v0[16];
@@ -1076,16 +1031,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 16; ++j) tot[c + j] += __uint_as_float(v0[j]);
         }
-#endif
         tc_fence_before();
         mbar_arrive_cluster(tempty_bar(buf) + lead_delta);
       }
 #ifdef DLUX_DEBUG_TIMING
       const long long te0_ = clock64();
 #endif
-#ifdef DLUX_DEBUG_NOEPI
-      if (m0 < p.rows && tot[5] == 123.456f) tile_epilogue_c64_lsu(p, item, nq0, m0, lane, tot, stg);
-#else
       if (FUSED && ustage == 0 && item >= ftp.ring) {   // the ring slot's previous tenant has been consumed
         if (lane == 0) wait_counter(ftp.consumed + (item - ftp.ring), ftp.consumed_target);
         __syncwarp();
@@ -1101,7 +1052,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         else
           tile_epilogue_c64_lsu(p, item, nq0, m0, lane, tot, stg);
       }
-#endif
       if (FUSED && lane == 0) {
         if (ustage == 0) {      // my share of the intermediate is in memory: one of the ready[item] arrivals
           bulk_wait_all();
@@ -1156,13 +1106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         uint8_t* sb = smem_gen + cstage * A_BYTES;
         convert_plane(sb + off_f, sb + off_b, lane);
         __syncwarp();
-#if defined(DLUX_CONV_RELAXED)
-        if (lane == 0) mbar_arrive_cluster(fullA_bar(cstage) + lead_delta);
-#elif defined(DLUX_CONV_RELEASE_CLUSTER)
-        if (lane == 0) mbar_arrive_release_cluster(fullA_bar(cstage) + lead_delta);
-#else
         if (lane == 0) mbar_arrive_remote(fullA_bar(cstage) + lead_delta);
-#endif
 #ifdef DLUX_DEBUG_TIMING
         dbg_cw += tc1_ - tc0_; dbg_cc += clock64() - tc1_;
 #endif
@@ -1183,7 +1127,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     const int q = warp & 3;                          // TMEM lane quarter
     const int ks = (warp - FIRST_GEN_WARP) >> 2;     // which k-step of the chunk
     const float dft_inv = DFT ? 1.0f / p.dft_period : 0.0f;
-    const int qshift = (lane & 1) ? -1 : 0;          // odd lane = imaginary row of the phasor column
     const int jcol = (q * 32 + lane) >> 1;           // phasor column within the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int stage = 0;
@@ -1220,12 +1163,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float sn, cs;
-#ifdef DLUX_DEBUG_NOGEN
-          sn = xk[j]; cs = u;
-#else
           fast_sincos_turn(DFT ? dft_arg(p.sign2pi, xk[j], u, p.dft_period, dft_inv) : phase_arg(p.sign2pi, xk[j], u),
                            &sn, &cs);
-#endif
           // even lane (Re row): (G1, G2) = (cos, -sin), k 0..3 mine, k 4..7 the partner's;
           // odd lane (Im row):  (G1, G2) = (sin,  cos), k 4..7 mine, k 0..3 the partner's
           const float ps = __shfl_xor_sync(0xFFFFFFFFu, sn, 1);
