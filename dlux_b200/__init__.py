@@ -18,7 +18,7 @@ from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, Cartesian
 from .sources import (BinarySource, PointResolvedSource, PointSource, PointSources, ResolvedSource,
                       Scene)
 from .wavefronts import CoordSpec, Wavefront
-from .graphs import GraphedValueAndGrad
+from .graphs import GraphedFitStep, GraphedValueAndGrad
 
 __version__ = "0.1.0"
 __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer",
@@ -28,4 +28,4 @@ __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "Aberrated
            "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "AberratedAperture", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "PSF", "DetectorLayer",
            "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",
-           "LayeredDetector", "Telescope", "GraphedValueAndGrad"]
+           "LayeredDetector", "Telescope", "GraphedValueAndGrad", "GraphedFitStep"]

@@ -361,6 +361,43 @@ def test_cuda_graph_step_matches_eager(dev):
         assert rel_l2(g.cpu().numpy(), c.grad.cpu().numpy()) < 1e-6
 
 
+def test_graphed_fit_step_with_host_io(dev):
+    """GraphedFitStep: the captured step with its host copies on side branches of the graph (data upload under the
+    forward pass, image download under the backward pass) returns what the eager step returns, for new host values
+    on every replay."""
+    import dlux_b200 as dl
+    from dlux_b200 import workloads
+    cfg = workloads.config("c2")
+    basis, T = (torch.as_tensor(cfg[k], device=dev) for k in ("basis", "transmission"))
+    c0 = torch.as_tensor(cfg["coefficients"], device=dev)
+    layer = dl.BasisOptic(basis, T, c0, normalise=True, effect="opd", device=dev)
+    optics = dl.AngularOpticalSystem(cfg["wf_npixels"], cfg["diameter"], [("p", layer)], cfg["psf_npixels"],
+                                     cfg["psf_pixel_scale"], cfg["oversample"], device=dev)
+    src = dl.PointSource(cfg["wavelengths"], np.zeros(2, np.float32), 1.0, weights=cfg["weights"])
+    M = cfg["psf_npixels"] * cfg["oversample"]
+    c_h = torch.empty(c0.numel(), dtype=torch.float32).pin_memory()
+    G_h = torch.empty(M, M, dtype=torch.float32).pin_memory()
+    psf_h = torch.empty(M, M, dtype=torch.float32).pin_memory()
+    g_h = torch.empty(c0.numel(), dtype=torch.float32).pin_memory()
+
+    def model_fn(c):
+        layer.coefficients = c
+        return src.model(optics)
+
+    fit = dl.GraphedFitStep(model_fn, lambda psf, G: (psf * G).sum(), [c0], [torch.zeros(M, M, device=dev)],
+                            host_params=[c_h], host_data=[G_h], host_image=psf_h, host_grads=[g_h])
+    rng = np.random.default_rng(5)
+    for scale in (1.0, -0.5, 2.0):
+        c_h.copy_(torch.as_tensor(cfg["coefficients"] * scale))
+        G_h.copy_(torch.as_tensor(rng.standard_normal((M, M)).astype(np.float32)))
+        fit.step()
+        c = c_h.to(dev).requires_grad_(True)
+        psf = model_fn(c)
+        (psf * G_h.to(dev)).sum().backward()
+        assert rel_l2(psf_h.numpy(), psf.detach().cpu().numpy()) < 1e-6
+        assert rel_l2(g_h.numpy(), c.grad.cpu().numpy()) < 1e-6
+
+
 def test_aberrated_aperture(dev):
     """AberratedAperture (apertures.py:643-800): Zernike OPD generated on the aperture's own transformed, normalised
     coordinates; forward on both routes and gradients w.r.t. the Zernike coefficients and the aperture translation
