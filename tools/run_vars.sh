@@ -8,7 +8,7 @@ for v in "$@"; do
     *T) timeout 60 python tools/timing_probe.py 64 2>&1 | grep "MMA\|DRAIN0\|GEN\|CONV" | tail -10 ;;
     *P) timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ;;
     *S) timeout 200 python bench.py --steps 50 --warmup 5 --sustained 4 --sparse 0 --c4-stars 0 2>/dev/null | tail -1 > /tmp/b.json; python tools/bench_summary.py /tmp/b.json ;;
-    *) timeout 150 python bench.py --steps 50 --warmup 5 --sustained 0 --sparse 0 --c4-stars 0 2>/dev/null | tail -1 > /tmp/b.json; python tools/bench_summary.py /tmp/b.json ;;
+    *) timeout 90 python bench.py --steps 50 --warmup 5 --sustained 0 --sparse 0 --c4-stars 0 2>/dev/null | tail -1 > /tmp/b.json; python tools/bench_summary.py /tmp/b.json ;;
   esac
 done
 cp dlux_b200/lib/var_CUR.so dlux_b200/lib/libdlux_b200.so 2>/dev/null
