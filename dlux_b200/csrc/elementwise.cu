@@ -325,6 +325,27 @@ __global__ void basis_eval_kernel(int nz, size_t npix, const float* __restrict__
   // (the buffer is padded to a multiple of 8 coefficients: the unrolled loop below may read them in 16-byte pieces)
   for (int z = threadIdx.x; z < ((nz + 7) & ~7); z += blockDim.x) c_sm[z] = z < nz ? coeffs[z] : 0.0f;
   __syncthreads();
+  if ((npix & 3) == 0 && ((reinterpret_cast<uintptr_t>(basis) | reinterpret_cast<uintptr_t>(out) |
+                            reinterpret_cast<uintptr_t>(base)) & 15) == 0) {
+    // four pixels per thread: 16-byte loads, 8 modes = 128 bytes in flight per thread
+    const size_t n4 = npix / 4;
+    const float4* b4 = reinterpret_cast<const float4*>(basis);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 8
+      for (int z = 0; z < nz; ++z) {
+        const float4 b = __ldg(b4 + (size_t)z * n4 + i);
+        const float c = c_sm[z];
+        acc.x = fmaf(c, b.x, acc.x); acc.y = fmaf(c, b.y, acc.y); acc.z = fmaf(c, b.z, acc.z); acc.w = fmaf(c, b.w, acc.w);
+      }
+      if (base) {
+        const float4 v = reinterpret_cast<const float4*>(base)[i];
+        acc.x = v.x + acc.x; acc.y = v.y + acc.y; acc.z = v.z + acc.z; acc.w = v.w + acc.w;
+      }
+      reinterpret_cast<float4*>(out)[i] = acc;
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
        i += (size_t)gridDim.x * blockDim.x) {
     float acc = 0.0f;
@@ -336,7 +357,7 @@ __global__ void basis_eval_kernel(int nz, size_t npix, const float* __restrict__
 
 int launch_basis_eval(int nz, int64_t npix, const float* basis, const float* coeffs,
                       const float* base, float* out, cudaStream_t st, int n_batch) {
-  dim3 grid(grid_for((size_t)npix, 256, n_batch > 1 ? 148 * 4 : 148 * 16), n_batch);
+  dim3 grid(grid_for((npix & 3) == 0 ? (size_t)npix / 4 : (size_t)npix, 256, n_batch > 1 ? 148 * 4 : 148 * 16), n_batch);
   basis_eval_kernel<<<grid, 256, ((nz + 7) & ~7) * sizeof(float), st>>>(nz, (size_t)npix, basis, coeffs, base, out);
   note_launch();
   return check_launch("basis_eval");
@@ -355,22 +376,39 @@ __global__ void basis_reduce_kernel(int nz, size_t npix, const float* __restrict
   float g[PER];
   out_bar += (size_t)blockIdx.y * npix;       // blockIdx.y = element of a parameter batch
   coeff_bar += (size_t)blockIdx.y * nz;
-  const size_t base_i = ((size_t)blockIdx.x * blockDim.x) * PER + threadIdx.x;
-  // each block owns a contiguous chunk of PER*blockDim pixels (grid sized to cover npix)
+  // each block owns a contiguous chunk of PER*blockDim pixels (grid sized to cover npix); a thread takes four
+  // CONSECUTIVE pixels with 16-byte loads when the arrays allow it, else four pixels blockDim apart
+  const bool vec = (npix & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(basis) | reinterpret_cast<uintptr_t>(out_bar)) & 15) == 0;
+  const size_t base_i = ((size_t)blockIdx.x * blockDim.x) * PER + (vec ? (size_t)threadIdx.x * PER : threadIdx.x);
+  const size_t step = vec ? 1 : blockDim.x;
+  if (vec) {
+    const float4 v = base_i < npix ? *reinterpret_cast<const float4*>(out_bar + base_i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+  } else {
 #pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const size_t i = base_i + (size_t)j * blockDim.x;
-    g[j] = i < npix ? out_bar[i] : 0.0f;
+    for (int j = 0; j < PER; ++j) {
+      const size_t i = base_i + (size_t)j * step;
+      g[j] = i < npix ? out_bar[i] : 0.0f;
+    }
   }
-  for (int z0 = 0; z0 < nz; z0 += 4) {        // four modes per round: 32 independent loads in flight per thread
+  for (int z0 = 0; z0 < nz; z0 += 4) {        // four modes per round: 16 values (64 bytes) in flight per thread
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int zz = 0; zz < 4; ++zz) {
       if (z0 + zz < nz) {
+        const float* bz = basis + (size_t)(z0 + zz) * npix;
+        if (vec) {
+          if (base_i < npix) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bz + base_i));
+            acc[zz] = fmaf(g[3], b.w, fmaf(g[2], b.z, fmaf(g[1], b.y, g[0] * b.x)));
+          }
+        } else {
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-          const size_t i = base_i + (size_t)j * blockDim.x;
-          if (i < npix) acc[zz] = fmaf(g[j], __ldg(basis + (size_t)(z0 + zz) * npix + i), acc[zz]);
+          for (int j = 0; j < PER; ++j) {
+            const size_t i = base_i + (size_t)j * step;
+            if (i < npix) acc[zz] = fmaf(g[j], __ldg(bz + i), acc[zz]);
+          }
         }
       }
     }
@@ -611,7 +649,7 @@ __global__ void q_reduce_kernel(int N, int n_items, const float2* __restrict__ q
     const float xc = ((float)c - half) * inv, yc = ((float)r - half) * inv;
     float kprev = 0.0f, sn = 0.0f, cs = 1.0f;
     bool have = false;
-    constexpr int UN = 4;                     // four independent loads of Q in flight per thread
+    constexpr int UN = 8;                     // eight independent loads of Q in flight per thread
     for (int it0 = 0; it0 < n_items; it0 += UN) {
       float2 vv[UN];
 #pragma unroll

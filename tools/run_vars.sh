@@ -1,5 +1,6 @@
 # usage: run_vars.sh VARIANT...   (libs prepared as dlux_b200/lib/var_<VARIANT>.so; a trailing T = timing build,
-# a trailing S = also the sustained record, a trailing P = run the GPU parity tests with that library)
+# a trailing S = also the sustained record, a trailing P = run the GPU parity tests with that library: do not
+# end a variant NAME in T, S or P)
 for v in "$@"; do
   lib=${v%S}; lib=${lib%P}
   cp dlux_b200/lib/var_$lib.so dlux_b200/lib/libdlux_b200.so
