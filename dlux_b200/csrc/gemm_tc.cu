@@ -1507,8 +1507,7 @@ int fill_tc_params(const GemmParams& p, int c64_tma, TcParams* tp) {
   return DLUX_OK;
 }
 template <class Kernel>
-int launch_tc(TcState& s, Kernel kernel, int n_units, cudaStream_t st, const CUtensorMap (&m)[7], const FusedTc& f,
-              bool co_resident = false) {
+int launch_tc(TcState& s, Kernel kernel, int n_units, cudaStream_t st, const CUtensorMap (&m)[7], const FusedTc& f) {
   const int max_clusters = s.num_sms / CLUSTER;
   const int n_clusters = n_units < max_clusters ? n_units : max_clusters;
   cudaLaunchConfig_t cfg{};
@@ -1516,19 +1515,13 @@ int launch_tc(TcState& s, Kernel kernel, int n_units, cudaStream_t st, const CUt
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CLUSTER;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  // The fused launch's clusters wait for each other's counters: every cluster of the grid must be resident
-  // at the same time.  The grid never exceeds one CTA per SM, but SMs may be busy with somebody else's
-  // kernel (another stream, another process) -- a cooperative launch makes the driver place the whole grid
-  // at once instead of letting resident clusters spin on counters that unscheduled ones would advance.
-  attr[1].id = cudaLaunchAttributeCooperative;
-  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = co_resident ? 2 : 1;
+  cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, m[0], m[1], m[2], m[3], m[4], m[5], m[6], f);
   if (e != cudaSuccess) {
     fprintf(stderr, "[dlux_b200] cudaLaunchKernelEx(gemm_tc): %s\n", cudaGetErrorString(e));
@@ -1621,7 +1614,7 @@ int launch_gemm_tc_fused(const GemmParams& g1, const GemmParams& g2, int ring, i
   f.ready_target = f.s[0].units_per_item * CLUSTER * NUM_EPI_WARPS;
   f.consumed_target = f.s[1].units_per_item * CLUSTER * NUM_EPI_WARPS;
   if ((rc = launch_zero(reinterpret_cast<float*>(sync_ws), 2 * (size_t)g1.n_items, st))) return rc;
-  return launch_tc(s, gemm_tc_kernel<false, false, true>, f.n_units_total, st, m, f, true);
+  return launch_tc(s, gemm_tc_kernel<false, false, true>, f.n_units_total, st, m, f);
 }
 
 // Launches the MMA-only probe; returns the real FLOPs it executes (0 on error) through *flops.
