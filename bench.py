@@ -107,54 +107,97 @@ def load_traffic():
 
 # ---------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """SM clock, power and throttle reasons of one board, sampled every ~10 ms by a thread of this process through
+    NVML (pynvml); `nvidia-smi -lms 20` through a line-buffered pipe when NVML cannot be loaded.  Every sample carries
+    the wall-clock time it was taken at, so `stop(t0, t1)` reports exactly the samples of the timed window."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, False
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
         try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                ["stdbuf", "-oL", "nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
-
-    def stop(self, t0=None, t1=None):
-        """Statistics of the samples received in [t0, t1] (perf_counter; default: all of them).  nvidia-smi needs
-        ~0.1-0.2 s to deliver its first line, so the sampler is started well before the window it is asked about."""
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r[1:] for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1 + 0.03)]
-        for r in rows:
+    def _poll(self):
+        n = self.nvml
+        bits = [(n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8),
+                (n.nvmlClocksEventReasonHwThermalSlowdown if hasattr(n, "nvmlClocksEventReasonHwThermalSlowdown") else 0x40),
+                (n.nvmlClocksEventReasonSwThermalSlowdown if hasattr(n, "nvmlClocksEventReasonSwThermalSlowdown") else 0x20),
+                (n.nvmlClocksEventReasonSwPowerCap if hasattr(n, "nvmlClocksEventReasonSwPowerCap") else 0x4)]
+        while not self._stop:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                try:
-                    pw.append(float(r[2]))
-                except ValueError:
-                    pass
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append((time.time(), sm, self.mx, pw, [nm for nm, b in zip(self.NAMES, bits) if rs & b]))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w": float(np.median(pw)) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(0.01)
+
+    def _read(self):
+        import datetime
+        for line in self.proc.stdout:
+            c = [x.strip() for x in line.split(",")]
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                pw = float(c[3]) if c[3].replace(".", "", 1).isdigit() else None
+                self.rows.append((ts, float(c[1]), float(c[2]), pw,
+                                  [nm for nm, v in zip(self.NAMES, c[4:8]) if v.lower().startswith("active")]))
+            except Exception:
+                pass
+
+    def alive(self):
+        return bool(self.rows)
+
+    def stop(self, t0=None, t1=None):
+        """Statistics of the samples taken in [t0, t1] (time.time(); default: all of them)."""
+        self._stop = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if not self.source:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML, no nvidia-smi"], "samples": 0}
+        rows = [r for r in list(self.rows) if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        sm = [r[1] for r in rows]
+        pw = [r[3] for r in rows if r[3] is not None]
+        reasons = sorted({x for r in rows for x in r[4]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "power_w": float(np.median(pw)) if pw else None, "reasons": reasons, "samples": len(sm),
+                "source": self.source}
 
 
 # ---------------------------------------------------------------------------- CPU arm
@@ -414,11 +457,11 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
-    while time.perf_counter() - t_w < 0.4 and not sampler.rows:   # untimed: wait for the sampler to be alive
+    while time.perf_counter() - t_w < 0.4 and not sampler.alive():   # untimed: wait for the sampler to be alive
         step_device()
         torch.cuda.synchronize()
     launches0 = _lib.launch_count()
-    t_c0 = time.perf_counter()
+    t_c0 = time.time()
     ms_total = timed(step_device, args.steps)
     launches = _lib.launch_count() - launches0
     ms_step = ms_total / args.steps
@@ -428,7 +471,7 @@ def run_ours(args):
     _lib.profile_enable(True)
     timed(step_device, args.steps)
     _lib.profile_enable(False)
-    t_c1 = time.perf_counter()
+    t_c1 = time.time()
     gemm_ms, gemm_launches, gemm_flops = _lib.profile_read()
     # clocks over the timed region + the identical roofline pass right after it (>= 0.1 s even at 20 steps)
     clocks = sampler.stop(t_c0, t_c1)
