@@ -420,6 +420,37 @@ def run_ours(args):
             print("bench: GraphedFitStep capture failed:", repr(e), file=sys.stderr)
             fstep = None
 
+    # N > 1: the local part of the step (this rank's shard, forward and backward) replayed from two CUDA graphs
+    # (torch.cuda.make_graphed_callables), the two NCCL all-reduces issued between / after them as usual
+    gshard = None
+    if world > 1:
+        def local_model(c):
+            e2e_layer.coefficients = c
+            return D.sharded_point_sources_model(optics, cfg["wavelengths"], all_positions, all_fluxes,
+                                                 cfg["weights"], reduce=False)
+        try:
+            gshard = torch.cuda.make_graphed_callables(local_model, (coeffs_d.detach().clone().requires_grad_(True),))
+        except Exception as e:                          # pragma: no cover
+            print("bench: graph capture of the sharded step failed:", repr(e), file=sys.stderr)
+            gshard = None
+        ok = torch.tensor([1 if gshard is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # every rank takes the same path
+        if int(ok.item()) == 0:
+            gshard = None
+
+    def step_e2e_sharded_graphs():
+        c = coeffs_h.to(dev, non_blocking=True).requires_grad_(True)
+        G = G_h.to(dev, non_blocking=True)
+        psf_local = gshard(c)
+        psf = psf_local.detach().clone()
+        dist.all_reduce(psf)
+        psf_h.copy_(psf, non_blocking=True)
+        psf_local.backward(G)                           # d sum(G * psf_total) / d psf_local = G on every rank
+        D.all_reduce_grads([c])
+        grad_h.copy_(c.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(psf_h[0, 0])
+
     def step_e2e_fit():
         fstep.step()
         return float(psf_h[0, 0])
@@ -513,10 +544,19 @@ def run_ours(args):
     # ---- e2e arm
     for _ in range(3):
         step_e2e()
+    psf_ref_h, grad_ref_h = psf_h.clone(), grad_h.clone()      # what the eager step delivered to the host
+
+    def same_as_eager(step):                                   # the captured variants must deliver the same
+        psf_h.zero_(); grad_h.zero_()
+        step()
+        r = lambda a, b: float((a - b).norm() / b.norm())
+        return max(r(psf_h, psf_ref_h), r(grad_h, grad_ref_h))
+    e2e_dev = {}
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_eager = world * 1e3 / ms_e2e
     e2e_api = "eager public API (BasisOptic + AngularOpticalSystem + PointSources.model + backward)"
     if gstep is not None:
+        e2e_dev["graph"] = same_as_eager(step_e2e_graph)
         for _ in range(3):
             step_e2e_graph()
         ms_g = timed(step_e2e_graph, args.steps) / args.steps
@@ -524,8 +564,19 @@ def run_ours(args):
             ms_e2e = ms_g
             e2e_api = ("the same public-API step captured once by dl.GraphedValueAndGrad and replayed (host buffers copied "
                        "in and out every step)")
+    if gshard is not None:
+        e2e_dev["sharded_graphs"] = same_as_eager(step_e2e_sharded_graphs)
+        for _ in range(3):
+            step_e2e_sharded_graphs()
+        ms_s = timed(step_e2e_sharded_graphs, args.steps) / args.steps
+        if ms_s < ms_e2e:
+            ms_e2e = ms_s
+            e2e_api = ("the public-API step with this rank's shard (forward and backward) replayed from two CUDA graphs "
+                       "(torch.cuda.make_graphed_callables) and the two NCCL all-reduces issued eagerly; host buffers "
+                       "copied in and out every step")
     e2e_serial = e2e_fit = None
     if fstep is not None:
+        e2e_dev["graph_with_host_io"] = same_as_eager(step_e2e_fit)
         for _ in range(3):
             step_e2e_fit()
         ms_f = timed(step_e2e_fit, args.steps) / args.steps
@@ -629,6 +680,7 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "api": e2e_api, "eager_value": e2e_eager,
                 "serial_copies_value": e2e_serial, "graph_with_host_io_value": e2e_fit,
+                "rel_diff_vs_eager_step": e2e_dev,
                 # (the eager step also re-uploads the wavelength / weight vectors; the captured steps keep them resident)
                 "h2d_bytes_per_step": int(coeffs_h.numel() * 4 + G_h.numel() * 4 +
                                           (4 * 3 * L + 8 * L if e2e_api.startswith("eager") else 0)),

@@ -81,12 +81,14 @@ def all_reduce_grads(params: Sequence[torch.Tensor], group=None) -> None:
 
 
 def sharded_point_sources_model(optics, wavelengths, positions, fluxes, weights=None, group=None,
-                                model_fn: Optional[Callable] = None):
+                                model_fn: Optional[Callable] = None, reduce: bool = True):
     """``PointSources(wavelengths, positions, fluxes, weights).model(optics)`` with the
     (source x wavelength) items sharded over the ranks of `group`.
 
     ``model_fn(wavelengths, positions, weights_SL) -> psf`` defaults to the fused CUDA
-    path ``optics.fused_propagate``; the CPU tests inject the oracle here."""
+    path ``optics.fused_propagate``; the CPU tests inject the oracle here.  ``reduce=False`` returns this
+    rank's partial image without the all-reduce (for callers that capture the local work into a CUDA graph and
+    issue the collective themselves)."""
     wavelengths = np.atleast_1d(np.asarray(wavelengths, dtype=np.float32))
     positions = positions if torch.is_tensor(positions) else np.asarray(positions, dtype=np.float32)
     fluxes = fluxes if torch.is_tensor(fluxes) else np.asarray(fluxes, dtype=np.float32)
@@ -111,4 +113,4 @@ def sharded_point_sources_model(optics, wavelengths, positions, fluxes, weights=
                           requires_grad=True)
     else:
         psf = fn(wavelengths[ls], positions[ss], w_sl[ss, ls])
-    return all_reduce_sum(psf, group)
+    return all_reduce_sum(psf, group) if reduce else psf
