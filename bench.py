@@ -422,8 +422,10 @@ def run_ours(args):
 
     # N > 1: the local part of the step (this rank's shard, forward and backward) replayed from two CUDA graphs
     # (torch.cuda.make_graphed_callables), the two NCCL all-reduces issued between / after them as usual
+    # OPT-IN (DLUX_BENCH_SHARD_GRAPHS=1): measured at N = 2 (+11 % over eager launches), but the capture hung
+    # the N = 4 run, so the default e2e path at N > 1 stays the eager step
     gshard = None
-    if world > 1:
+    if world > 1 and os.environ.get("DLUX_BENCH_SHARD_GRAPHS", "0") == "1":
         def local_model(c):
             e2e_layer.coefficients = c
             return D.sharded_point_sources_model(optics, cfg["wavelengths"], all_positions, all_fluxes,
