@@ -52,6 +52,34 @@ def test_scratch_sizes_and_arg_checks(lib):
     assert lib.dlux_basis_eval(0, 10, None, None, None, None, None) == -1
 
 
+def test_round2_descriptors_host_checks(lib):
+    """ABI v2 additions, checked on the host side only (no CUDA call is reached): the exact-DFT period of
+    ``dlux_mft_desc``, the parameter-batch descriptor and the scratch queries that size the fused launch's ring."""
+    import ctypes as C
+    from dlux_b200._lib import MftDesc, PolyPsfBatchDesc, PolyPsfDesc
+    assert lib.dlux_abi_version() == 2
+    # dlu.FFT through the MFT kernels: period = padded size; negative periods and index products that are not
+    # exact in float32 are refused
+    assert lib.dlux_mft_scratch_bytes(C.byref(MftDesc(1024, 2048, 1, 0, 0, 0, 2048, 0))) > 0
+    assert lib.dlux_mft_scratch_bytes(C.byref(MftDesc(64, 128, 1, 0, 0, 0, -1, 0))) == 0
+    assert lib.dlux_mft_scratch_bytes(C.byref(MftDesc(4096, 8192, 1, 0, 0, 0, 8192, 0))) == 0
+    assert lib.dlux_mft_c64(C.byref(MftDesc(64, 128, 1, 0, 0, 0, -1, 0)), None, None, None, None, None, None,
+                            None, 0, None) == -1
+    # the sparse option does not change the scratch layout; more items never need less scratch
+    dense = lib.dlux_polypsf_scratch_bytes(C.byref(PolyPsfDesc(1024, 512, 64, 1, 1, 0, 1, 0)))
+    assert lib.dlux_polypsf_scratch_bytes(C.byref(PolyPsfDesc(1024, 512, 64, 1, 1, 0, 1, 1))) == dense
+    assert lib.dlux_polypsf_scratch_bytes(C.byref(PolyPsfDesc(1024, 512, 64, 4, 1, 0, 1, 0))) >= dense
+    assert lib.dlux_polypsf_scratch_bytes(C.byref(PolyPsfDesc(1024, 512, 0, 1, 1, 0, 1, 0))) == 0
+    b = PolyPsfBatchDesc()
+    b.n_pupil, b.n_psf, b.n_wavels, b.n_batch, b.n_basis, b.normalise = 1024, 256, 32, 128, 10, 1
+    n128 = lib.dlux_polypsf_batch_scratch_bytes(C.byref(b))
+    assert n128 > 0
+    b.n_batch = 4096                                  # chunked by whole batch elements: bounded scratch
+    assert n128 <= lib.dlux_polypsf_batch_scratch_bytes(C.byref(b)) < 40 * 1024 ** 3
+    b.n_basis = 0
+    assert lib.dlux_polypsf_batch_scratch_bytes(C.byref(b)) == 0
+
+
 def test_missing_library_is_loud(monkeypatch):
     from dlux_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
