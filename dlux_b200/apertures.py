@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from collections import OrderedDict
 
+import math
+
 import numpy as np
 import torch
 
@@ -108,9 +110,6 @@ class AberratedAperture(OpticalLayer):
             raise TypeError("AberratedApertures cannot contain Static, Compound or Multi Apertures (or spiders).")
         if aperture.occulting:
             raise TypeError("AberratedApertures cannot be occulting.")
-        if getattr(aperture, "nsides", None) != 0:
-            raise NotImplementedError("dlux_b200: AberratedAperture mirrors circular apertures (Zernike basis); "
-                                      "the polygon 'polike' bases are not implemented")
         if effect not in ("opd", "phase", "amplitude"):
             raise ValueError("effect must be 'opd', 'phase', or 'amplitude'.")
         self.aperture = aperture
@@ -129,13 +128,16 @@ class AberratedAperture(OpticalLayer):
     def transmission(self, coords, pixel_scale):        # :732-733
         return self.aperture.transmission(coords, pixel_scale)
 
-    def calc_basis(self, coords):                       # :735-752
-        from .utils.zernikes import zernike_basis_torch
+    def calc_basis(self, coords):                       # :735-752; polynomials.py:40-51: Zernikes on a circular
+        from .utils.zernikes import polike_basis_torch, zernike_basis_torch   # aperture, "polikes" on n sides
         if self.aperture.transformation is not None:
             coords = self.aperture.transformation(coords)
         ext = self.aperture.extent
         ext = ext.to(coords.device, coords.dtype) if torch.is_tensor(ext) else float(ext)
-        return zernike_basis_torch(self.noll_inds, coords / ext)
+        nsides = int(self.aperture.nsides)
+        if nsides == 0:
+            return zernike_basis_torch(self.noll_inds, coords / ext)
+        return polike_basis_torch(nsides, self.noll_inds, coords / ext)
 
     def eval_basis(self, coords):                       # :754-771
         c = self.coefficients
@@ -163,6 +165,12 @@ class SquareAperture(_DynamicAperture):
     def _shape(self, coords, clip):
         return G.soft_square(coords, self.width, clip, self.occulting)
 
+    @property
+    def extent(self):                                   # apertures.py:382-383
+        return math.sqrt(2) * self.width
+
+    nsides = 4                                          # :386-387
+
 
 class RectangularAperture(_DynamicAperture):
     def __init__(self, height, width, transformation=None, occulting=False, softening=1.0, normalise=False):
@@ -172,6 +180,14 @@ class RectangularAperture(_DynamicAperture):
 
     def _shape(self, coords, clip):
         return G.soft_rectangle(coords, self.width, self.height, clip, self.occulting)
+
+    @property
+    def extent(self):                                   # apertures.py:467-468
+        if torch.is_tensor(self.height) or torch.is_tensor(self.width):
+            return torch.hypot(torch.as_tensor(self.height) / 2.0, torch.as_tensor(self.width) / 2.0)
+        return np.float32(np.hypot(self.height / 2.0, self.width / 2.0))
+
+    nsides = 4                                          # :471-472
 
 
 class RegPolyAperture(_DynamicAperture):
@@ -183,6 +199,10 @@ class RegPolyAperture(_DynamicAperture):
 
     def _shape(self, coords, clip):
         return G.soft_reg_polygon(coords, self.rmax, self.nsides, clip, self.occulting)
+
+    @property
+    def extent(self):                                   # apertures.py:550-551
+        return self.rmax
 
 
 class Spider(_DynamicAperture):

@@ -10,7 +10,8 @@ import math
 
 import numpy as np
 
-__all__ = ["noll_indices", "zernike", "zernike_basis", "zernike_basis_torch"]
+__all__ = ["noll_indices", "zernike", "zernike_basis", "zernike_basis_torch", "polike", "polike_basis",
+           "polike_basis_torch"]
 
 
 def noll_indices(j: int):
@@ -30,7 +31,12 @@ def noll_indices(j: int):
 def zernike(j: int, coordinates, diameter: float = 2.0):
     """Z_j on cartesian `coordinates` [2, npix, npix] (x first), zero outside the unit disk of
     the given diameter."""
-    c = np.asarray(coordinates, dtype=np.float64) / (float(diameter) / 2)
+    # the support test rho <= 1 is made on float32 radii, as the reference's float32 arrays make it (pixels that
+    # sit exactly on the edge -- every polygon edge pixel of a symmetric grid -- would otherwise fall outside);
+    # the polynomial itself is evaluated in float64 and rounded once
+    c32 = np.asarray(coordinates, dtype=np.float32) / np.float32(float(diameter) / 2)
+    inside = np.hypot(c32[0], c32[1]) <= np.float32(1.0)
+    c = c32.astype(np.float64)
     rho, theta = np.hypot(c[0], c[1]), np.arctan2(c[1], c[0])
     n, m = noll_indices(j)
     ma = abs(m)
@@ -41,7 +47,7 @@ def zernike(j: int, coordinates, diameter: float = 2.0):
         radial += coef * rho ** (n - 2 * k)
     norm = math.sqrt(n + 1) * (math.sqrt(2) if m != 0 else 1.0)
     az = np.cos(ma * theta) if m >= 0 else np.sin(ma * theta)
-    return ((rho <= 1.0) * radial * norm * az).astype(np.float32)
+    return (inside * radial * norm * az).astype(np.float32)
 
 
 def zernike_basis(js, coordinates, diameter: float = 2.0):
@@ -69,3 +75,47 @@ def zernike_basis_torch(js, coordinates, diameter: float = 2.0):
         az = torch.cos(ma * theta) if m >= 0 else torch.sin(ma * theta)
         out.append(inside * radial * norm * az)
     return torch.stack(out)
+
+
+def _polike_radius(theta, nsides: int, xp):
+    """r_alpha(theta): the polygon's edge distance along direction theta in units of its circumradius
+    (/root/reference/src/dLux/utils/zernikes.py:343-348, 390-394): the Zernikes are evaluated on coordinates
+    stretched by 1 / r_alpha so that the unit disk maps onto the n-sided polygon."""
+    alpha = math.pi / nsides
+    phi = theta + alpha
+    wedge = xp.floor((phi + alpha) / (2.0 * alpha))
+    u_alpha = phi - wedge * (2 * alpha)
+    return math.cos(alpha) / xp.cos(u_alpha)
+
+
+def polike(nsides: int, j: int, coordinates, diameter: float = 2.0):
+    """Z_j on an n-sided regular polygon ("polike", utils/zernikes.py:318-349): ``1 / r_alpha * Z_j(c / r_alpha)``."""
+    if nsides < 3:
+        raise ValueError(f"nsides must be >= 3, not {nsides}.")
+    # float32 throughout the coordinate stretch, in the reference's order of operations: which edge pixels are
+    # inside depends on these roundings
+    F = np.float32
+    c = np.asarray(coordinates, dtype=np.float32) / F(float(diameter) / 2)
+    alpha = math.pi / nsides
+    phi = np.arctan2(c[1], c[0]) + F(alpha)
+    wedge = np.floor((phi + F(alpha)) / F(2.0 * alpha))
+    u_alpha = phi - wedge * F(2 * alpha)
+    r_alpha = F(math.cos(alpha)) / np.cos(u_alpha)
+    return (F(1) / r_alpha * zernike(j, c / r_alpha, 2.0)).astype(np.float32)
+
+
+def polike_basis(nsides: int, js, coordinates, diameter: float = 2.0):
+    return np.stack([polike(nsides, int(j), coordinates, diameter) for j in js])
+
+
+def polike_basis_torch(nsides: int, js, coordinates, diameter: float = 2.0):
+    """Differentiable torch form on a (possibly transformed) coordinate tensor: what ``DynamicZernikeBasis``
+    evaluates for an aperture with ``nsides > 0`` (/root/reference/src/dLux/polynomials.py:40-51 ->
+    ``polike_fast``, utils/zernikes.py:352-395)."""
+    import torch
+    if nsides < 3:
+        raise ValueError(f"nsides must be >= 3, not {nsides}.")
+    c = coordinates / (float(diameter) / 2)
+    r_alpha = _polike_radius(torch.atan2(c[1], c[0]), nsides, torch)
+    return 1.0 / r_alpha * zernike_basis_torch(js, c / r_alpha, 2.0)
+

@@ -104,6 +104,12 @@ def main():
     zer = sys.modules["dLux.utils.zernikes"]
     out["zernikes_1_15"] = onp.asarray(zer.zernike_basis(list(range(1, 16)), coords, f32(diam)), onp.float32)
     out["noll_nm_1_21"] = onp.array([zer.noll_indices(j) for j in range(1, 22)], onp.int64)
+    # the same polynomials on n-sided regular polygons ("polikes", utils/zernikes.py:318-416), plain and on the
+    # transformed coordinates
+    for ns in (4, 5, 6):
+        out[f"polike_{ns}_1_10"] = onp.asarray(zer.polike_basis(ns, list(range(1, 11)), coords, f32(diam)), onp.float32)
+    out["polike_6_1_10_xf"] = onp.asarray(zer.polike_basis(6, list(range(1, 11)), ro.astype(onp.float32), f32(1.6)),
+                                          onp.float32)
     path = os.path.join(HERE, "reference_geometry.npz")
     onp.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays", os.path.getsize(path), "bytes")

@@ -97,6 +97,56 @@ def test_zernike_basis_matches_reference(gold):
         assert abs(np.sqrt((got[j][inside] ** 2).mean()) - 1.0) < 0.06
 
 
+def test_polike_basis_matches_reference(gold):
+    # utils/zernikes.py:318-416 executed by make_golden_geometry.py: the Zernikes stretched onto 4-, 5- and 6-sided
+    # polygons, plain and on transformed coordinates with another diameter; NumPy and differentiable torch forms
+    import torch
+    from dlux_b200.utils.zernikes import polike, polike_basis, polike_basis_torch
+    for key, ns, coords, diam in (("polike_4_1_10", 4, gold["coords"], 2.0), ("polike_5_1_10", 5, gold["coords"], 2.0),
+                                  ("polike_6_1_10", 6, gold["coords"], 2.0),
+                                  ("polike_6_1_10_xf", 6, gold["rotated"].astype(np.float32), 1.6)):
+        want = gold[key]
+        got = polike_basis(ns, range(1, 11), coords, diam)
+        got_t = polike_basis_torch(ns, range(1, 11), torch.as_tensor(coords, dtype=torch.float32), diam).numpy()
+        assert got.shape == want.shape and got.dtype == np.float32
+        for j in range(10):
+            # pixels exactly on the polygon's edge (stretched radius within one float32 rounding of 1) may fall on
+            # either side: allowed for a handful of pixels, and only as "inside here, outside there"
+            tol = 2e-5 * np.abs(want[j]).max()
+            for name, g, frac in (("numpy", got[j], 0.005), ("torch", got_t[j], 0.02)):
+                bad = np.abs(g - want[j]) > tol
+                assert bad.mean() < frac, (key, name, j, int(bad.sum()))
+                assert np.all((g[bad] == 0) | (want[j][bad] == 0)), (key, name, j)
+    with pytest.raises(ValueError):
+        polike(2, 1, gold["coords"])
+
+
+def test_aberrated_polygon_aperture_on_a_cpu_wavefront():
+    # layers/apertures.py:643-800 with a RegPolyAperture: the aberration basis follows the aperture's transformation
+    # and extent, and is the polike basis of its number of sides (polynomials.py:40-51)
+    import torch
+    import dlux_b200 as dl
+    from dlux_b200.utils.zernikes import polike_basis_torch
+    wf = dl.Wavefront(1e-6, 48, diameter=2.0, device="cpu")
+    tfm = dl.CoordTransform(translation=np.array([0.05, -0.03], np.float32), rotation=np.float32(0.2))
+    hexa = dl.RegPolyAperture(6, np.float32(0.8), tfm, normalise=True)
+    coeffs = torch.tensor([2e-8, -1e-8, 3e-8], dtype=torch.float32, requires_grad=True)
+    ab = dl.AberratedAperture(hexa, [4, 5, 6], coeffs, effect="opd")
+    coords = wf.coordinates()
+    want_basis = polike_basis_torch(6, [4, 5, 6], tfm(coords) / 0.8)
+    np.testing.assert_allclose(ab.calc_basis(coords).detach().numpy(), want_basis.numpy(), rtol=1e-6, atol=1e-7)
+    out = ab(wf)
+    want = wf * hexa.transmission(coords, wf.pixel_scale)
+    want = want.normalise().add_opd(torch.tensordot(coeffs.detach(), want_basis.to(torch.float32), dims=1))
+    np.testing.assert_allclose(out.phasor.detach().numpy(), want.phasor.numpy(), rtol=1e-5, atol=1e-9)
+    out.phasor.real.sum().backward()                     # the coefficients stay differentiable through the layer
+    assert coeffs.grad is not None and float(coeffs.grad.abs().sum()) > 0
+    sq = dl.AberratedAperture(dl.SquareAperture(np.float32(1.0)), [1, 2, 3])
+    assert sq.calc_basis(coords).shape == (3, 48, 48)    # nsides = 4, extent = sqrt(2) * width
+    with pytest.raises(TypeError):
+        dl.AberratedAperture(dl.Spider(np.float32(0.05), [0.0, 90.0]), [1])
+
+
 def test_aperture_layers_on_a_cpu_wavefront():
     # layers/apertures.py:134-152, 1005-1117: a dynamic aperture multiplies the wavefront by its
     # transmission on the wavefront's own coordinates; Compound = product, Multi = sum
