@@ -398,10 +398,12 @@ def test_graphed_fit_step_with_host_io(dev):
         assert rel_l2(g_h.numpy(), c.grad.cpu().numpy()) < 1e-6
 
 
-def test_aberrated_aperture(dev):
-    """AberratedAperture (apertures.py:643-800): Zernike OPD generated on the aperture's own transformed, normalised
-    coordinates; forward on both routes and gradients w.r.t. the Zernike coefficients and the aperture translation
-    against the float64 twin fed by the same geometry evaluated in float64 on the CPU."""
+@pytest.mark.parametrize("shape", ["circle", "hexagon"])
+def test_aberrated_aperture(dev, shape):
+    """AberratedAperture (apertures.py:643-800): Zernike OPD (polike OPD on the polygon, utils/zernikes.py:318-395)
+    generated on the aperture's own transformed, normalised coordinates; forward on both routes and gradients w.r.t.
+    the coefficients and the aperture translation against the float64 twin fed by the same geometry evaluated in
+    float64 on the CPU."""
     import dlux_b200 as dl
     from conftest import check, rel_scalar
     from dlux_b200.utils import geometry as G
@@ -415,8 +417,9 @@ def test_aberrated_aperture(dev):
     t0 = np.array([0.02, -0.03], np.float32)
 
     def build(coeffs, trans):
-        ap = dl.CircularAperture(np.float32(0.42), transformation=dl.CoordTransform(translation=trans), softening=2.0,
-                                 normalise=True)
+        tf = dl.CoordTransform(translation=trans)
+        ap = (dl.CircularAperture(np.float32(0.42), transformation=tf, softening=2.0, normalise=True)
+              if shape == "circle" else dl.RegPolyAperture(6, np.float32(0.42), tf, softening=2.0, normalise=True))
         return dl.AberratedAperture(ap, [4, 5, 6, 7, 8], coeffs, effect="opd")
 
     c64 = torch.tensor(c0, dtype=torch.float64, requires_grad=True)
