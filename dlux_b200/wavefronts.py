@@ -165,6 +165,10 @@ class Wavefront:
     def psf(self):                                     # wavefronts.py:279
         return self.phasor.real ** 2 + self.phasor.imag ** 2
 
+    def to_psf(self):                                  # wavefronts.py:281-292
+        from .psfs import PSF
+        return PSF(self.psf, self.pixel_scale)
+
     @property
     def wavenumber(self):                              # wavefronts.py:303
         return np.float32(2 * math.pi) / self.wavelength

@@ -175,6 +175,9 @@ def test_aperture_layers_on_a_cpu_wavefront():
         tt = ap.transmission(coords, ps)
         assert tt.shape == (32, 32) and float(tt.min()) >= 0 and float(tt.max()) <= 1 + 1e-6
     assert float(rect.transmission(coords, ps).sum()) < float(sq.transmission(coords, ps).sum())
+    p = out.to_psf()                                     # wavefronts.py:281-292
+    assert isinstance(p, dl.PSF) and float(p.pixel_scale) == float(out.pixel_scale)
+    np.testing.assert_allclose(p.data.numpy(), out.psf.numpy())
     with pytest.raises(TypeError):
         dl.CircularAperture(0.5, transformation="shift")
     with pytest.raises(ValueError):
