@@ -10,8 +10,8 @@ from .apertures import (AberratedAperture, CircularAperture, CompoundAperture, C
 from .psfs import PSF
 from .detectors import (AddConstant, ApplyJitter, ApplyPixelResponse, ApplySaturation, DetectorLayer,
                         Downsample, LayeredDetector, Telescope)
-from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, MFT, Normalise, Optic, OpticalLayer,
-                     Tilt, TransmissiveLayer)
+from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, Flip, Lambda, MFT, Normalise, Optic, OpticalLayer,
+                     Resize, Tilt, TransmissiveLayer, UnifiedLayer)
 from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, CartesianOpticalSystem,
                               LayeredOpticalSystem, OpticalSystem, ParametricLayeredOpticalSystem,
                               ParametricOpticalSystem)
@@ -28,4 +28,5 @@ __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "Aberrated
            "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "AberratedAperture", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "PSF", "DetectorLayer",
            "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",
-           "LayeredDetector", "Telescope", "GraphedValueAndGrad", "GraphedFitStep"]
+           "LayeredDetector", "Telescope", "GraphedValueAndGrad", "GraphedFitStep", "UnifiedLayer", "Resize", "Flip",
+           "Lambda"]

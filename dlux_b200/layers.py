@@ -11,7 +11,7 @@ from .utils import propagation as _prop
 from .wavefronts import CoordSpec, Wavefront
 
 __all__ = ["OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer", "Tilt", "Normalise",
-           "Optic", "BasisOptic", "MFT", "FFT"]
+           "Optic", "BasisOptic", "MFT", "FFT", "UnifiedLayer", "Resize", "Flip", "Lambda"]
 
 
 def _arr(x, device=None):
@@ -163,3 +163,40 @@ class FFT(OpticalLayer):
         size_out = wavefront.npixels * self.pad // self.crop
         return wavefront.propagate_FFT(pad=self.pad, focal_length=self.focal_length, inverse=self.inverse,
                                        spec_out=spec).resize(size_out)
+
+
+class UnifiedLayer(OpticalLayer):
+    """layers/unified_layers.py:14-22: layers that act on a ``Wavefront`` or a ``PSF`` alike."""
+
+
+class Resize(UnifiedLayer):
+    """unified_layers.py:25-66: centre-preserving crop / zero pad to ``npixels`` (even -> even, odd -> odd)."""
+
+    def __init__(self, npixels: int):
+        self.npixels = int(npixels)
+
+    def __call__(self, target):
+        return target.resize(self.npixels)
+
+
+class Flip(UnifiedLayer):
+    """unified_layers.py:136-186: flip about the given axes ('ij' convention: axis 0 = y, axis 1 = x)."""
+
+    def __init__(self, axes):
+        self.axes = axes
+        if isinstance(axes, tuple):
+            if not all(isinstance(a, int) for a in axes):
+                raise ValueError("All axes must be integers.")
+        elif not isinstance(axes, int):
+            raise ValueError("axes must be an int or tuple of ints.")
+
+    def __call__(self, target):
+        return target.flip(self.axes)
+
+
+class Lambda(UnifiedLayer):
+    """unified_layers.py:189-212: returns its input unchanged (placeholder in a layer list)."""
+
+    def __call__(self, target):
+        return target
+

@@ -52,6 +52,23 @@ class PSF:
         other = other if torch.is_tensor(other) else torch.as_tensor(np.asarray(other, np.float32))
         return self.set(data=convolve_same(self.data, other.to(self.data.device, self.data.dtype)))
 
+    def resize(self, npixels: int):                    # psfs.py:159-173 -> dlu.resize: centred crop / zero pad
+        n_in = self.npixels
+        if npixels == n_in:
+            return self
+        if n_in % 2 != npixels % 2:
+            raise ValueError("Center-preserving resizing requires parity consistency, i.e. even -> even "
+                             f"or odd -> odd: {n_in} -> {npixels}.")
+        if npixels < n_in:
+            a, b = (n_in - npixels) // 2, (n_in + npixels) // 2
+            return self.set(data=self.data[..., a:b, a:b])
+        p = (npixels - n_in) // 2
+        return self.set(data=torch.nn.functional.pad(self.data, (p, p, p, p)))
+
+    def flip(self, axis):                              # psfs.py:175-190 (np.flip on the given axes)
+        axes = (axis,) if isinstance(axis, int) else tuple(axis)
+        return self.set(data=torch.flip(self.data, list(axes)))
+
     def _op(self, other, fn):
         if other is None:
             return self

@@ -186,6 +186,35 @@ def test_convolve_same_matches_scipy():
         np.testing.assert_allclose(got, convolve(img, k, mode="same"), rtol=1e-10, atol=1e-12)
 
 
+def test_unified_layers_on_wavefront_and_psf():
+    # layers/unified_layers.py:25-66, 136-212; psfs.py:159-190; wavefronts.py:426-440, 568-582
+    import dlux_b200 as dl
+    rng = np.random.default_rng(3)
+    img = rng.random((6, 6)).astype(np.float32)
+    psf = dl.PSF(img, np.float32(0.1))
+    wf = dl.Wavefront(1e-6, 6, diameter=1.0, device="cpu") * torch.as_tensor(img)
+    for target, get in ((psf, lambda t: t.data.numpy()), (wf, lambda t: t.amplitude.numpy() * 36)):
+        np.testing.assert_allclose(get(dl.Resize(4)(target)), img[1:5, 1:5], rtol=1e-6)
+        padded = get(dl.Resize(10)(target))
+        assert padded.shape == (10, 10) and np.all(padded[:2] == 0)
+        np.testing.assert_allclose(padded[2:8, 2:8], img, rtol=1e-6)
+        np.testing.assert_allclose(get(dl.Flip(0)(target)), img[::-1], rtol=1e-6)
+        np.testing.assert_allclose(get(dl.Flip((0, 1))(target)), img[::-1, ::-1], rtol=1e-6)
+        assert dl.Lambda()(target) is target and dl.Resize(6)(target) is target
+        with pytest.raises(ValueError):
+            dl.Resize(5)(target)                       # even -> odd is not centre preserving
+    with pytest.raises(ValueError):
+        dl.Flip(0.5)
+    with pytest.raises(ValueError):
+        dl.Flip((0, "x"))
+    # in a layer list, in front of the propagator
+    layers = [("pad", dl.Resize(8)), ("noop", dl.Lambda())]
+    out = wf
+    for _, layer in layers:
+        out = layer(out)
+    assert out.npixels == 8 and isinstance(out, dl.Wavefront)
+
+
 def test_detector_layers_cpu():
     # layers/detector_layers.py:100-296, detectors.py:103-128, psfs.py:74-110 on CPU tensors
     import torch
