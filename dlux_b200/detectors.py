@@ -6,7 +6,6 @@ fused kernels return (differentiable, device-agnostic); it is kept out of the CU
 purpose -- at C3 it touches 1 MB per step against the GB-scale operand traffic of the MFT."""
 from __future__ import annotations
 
-import copy
 from collections import OrderedDict
 
 import numpy as np
