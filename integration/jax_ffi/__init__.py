@@ -15,12 +15,13 @@ try:
     import jax.numpy as jnp
     import numpy as np
 except ImportError as e:  # pragma: no cover
-    raise ImportError("dlux_b200.jax_ffi needs JAX (>= 0.4.31 for jax.ffi); it is not available "
+    raise ImportError("integration.jax_ffi needs JAX (>= 0.4.31 for jax.ffi); it is not available "
                       "in this environment") from e
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "..", "lib", "libdlux_b200_ffi.so")
-_core = ctypes.CDLL(os.path.join(_HERE, "..", "lib", "libdlux_b200.so"))
+_LIBDIR = os.path.join(_HERE, "..", "..", "dlux_b200", "lib")
+_LIB = os.path.join(_LIBDIR, "libdlux_b200_ffi.so")
+_core = ctypes.CDLL(os.path.join(_LIBDIR, "libdlux_b200.so"))
 _core.dlux_mft_scratch_bytes.restype = ctypes.c_size_t
 
 

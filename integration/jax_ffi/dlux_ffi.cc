@@ -3,7 +3,7 @@
 // file is untested there and is excluded from dlux_b200/build.py.  See INTEGRATION.md.
 //
 //   g++ -shared -fPIC -std=c++17 -I$(python -c "import jax; print(jax.ffi.include_dir())") \
-//       -I include dlux_b200/jax_ffi/dlux_ffi.cc -L dlux_b200/lib -ldlux_b200 -o libdlux_b200_ffi.so
+//       -I include integration/jax_ffi/dlux_ffi.cc -L dlux_b200/lib -ldlux_b200 -o libdlux_b200_ffi.so
 #if __has_include("xla/ffi/api/ffi.h")
 #include <cuda_runtime_api.h>
 #include "xla/ffi/api/ffi.h"
