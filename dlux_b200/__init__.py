@@ -11,7 +11,7 @@ from .psfs import PSF
 from .detectors import (AddConstant, ApplyJitter, ApplyPixelResponse, ApplySaturation, DetectorLayer,
                         Downsample, LayeredDetector, Telescope)
 from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, Flip, Lambda, MFT, Normalise, Optic, OpticalLayer,
-                     Resize, Tilt, TransmissiveLayer, UnifiedLayer)
+                     Resize, Rotate, Tilt, TransmissiveLayer, UnifiedLayer)
 from .optical_systems import (AngularOpticalSystem, BaseOpticalSystem, CartesianOpticalSystem,
                               LayeredOpticalSystem, OpticalSystem, ParametricLayeredOpticalSystem,
                               ParametricOpticalSystem)
@@ -28,5 +28,5 @@ __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "Aberrated
            "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "AberratedAperture", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "PSF", "DetectorLayer",
            "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",
-           "LayeredDetector", "Telescope", "GraphedValueAndGrad", "GraphedFitStep", "UnifiedLayer", "Resize", "Flip",
+           "LayeredDetector", "Telescope", "GraphedValueAndGrad", "GraphedFitStep", "UnifiedLayer", "Resize", "Rotate", "Flip",
            "Lambda"]

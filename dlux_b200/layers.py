@@ -11,7 +11,7 @@ from .utils import propagation as _prop
 from .wavefronts import CoordSpec, Wavefront
 
 __all__ = ["OpticalLayer", "TransmissiveLayer", "AberratedLayer", "BasisLayer", "Tilt", "Normalise",
-           "Optic", "BasisOptic", "MFT", "FFT", "UnifiedLayer", "Resize", "Flip", "Lambda"]
+           "Optic", "BasisOptic", "MFT", "FFT", "UnifiedLayer", "Resize", "Rotate", "Flip", "Lambda"]
 
 
 def _arr(x, device=None):
@@ -177,6 +177,22 @@ class Resize(UnifiedLayer):
 
     def __call__(self, target):
         return target.resize(self.npixels)
+
+
+class Rotate(UnifiedLayer):
+    """unified_layers.py:69-133: rotation by ``angle`` radians through interpolation; ``complex`` picks the (real,
+    imaginary) or the (amplitude, phase) fields of a wavefront and is ignored for a PSF."""
+
+    def __init__(self, angle, method: str = "linear", complex: bool = False):
+        self.angle = angle if torch.is_tensor(angle) else np.asarray(angle, dtype=np.float32)
+        self.method = str(method)
+        self.complex = bool(complex)
+
+    def __call__(self, target):
+        from .psfs import PSF
+        if isinstance(target, PSF):
+            return target.rotate(self.angle, self.method)
+        return target.rotate(self.angle, self.method, self.complex)
 
 
 class Flip(UnifiedLayer):

@@ -52,6 +52,19 @@ class PSF:
         other = other if torch.is_tensor(other) else torch.as_tensor(np.asarray(other, np.float32))
         return self.set(data=convolve_same(self.data, other.to(self.data.device, self.data.dtype)))
 
+    def rotate(self, angle, method: str = "linear"):   # psfs.py:112-128
+        from .utils import interpolation as _interp
+        return self.set(data=_interp.rotate(self.data, angle, method))
+
+    def interpolate(self, transformation, method: str = "linear", fill: float = 0.0):   # psfs.py:130-157
+        from .apertures import CoordTransform
+        from .utils import geometry as _G, interpolation as _interp
+        if not isinstance(transformation, CoordTransform):
+            raise TypeError("transformation must be a BaseCoordTransform.")
+        knots = _G.pixel_coords(self.npixels, self.npixels * self.pixel_scale.to(self.data.dtype),
+                                device=self.data.device, dtype=self.data.dtype)
+        return self.set(data=_interp.interp(self.data, knots, transformation(knots), method, fill))
+
     def resize(self, npixels: int):                    # psfs.py:159-173 -> dlu.resize: centred crop / zero pad
         n_in = self.npixels
         if npixels == n_in:

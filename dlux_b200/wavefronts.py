@@ -269,6 +269,36 @@ class Wavefront:
             np.asarray(pixel_scale, dtype=np.float32), device=phasor.device)
         return self.set(phasor=phasor, pixel_scale=ps, center=center)
 
+    # ------------------------------------------------------------------ interpolating operations (off the hot path)
+    def _resample(self, fn, complex: bool):
+        """Applies ``fn`` to the two real fields of a monochromatic wavefront -- (real, imaginary) or (amplitude,
+        phase) -- and reassembles the phasor (wavefronts.py:472-483, 511-524, 552-566)."""
+        if self.phasor.dim() != 2:
+            raise ValueError("dlux_b200: interpolating Wavefront operations act on a monochromatic (2-D) wavefront")
+        a, b = self.complex if complex else self.polar
+        a, b = fn(a), fn(b)
+        return torch.complex(a, b) if complex else torch.polar(a, b)
+
+    def scale_to(self, npixels: int, pixel_scale, complex: bool = True):        # wavefronts.py:442-483
+        from .utils import interpolation as _interp
+        ps = pixel_scale if torch.is_tensor(pixel_scale) else torch.as_tensor(
+            np.asarray(pixel_scale, dtype=np.float32), device=self.phasor.device)
+        ratio = ps / self.pixel_scale
+        return self.set(phasor=self._resample(lambda f: _interp.scale(f, int(npixels), ratio), complex), pixel_scale=ps)
+
+    def interpolate(self, transformation, method: str = "linear", complex: bool = True, fill: float = 0.0):
+        from .apertures import CoordTransform                                    # wavefronts.py:485-524
+        from .utils import interpolation as _interp
+        if not isinstance(transformation, CoordTransform):
+            raise TypeError("transformation must be a BaseCoordTransform.")
+        knots = self.coordinates()
+        samples = transformation(knots)
+        return self.set(phasor=self._resample(lambda f: _interp.interp(f, knots, samples, method, fill), complex))
+
+    def rotate(self, angle, method: str = "linear", complex: bool = True):       # wavefronts.py:526-566
+        from .utils import interpolation as _interp
+        return self.set(phasor=self._resample(lambda f: _interp.rotate(f, angle, method), complex))
+
     def resize(self, npixels: int):
         """wavefronts.py:562-582 -> dlu.resize: centre-preserving crop / zero pad."""
         n_in = self.npixels

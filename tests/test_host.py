@@ -215,6 +215,67 @@ def test_unified_layers_on_wavefront_and_psf():
     assert out.npixels == 8 and isinstance(out, dl.Wavefront)
 
 
+def test_interpolating_operations_against_scipy_bilinear():
+    """utils/interpolation.py:13-107, wavefronts.py:442-566, psfs.py:112-157, unified_layers.py:69-133.  The reference's
+    arithmetic lives in interpax (absent): the bilinear definition is pinned to SciPy's RegularGridInterpolator."""
+    from scipy.interpolate import RegularGridInterpolator
+    import dlux_b200 as dl
+    from dlux_b200.utils import geometry as G, interpolation as I
+    rng = np.random.default_rng(11)
+    n = 16
+    img = rng.standard_normal((n, n))
+
+    def scipy_at(image, knots, samples, fill=0.0):
+        xs, ys = knots[0][0].numpy(), knots[1][:, 0].numpy()
+        f = RegularGridInterpolator((ys, xs), image, method="linear", bounds_error=False, fill_value=fill)
+        return f(np.stack([samples[1].numpy().ravel(), samples[0].numpy().ravel()], 1)).reshape(samples[0].shape)
+
+    t = torch.as_tensor(img)
+    # rotate: unit-pixel centred grid, samples = rotated grid, zeros outside
+    knots = G.pixel_coords(n, float(n), dtype=torch.float64)
+    np.testing.assert_allclose(I.rotate(t, 0.4).numpy(), scipy_at(img, knots, G.rotate_coords(knots, 0.4)), atol=1e-13)
+    np.testing.assert_allclose(I.rotate(t, 0.0).numpy(), img, atol=1e-13)
+    np.testing.assert_allclose(I.rotate(t, np.pi / 2).numpy()[1:-1, 1:-1], np.rot90(img, 1)[1:-1, 1:-1], atol=1e-12)
+    # scale: npixels_out pixels, each `ratio` input pixels wide
+    k_in = G.pixel_coords(n, 1.0, dtype=torch.float64)
+    k_out = G.pixel_coords(24, 1.0, dtype=torch.float64) * (0.5 * 24 / n)
+    np.testing.assert_allclose(I.scale(t, 24, 0.5).numpy(), scipy_at(img, k_in, k_out), atol=1e-13)
+    np.testing.assert_allclose(I.scale(t, n, 1.0).numpy(), img, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        I.rotate(t, 0.1, method="cubic")
+    # Wavefront: both field decompositions, new pixel scale, layer form; differentiable in the angle
+    ph = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+    wf = dl.Wavefront.from_phasor(torch.as_tensor(ph), 1e-6, pixel_scale=np.float32(0.1))
+    r = wf.rotate(np.float32(0.3))
+    k32 = G.pixel_coords(n, float(n))
+    want = scipy_at(ph.real, k32.double(), G.rotate_coords(k32, 0.3).double()) + \
+        1j * scipy_at(ph.imag, k32.double(), G.rotate_coords(k32, 0.3).double())
+    np.testing.assert_allclose(r.phasor.numpy(), want, atol=2e-5)
+    rp = dl.Rotate(np.float32(0.3))(wf)                        # layer default: amplitude / phase fields
+    want_p = scipy_at(np.abs(ph), k32.double(), G.rotate_coords(k32, 0.3).double()) * np.exp(
+        1j * scipy_at(np.angle(ph), k32.double(), G.rotate_coords(k32, 0.3).double()))
+    np.testing.assert_allclose(rp.phasor.numpy(), want_p, atol=2e-5)
+    s = wf.scale_to(20, np.float32(0.05))
+    assert s.npixels == 20 and abs(float(s.pixel_scale) - 0.05) < 1e-8
+    np.testing.assert_allclose(s.phasor.real.numpy(), I.scale(torch.as_tensor(ph.real), 20, 0.5).numpy(), atol=1e-6)
+    tf = dl.CoordTransform(translation=np.array([0.12, -0.07], np.float32), rotation=np.float32(0.2))
+    wi = wf.interpolate(tf, fill=0.0)
+    kw = wf.coordinates()
+    np.testing.assert_allclose(wi.phasor.real.numpy(), scipy_at(ph.real, kw.double(), tf(kw).double()), atol=2e-5)
+    with pytest.raises(TypeError):
+        wf.interpolate("shift")
+    ang = torch.tensor(0.3, requires_grad=True)
+    wf.rotate(ang).phasor.real.sum().backward()
+    assert ang.grad is not None and torch.isfinite(ang.grad)
+    # PSF
+    psf = dl.PSF(np.abs(ph) ** 2, np.float32(0.1))
+    np.testing.assert_allclose(dl.Rotate(np.float32(0.3))(psf).data.numpy(),
+                               scipy_at(np.abs(ph) ** 2, k32.double(), G.rotate_coords(k32, 0.3).double()), atol=2e-5)
+    kp = G.pixel_coords(n, n * 0.1)
+    np.testing.assert_allclose(psf.interpolate(tf).data.numpy(),
+                               scipy_at(np.abs(ph) ** 2, kp.double(), tf(kp).double()), atol=2e-5)
+
+
 def test_detector_layers_cpu():
     # layers/detector_layers.py:100-296, detectors.py:103-128, psfs.py:74-110 on CPU tensors
     import torch
