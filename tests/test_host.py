@@ -276,6 +276,22 @@ def test_interpolating_operations_against_scipy_bilinear():
                                scipy_at(np.abs(ph) ** 2, kp.double(), tf(kp).double()), atol=2e-5)
 
 
+def test_bench_clock_sampler_window():
+    """bench.ClockSampler reports the samples of the timed window only (each sample carries its wall-clock time)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.source = "nvml"
+    s.rows = [(100.0 + 0.01 * i, 1965.0 if i < 50 else 1650.0, 1965.0, 300.0 + i, ["sw_power_cap"] if i >= 50 else [])
+              for i in range(100)]
+    early = s.stop(100.0, 100.2)
+    assert early["samples"] == 21 and early["sm_mhz"] == 1965.0 and early["reasons"] == []
+    late = s.stop(100.6, 101.0)
+    assert late["samples"] == 40 and late["sm_mhz"] == 1650.0 and late["reasons"] == ["sw_power_cap"]
+    assert s.stop(200.0, 201.0)["samples"] == 0 and s.stop()["samples"] == 100
+    assert bench.mft_flops(1024, 512) == 8 * 512 * 1024 * (1024 + 512)
+
+
 def test_detector_layers_cpu():
     # layers/detector_layers.py:100-296, detectors.py:103-128, psfs.py:74-110 on CPU tensors
     import torch
