@@ -8,7 +8,7 @@ from . import utils
 from .apertures import (AberratedAperture, CircularAperture, CompoundAperture, CoordTransform, MultiAperture,
                         RectangularAperture, RegPolyAperture, Spider, SquareAperture)
 from .psfs import PSF
-from .detectors import (AddConstant, ApplyJitter, ApplyPixelResponse, ApplySaturation, DetectorLayer,
+from .detectors import (AddConstant, ApplyInterpolation, ApplyJitter, ApplyPixelResponse, ApplySaturation, DetectorLayer,
                         Downsample, LayeredDetector, Telescope)
 from .layers import (AberratedLayer, BasisLayer, BasisOptic, FFT, Flip, Lambda, MFT, Normalise, Optic, OpticalLayer,
                      Resize, Rotate, Tilt, TransmissiveLayer, UnifiedLayer)
@@ -27,6 +27,6 @@ __all__ = ["utils", "Wavefront", "OpticalLayer", "TransmissiveLayer", "Aberrated
            "LayeredOpticalSystem", "ParametricLayeredOpticalSystem", "AngularOpticalSystem", "CartesianOpticalSystem", "PointSource",
            "PointSources", "BinarySource", "ResolvedSource", "PointResolvedSource", "Scene", "CoordTransform", "AberratedAperture", "CircularAperture", "SquareAperture", "RectangularAperture",
            "RegPolyAperture", "Spider", "CompoundAperture", "MultiAperture", "PSF", "DetectorLayer",
-           "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",
+           "ApplyInterpolation", "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant", "Downsample",
            "LayeredDetector", "Telescope", "GraphedValueAndGrad", "GraphedFitStep", "UnifiedLayer", "Resize", "Rotate", "Flip",
            "Lambda"]

@@ -15,7 +15,7 @@ from .psfs import PSF
 from .sources import Scene, _Source
 from .utils.array_ops import downsample
 
-__all__ = ["PSF", "DetectorLayer", "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant",
+__all__ = ["ApplyInterpolation", "PSF", "DetectorLayer", "ApplyPixelResponse", "ApplyJitter", "ApplySaturation", "AddConstant",
            "Downsample", "LayeredDetector", "Telescope", "gaussian_kernel"]
 
 
@@ -37,6 +37,22 @@ class DetectorLayer:
 
     def __call__(self, psf: PSF) -> PSF:  # pragma: no cover - abstract
         raise NotImplementedError
+
+
+class ApplyInterpolation(DetectorLayer):
+    """detector_layers.py:68-97: re-samples the PSF on transformed pixel coordinates (``PSF.interpolate``; bilinear
+    only, see utils/interpolation.py)."""
+
+    def __init__(self, transformation, method: str = "linear", fill: float = 0.0):
+        from .apertures import CoordTransform
+        if not isinstance(transformation, CoordTransform):
+            raise TypeError("transformation must be a BaseCoordTransform.")
+        self.transformation = transformation
+        self.method = str(method)
+        self.fill = float(fill)
+
+    def __call__(self, psf):
+        return psf.interpolate(self.transformation, method=self.method, fill=self.fill)
 
 
 class ApplyPixelResponse(DetectorLayer):

@@ -274,6 +274,10 @@ def test_interpolating_operations_against_scipy_bilinear():
     kp = G.pixel_coords(n, n * 0.1)
     np.testing.assert_allclose(psf.interpolate(tf).data.numpy(),
                                scipy_at(np.abs(ph) ** 2, kp.double(), tf(kp).double()), atol=2e-5)
+    np.testing.assert_allclose(dl.ApplyInterpolation(tf, fill=0.5)(psf).data.numpy(),       # detector_layers.py:68-97
+                               scipy_at(np.abs(ph) ** 2, kp.double(), tf(kp).double(), fill=0.5), atol=2e-5)
+    with pytest.raises(TypeError):
+        dl.ApplyInterpolation("shift")
 
 
 def test_bench_clock_sampler_window():
